@@ -1,0 +1,363 @@
+// C ABI of libddope_b200 (include/ddope_b200.h): scene objects, work buffers, kernel sequencing.
+// No torch, no host threads, one stream per call.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ddope_b200.h"
+#include "ddope_launch.h"
+
+using namespace ddope;
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg) {
+    g_err = msg;
+    return -1;
+}
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+struct ddope_scene {
+    // owned device copies of the mesh
+    float* pos = nullptr;
+    int* tri = nullptr;
+    int* opp = nullptr;
+    float* uv = nullptr;
+    float* tex = nullptr;
+    float* vcol = nullptr;
+    int* seg_bbox = nullptr;
+    int* total_tiles = nullptr;
+    SceneDev dev{};
+    bool have_camera = false;
+    // work buffers (grown on demand)
+    HypState* hyp = nullptr;
+    int hyp_cap = 0;
+    unsigned long long* zbuf = nullptr;
+    size_t zbuf_cap = 0;
+    float* partials = nullptr;
+    size_t partials_cap = 0;
+    float* lr_sched = nullptr;
+    int lr_cap = 0;
+    float* xfm_scratch = nullptr;
+    int num_sms = 148;
+    int64_t launches = 0;
+};
+
+extern "C" int ddope_abi_version(void) { return DDOPE_ABI_VERSION; }
+extern "C" const char* ddope_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t ddope_last_launch_count(const ddope_scene* s) { return s ? s->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// renderutils_plugin replacements
+
+static float* g_xfm_scratch = nullptr;
+static size_t g_xfm_scratch_cap = 0;
+
+extern "C" int ddope_xfm_fwd(const float* points, int Bp, int N, const float* matrix, int B, int is_points,
+                             float* out, void* stream) {
+    if (!points || !matrix || !out) return fail("ddope_xfm_fwd: null pointer");
+    if (B <= 0 || N < 0 || !(Bp == B || Bp == 1)) return fail("ddope_xfm_fwd: bad shape (Bp must be B or 1)");
+    if (N == 0) return 0;
+    launch_xfm_fwd(points, Bp, N, matrix, B, is_points, out, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ddope_xfm_bwd(const float* matrix, int B, int N, const float* grad, int is_points, float* d_points,
+                             void* stream) {
+    if (!matrix || !grad || !d_points) return fail("ddope_xfm_bwd: null pointer");
+    if (B <= 0 || N < 0) return fail("ddope_xfm_bwd: bad shape");
+    if (N == 0) return 0;
+    launch_xfm_bwd(matrix, B, N, grad, is_points, d_points, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ddope_xfm_bwd_mtx(const float* points, int Bp, int N, const float* grad, int B, int is_points,
+                                 float* d_matrix, void* stream) {
+    if (!points || !grad || !d_matrix) return fail("ddope_xfm_bwd_mtx: null pointer");
+    if (B <= 0 || N < 0 || !(Bp == B || Bp == 1)) return fail("ddope_xfm_bwd_mtx: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) {
+        CK(cudaMemsetAsync(d_matrix, 0, sizeof(float) * 16 * B, st));
+        return 0;
+    }
+    size_t need = (size_t)B * xfm_bwd_mtx_blocks(N) * 16 * sizeof(float);
+    if (need > g_xfm_scratch_cap) {
+        if (g_xfm_scratch) CK(cudaFree(g_xfm_scratch));
+        CK(cudaMalloc(&g_xfm_scratch, need));
+        g_xfm_scratch_cap = need;
+    }
+    launch_xfm_bwd_mtx(points, Bp, N, grad, B, is_points, d_matrix, g_xfm_scratch, st);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ddope_xfm_bwd_full(const float* points, int Bp, int N, const float* matrix, const float* grad, int B,
+                                  int is_points, float* d_points, float* d_matrix, void* stream) {
+    int r = ddope_xfm_bwd(matrix, B, N, grad, is_points, d_points, stream);
+    if (r) return r;
+    return ddope_xfm_bwd_mtx(points, Bp, N, grad, B, is_points, d_matrix, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene
+
+static void build_opposites(const int32_t* tri, int T, std::vector<int>& opp) {
+    // first two opposite vertices per undirected edge, in triangle order (oracle/nvdr.py build_edge_opposites)
+    std::unordered_map<uint64_t, std::pair<int, int>> slots;
+    slots.reserve((size_t)T * 3);
+    auto key = [](int a, int b) { return a < b ? ((uint64_t)(uint32_t)a << 32) | (uint32_t)b : ((uint64_t)(uint32_t)b << 32) | (uint32_t)a; };
+    for (int t = 0; t < T; t++)
+        for (int i = 0; i < 3; i++) {
+            int a = tri[3 * t + (i + 1) % 3], b = tri[3 * t + (i + 2) % 3], c = tri[3 * t + i];
+            auto it = slots.find(key(a, b));
+            if (it == slots.end()) slots.emplace(key(a, b), std::make_pair(c, -1));
+            else if (it->second.second < 0) it->second.second = c;
+        }
+    opp.assign((size_t)T * 3, -1);
+    for (int t = 0; t < T; t++)
+        for (int i = 0; i < 3; i++) {
+            int a = tri[3 * t + (i + 1) % 3], b = tri[3 * t + (i + 2) % 3], c = tri[3 * t + i];
+            auto& s = slots[key(a, b)];
+            opp[3 * t + i] = (s.first != c) ? s.first : s.second;
+        }
+}
+
+extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, const int32_t* tri, int T,
+                                  const float* uv, const float* tex, int tex_h, int tex_w, const float* vcol) {
+    if (!out || !pos || !tri) return fail("ddope_scene_create: null pointer");
+    if (V <= 0 || T <= 0) return fail("ddope_scene_create: empty mesh");
+    const bool textured = (uv != nullptr && tex != nullptr);
+    if (!textured && vcol == nullptr) return fail("ddope_scene_create: need (uv, tex) or vcol");
+    if (textured && (tex_h <= 0 || tex_w <= 0)) return fail("ddope_scene_create: bad texture size");
+    for (int i = 0; i < 3 * T; i++)
+        if (tri[i] < 0 || tri[i] >= V) return fail("ddope_scene_create: triangle index out of range");
+    if ((uint64_t)T >= 0xFFFFFFFFull) return fail("ddope_scene_create: too many triangles");
+
+    ddope_scene* s = new ddope_scene();
+    CK(cudaMalloc(&s->pos, sizeof(float) * 3 * V));
+    CK(cudaMemcpy(s->pos, pos, sizeof(float) * 3 * V, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&s->tri, sizeof(int) * 3 * T));
+    CK(cudaMemcpy(s->tri, tri, sizeof(int) * 3 * T, cudaMemcpyHostToDevice));
+    std::vector<int> opp;
+    build_opposites(tri, T, opp);
+    CK(cudaMalloc(&s->opp, sizeof(int) * 3 * T));
+    CK(cudaMemcpy(s->opp, opp.data(), sizeof(int) * 3 * T, cudaMemcpyHostToDevice));
+    if (textured) {
+        CK(cudaMalloc(&s->uv, sizeof(float) * 2 * V));
+        CK(cudaMemcpy(s->uv, uv, sizeof(float) * 2 * V, cudaMemcpyHostToDevice));
+        size_t nb = sizeof(float) * 3 * (size_t)tex_h * tex_w;
+        CK(cudaMalloc(&s->tex, nb));
+        CK(cudaMemcpy(s->tex, tex, nb, cudaMemcpyHostToDevice));
+    } else {
+        CK(cudaMalloc(&s->vcol, sizeof(float) * 3 * V));
+        CK(cudaMemcpy(s->vcol, vcol, sizeof(float) * 3 * V, cudaMemcpyHostToDevice));
+    }
+    CK(cudaMalloc(&s->seg_bbox, sizeof(int) * 4));
+    int init_bbox[4] = {1 << 30, 1 << 30, -1, -1};
+    CK(cudaMemcpy(s->seg_bbox, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&s->total_tiles, sizeof(int)));
+
+    SceneDev& d = s->dev;
+    d.pos = s->pos; d.tri = s->tri; d.opp = s->opp; d.uv = s->uv; d.tex = s->tex; d.vcol = s->vcol;
+    d.V = V; d.T = T; d.tex_h = textured ? tex_h : 0; d.tex_w = textured ? tex_w : 0;
+    d.seg_bbox = s->seg_bbox;
+    for (int k = 0; k < 3; k++) { d.bbmin[k] = 1e30f; d.bbmax[k] = -1e30f; }
+    for (int v = 0; v < V; v++)
+        for (int k = 0; k < 3; k++) {
+            float x = pos[3 * v + k];
+            if (x < d.bbmin[k]) d.bbmin[k] = x;
+            if (x > d.bbmax[k]) d.bbmax[k] = x;
+        }
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, dev_id);
+    *out = s;
+    return 0;
+}
+
+extern "C" int ddope_scene_destroy(ddope_scene* s) {
+    if (!s) return 0;
+    cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex); cudaFree(s->vcol);
+    cudaFree(s->seg_bbox); cudaFree(s->total_tiles); cudaFree(s->hyp); cudaFree(s->zbuf); cudaFree(s->partials);
+    cudaFree(s->lr_sched); cudaFree(s->xfm_scratch);
+    delete s;
+    return 0;
+}
+
+static void set_window(ddope_scene* s, int y0, int x0, int h, int w) {
+    SceneDev& d = s->dev;
+    d.wy0 = y0; d.wx0 = x0; d.wh = h; d.ww = w;
+    int zx0 = x0 - 1 < 0 ? 0 : x0 - 1, zy0 = y0 - 1 < 0 ? 0 : y0 - 1;
+    int zx1 = x0 + w + 1 > d.W ? d.W : x0 + w + 1, zy1 = y0 + h + 1 > d.H ? d.H : y0 + h + 1;
+    d.zx0 = zx0; d.zy0 = zy0; d.zw = zx1 - zx0; d.zh = zy1 - zy0;
+}
+
+extern "C" int ddope_scene_set_camera(ddope_scene* s, const float* proj16, int frame_h, int frame_w) {
+    if (!s || !proj16) return fail("ddope_scene_set_camera: null pointer");
+    if (frame_h <= 0 || frame_w <= 0 || frame_h > 16384 || frame_w > 16384) return fail("ddope_scene_set_camera: bad frame size");
+    memcpy(s->dev.proj, proj16, sizeof(float) * 16);
+    if (s->have_camera && (s->dev.H != frame_h || s->dev.W != frame_w)) {
+        s->dev.gt_rgb = s->dev.gt_depth = s->dev.gt_seg = nullptr;  // targets belong to the old frame size
+    }
+    s->dev.H = frame_h; s->dev.W = frame_w;
+    s->have_camera = true;
+    set_window(s, 0, 0, frame_h, frame_w);
+    return 0;
+}
+
+extern "C" int ddope_scene_set_window(ddope_scene* s, int y0, int x0, int h, int w) {
+    if (!s) return fail("ddope_scene_set_window: null scene");
+    if (!s->have_camera) return fail("ddope_scene_set_window: set the camera first");
+    if (y0 < 0 || x0 < 0 || h <= 0 || w <= 0 || y0 + h > s->dev.H || x0 + w > s->dev.W)
+        return fail("ddope_scene_set_window: window outside the frame");
+    set_window(s, y0, x0, h, w);
+    return 0;
+}
+
+extern "C" int ddope_scene_set_target(ddope_scene* s, const float* rgb, const float* depth, const float* seg,
+                                      int seg_c, void* stream) {
+    if (!s) return fail("ddope_scene_set_target: null scene");
+    if (!s->have_camera) return fail("ddope_scene_set_target: set the camera first");
+    if (seg && !(seg_c == 1 || seg_c == 3)) return fail("ddope_scene_set_target: seg_c must be 1 or 3");
+    SceneDev& d = s->dev;
+    d.gt_rgb = rgb; d.gt_depth = depth; d.gt_seg = seg;
+    d.seg_pix_stride = seg ? seg_c : 0;
+    d.seg_ch_stride = (seg && seg_c == 3) ? 1 : 0;
+    if (seg) {
+        launch_seg_bbox(seg, d.H, d.W, seg_c, s->seg_bbox, (cudaStream_t)stream);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hot path
+
+static int ensure_buffers(ddope_scene* s, int B, bool need_partials) {
+    const SceneDev& d = s->dev;
+    if (B > s->hyp_cap) {
+        if (s->hyp) CK(cudaFree(s->hyp));
+        CK(cudaMalloc(&s->hyp, sizeof(HypState) * (size_t)B));
+        s->hyp_cap = B;
+    }
+    size_t zneed = (size_t)B * d.zh * d.zw;
+    if (zneed > s->zbuf_cap) {
+        if (s->zbuf) CK(cudaFree(s->zbuf));
+        CK(cudaMalloc(&s->zbuf, sizeof(unsigned long long) * zneed));
+        s->zbuf_cap = zneed;
+    }
+    if (need_partials) {
+        size_t tiles = (size_t)((d.ww + TILE_W - 1) / TILE_W) * ((d.wh + TILE_H - 1) / TILE_H);
+        size_t pneed = (size_t)B * tiles * NACC;
+        if (pneed > s->partials_cap) {
+            if (s->partials) CK(cudaFree(s->partials));
+            CK(cudaMalloc(&s->partials, sizeof(float) * pneed));
+            s->partials_cap = pneed;
+        }
+    }
+    return 0;
+}
+
+static int max_tiles(const ddope_scene* s, int B) {
+    const SceneDev& d = s->dev;
+    long long t = (long long)((d.ww + TILE_W - 1) / TILE_W) * ((d.wh + TILE_H - 1) / TILE_H) * B;
+    return t > 0x7fffffffLL ? 0x7fffffff : (int)t;
+}
+
+static LossCfgDev to_dev(const ddope_loss_cfg* c) {
+    LossCfgDev o;
+    o.use_rgb = c->use_rgb != 0; o.use_depth = c->use_depth != 0; o.use_mask = c->use_mask != 0;
+    o.w_rgb = c->weight_rgb; o.w_depth = c->weight_depth; o.w_mask = c->weight_mask;
+    return o;
+}
+
+static int check_loss_inputs(const ddope_scene* s, const ddope_loss_cfg* cfg, const char* who) {
+    const SceneDev& d = s->dev;
+    if (!s->have_camera) return fail(std::string(who) + ": set the camera first");
+    if (!cfg) return fail(std::string(who) + ": null loss config");
+    if (!(cfg->use_rgb || cfg->use_depth || cfg->use_mask)) return fail(std::string(who) + ": no loss enabled");
+    if (!d.gt_seg) return fail(std::string(who) + ": every reference loss needs the segmentation target");
+    if (cfg->use_rgb && !d.gt_rgb) return fail(std::string(who) + ": rgb loss needs the rgb target");
+    if (cfg->use_depth && !d.gt_depth) return fail(std::string(who) + ": depth loss needs the depth target");
+    return 0;
+}
+
+extern "C" int ddope_render(ddope_scene* s, const float* quat, const float* trans, int B, float* rgb, float* depth,
+                            float* mask, float* rast, float* mtx, void* stream) {
+    if (!s || !quat || !trans) return fail("ddope_render: null pointer");
+    if (B <= 0 || B > 65535) return fail("ddope_render: B must be in [1, 65535]");
+    if (!s->have_camera) return fail("ddope_render: set the camera first");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = ensure_buffers(s, B, false)) return r;
+    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f};
+    s->launches = 0;
+    launch_pose(s->dev, quat, trans, nullptr, B, B, cfg, 0, s->hyp, s->total_tiles, st);
+    launch_clear(s->dev, s->hyp, B, s->zbuf, st);
+    launch_raster(s->dev, s->hyp, B, s->zbuf, st);
+    RenderOut out = {rgb, depth, mask, rast};
+    launch_pixel_render(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), s->zbuf, out, s->num_sms, st);
+    s->launches = 4;
+    if (mtx) {
+        launch_copy_mtx(s->hyp, B, mtx, st);
+        s->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static void enqueue_iteration(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
+                              LossCfgDev cfg, int it, int do_update, float* loss_table, float* grad,
+                              float* pose_hist, float* loss_hist, cudaStream_t st) {
+    launch_pose(s->dev, quat, trans, lr_mult, B, B_global, cfg, 1, s->hyp, s->total_tiles, st);
+    launch_clear(s->dev, s->hyp, B, s->zbuf, st);
+    launch_raster(s->dev, s->hyp, B, s->zbuf, st);
+    launch_pixel_loss(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), cfg, s->zbuf, s->partials, s->num_sms, st);
+    launch_step(s->dev, s->hyp, s->partials, B, cfg, quat, trans, s->lr_sched, it, do_update, loss_table, grad,
+                pose_hist, loss_hist, st);
+    s->launches += 5;
+}
+
+extern "C" int ddope_loss_grad(ddope_scene* s, const float* quat, const float* trans, const float* lr_mult, int B,
+                               int B_global, const ddope_loss_cfg* cfg, float* loss_table, float* grad,
+                               void* stream) {
+    if (!s || !quat || !trans) return fail("ddope_loss_grad: null pointer");
+    if (B <= 0 || B > 65535 || B_global < B) return fail("ddope_loss_grad: need 1 <= B <= 65535 and B_global >= B");
+    if (int r = check_loss_inputs(s, cfg, "ddope_loss_grad")) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = ensure_buffers(s, B, true)) return r;
+    s->launches = 0;
+    enqueue_iteration(s, const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B, B_global, to_dev(cfg), 0, 0,
+                      loss_table, grad, nullptr, nullptr, st);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
+                              const float* lr_sched, int n_iters, const ddope_loss_cfg* cfg, float* pose_hist,
+                              float* loss_hist, void* stream) {
+    if (!s || !quat || !trans || !lr_sched) return fail("ddope_optimize: null pointer");
+    if (B <= 0 || B > 65535 || B_global < B) return fail("ddope_optimize: need 1 <= B <= 65535 and B_global >= B");
+    if (n_iters <= 0) return fail("ddope_optimize: n_iters must be positive");
+    if (int r = check_loss_inputs(s, cfg, "ddope_optimize")) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = ensure_buffers(s, B, true)) return r;
+    if (n_iters > s->lr_cap) {
+        if (s->lr_sched) CK(cudaFree(s->lr_sched));
+        CK(cudaMalloc(&s->lr_sched, sizeof(float) * n_iters));
+        s->lr_cap = n_iters;
+    }
+    CK(cudaMemcpyAsync(s->lr_sched, lr_sched, sizeof(float) * n_iters, cudaMemcpyHostToDevice, st));
+    LossCfgDev c = to_dev(cfg);
+    s->launches = 0;
+    for (int it = 0; it < n_iters; it++)
+        enqueue_iteration(s, quat, trans, lr_mult, B, B_global, c, it, 1, nullptr, nullptr, pose_hist, loss_hist, st);
+    CK(cudaGetLastError());
+    return 0;
+}

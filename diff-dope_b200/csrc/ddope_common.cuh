@@ -1,0 +1,79 @@
+// Shared device-side definitions of libddope_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ddope {
+
+constexpr int TILE_W = 32;
+constexpr int TILE_H = 8;
+constexpr int TILE_THREADS = TILE_W * TILE_H;
+constexpr int NACC = 20;  // 12 dMVP(rows x,y,w) + 4 dM(row z) + 3 loss sums + 1 pad
+constexpr unsigned long long EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
+constexpr int SUBPIX = 256;
+constexpr float COORD_LIMIT = 1048576.f;  // 2^20 px
+
+// ---------------------------------------------------------------------------------------------
+// Separately-rounded IEEE float32 ops. Everything that feeds a discrete decision (snapping,
+// coverage, depth test, barycentrics, antialias analysis) goes through these so the compiler
+// cannot contract a*b+c into an FMA and the results equal the oracle's numpy float32 bit for bit.
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// Everything a kernel needs to know about the mesh, camera, target and window. By value.
+struct SceneDev {
+    const float* pos;    // [V,3]
+    const int* tri;      // [T,3]
+    const int* opp;      // [T,3] opposite vertex across edge i, or -1
+    const float* uv;     // [V,2] or null
+    const float* tex;    // [tex_h,tex_w,3] or null
+    const float* vcol;   // [V,3] or null
+    const float* gt_rgb;    // [H,W,3] or null
+    const float* gt_depth;  // [H,W] or null
+    const float* gt_seg;    // [H,W,seg_c] or null
+    const int* seg_bbox;    // device int[4]: xmin,ymin,xmax,ymax of seg != 0 (inclusive); xmin > xmax if none
+    int V, T, tex_h, tex_w;
+    int seg_pix_stride, seg_ch_stride;
+    int H, W;                // frame
+    int wy0, wx0, wh, ww;    // loss window
+    int zy0, zx0, zh, zw;    // z-buffer region: window grown by 1 px, clipped to the frame
+    float proj[16];
+    float bbmin[3], bbmax[3];  // object-space AABB
+};
+
+// Per-hypothesis state for one iteration.
+struct __align__(16) HypState {
+    float mvp[16];
+    float m[16];
+    float qhat[4];
+    float qnorm;
+    float k_rgb, k_depth, k_mask;  // d loss / d pixel value scale: w_k * lr_b / (B_global * P * C)
+    int rx0, ry0, rx1, ry1;        // loss ROI in frame pixels, [rx0,rx1) x [ry0,ry1)
+    int tiles_x, tiles_y, tile_base, pad0;
+};
+
+struct LossCfgDev {
+    int use_rgb, use_depth, use_mask;
+    float w_rgb, w_depth, w_mask;
+};
+
+__device__ __forceinline__ void xfm_exact(const float* __restrict__ m, float x, float y, float z, float* c) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        c[r] = xadd(xadd(xadd(xmul(m[4 * r + 0], x), xmul(m[4 * r + 1], y)), xmul(m[4 * r + 2], z)), m[4 * r + 3]);
+}
+
+__device__ __forceinline__ unsigned int float_orderable(float f) {
+    unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float orderable_float(unsigned int k) {
+    unsigned int b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(b);
+}
+
+__device__ __forceinline__ bool same_sign(float a, float b) { return ((__float_as_int(a) ^ __float_as_int(b)) >= 0); }
+
+}  // namespace ddope

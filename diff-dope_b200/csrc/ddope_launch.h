@@ -1,0 +1,43 @@
+// Host-side launchers of the kernels of libddope_b200 (one per .cu file).
+#pragma once
+#include "ddope_common.cuh"
+
+namespace ddope {
+
+// pose.cu
+// quat/trans -> HypState (M, MVP, loss ROI, tile prefix). roi_mode: 0 = window (render), 1 = tight (loss).
+void launch_pose(const SceneDev& S, const float* quat, const float* trans, const float* lr_mult, int B,
+                 int B_global, LossCfgDev cfg, int roi_mode, HypState* hyp, int* total_tiles, cudaStream_t st);
+// Reduce tile partials per hypothesis, chain to d(quat,trans), optionally apply the SGD step.
+void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg,
+                 float* quat, float* trans, const float* lr_sched, int it, int do_update, float* loss_table,
+                 float* grad_out, float* pose_hist, float* loss_hist, cudaStream_t st);
+void launch_seg_bbox(const float* seg, int H, int W, int seg_c, int* bbox4, cudaStream_t st);
+void launch_copy_mtx(const HypState* hyp, int B, float* mtx, cudaStream_t st);
+
+// raster.cu
+void launch_clear(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, cudaStream_t st);
+void launch_raster(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, cudaStream_t st);
+
+// pixel.cu
+struct RenderOut {
+    float* rgb;    // [B,wh,ww,3]
+    float* depth;  // [B,wh,ww]
+    float* mask;   // [B,wh,ww]
+    float* rast;   // [B,wh,ww,4]
+};
+void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
+                       LossCfgDev cfg, const unsigned long long* zbuf, float* partials, int num_sms, cudaStream_t st);
+void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
+                         const unsigned long long* zbuf, RenderOut out, int num_sms, cudaStream_t st);
+
+// xfm.cu
+void launch_xfm_fwd(const float* points, int Bp, int N, const float* matrix, int B, int is_points, float* out,
+                    cudaStream_t st);
+void launch_xfm_bwd(const float* matrix, int B, int N, const float* grad, int is_points, float* d_points,
+                    cudaStream_t st);
+void launch_xfm_bwd_mtx(const float* points, int Bp, int N, const float* grad, int B, int is_points,
+                        float* d_matrix, float* scratch, cudaStream_t st);
+int xfm_bwd_mtx_blocks(int N);
+
+}  // namespace ddope

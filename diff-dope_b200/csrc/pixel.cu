@@ -1,0 +1,505 @@
+// The pixel pass: per loss-ROI tile, in one kernel, everything the reference does between
+// dr.rasterize and optimizer.step at pixel granularity (diffdope/diffdope.py:203-231,547-613 and the
+// autograd reverse of it): barycentrics, depth, uv + bilinear texture (or vertex colour), coverage
+// mask + silhouette antialias, the three masked L1 losses, and their analytic backward accumulated
+// straight into dL/dMVP (rows x,y,w) and dL/dM (row z) -- no [B,H,W,*] intermediate and no [B,V,4]
+// vertex-gradient buffer ever exists. A persistent grid walks (hypothesis, tile) work items.
+#include "ddope_launch.h"
+
+namespace ddope {
+
+constexpr int IDS_W = TILE_W + 4, IDS_H = TILE_H + 4;  // triangle ids: tile + 2 px halo
+constexpr int MAA_W = TILE_W + 2, MAA_H = TILE_H + 2;  // antialiased mask: tile + 1 px halo
+constexpr int ID_NONE = -1;                             // inside the frame, not covered
+constexpr int ID_OUTSIDE = -2;                          // outside the frame: no pixel, no pair
+
+struct Shade {
+    float u, v, zw;
+    float c0[4], c1[4], c2[4];  // clip verts
+    float p0x, p0y, p1x, p1y, p2x, p2y, a0, a1, a2, fx, fy;
+    int i0, i1, i2;
+};
+
+// Barycentrics of pixel (px,py) w.r.t. triangle tri: nvdiffrast's fragment formula, exact ops.
+__device__ __forceinline__ void shade_setup(const SceneDev& S, const float* mvp, int tri, int px, int py, Shade& s) {
+    s.i0 = S.tri[3 * tri]; s.i1 = S.tri[3 * tri + 1]; s.i2 = S.tri[3 * tri + 2];
+    xfm_exact(mvp, S.pos[3 * s.i0], S.pos[3 * s.i0 + 1], S.pos[3 * s.i0 + 2], s.c0);
+    xfm_exact(mvp, S.pos[3 * s.i1], S.pos[3 * s.i1 + 1], S.pos[3 * s.i1 + 2], s.c1);
+    xfm_exact(mvp, S.pos[3 * s.i2], S.pos[3 * s.i2 + 1], S.pos[3 * s.i2 + 2], s.c2);
+    const float xs = xdiv(2.f, (float)S.W), xo = xsub(xdiv(1.f, (float)S.W), 1.f);
+    const float ys = xdiv(2.f, (float)S.H), yo = xsub(xdiv(1.f, (float)S.H), 1.f);
+    s.fx = xadd(xmul(xs, (float)px), xo);
+    s.fy = xadd(xmul(ys, (float)py), yo);
+    s.p0x = xsub(s.c0[0], xmul(s.fx, s.c0[3])); s.p0y = xsub(s.c0[1], xmul(s.fy, s.c0[3]));
+    s.p1x = xsub(s.c1[0], xmul(s.fx, s.c1[3])); s.p1y = xsub(s.c1[1], xmul(s.fy, s.c1[3]));
+    s.p2x = xsub(s.c2[0], xmul(s.fx, s.c2[3])); s.p2y = xsub(s.c2[1], xmul(s.fy, s.c2[3]));
+    s.a0 = xsub(xmul(s.p1x, s.p2y), xmul(s.p1y, s.p2x));
+    s.a1 = xsub(xmul(s.p2x, s.p0y), xmul(s.p2y, s.p0x));
+    s.a2 = xsub(xmul(s.p0x, s.p1y), xmul(s.p0y, s.p1x));
+    const float iw = xdiv(1.f, xadd(xadd(s.a0, s.a1), s.a2));
+    s.u = __saturatef(xmul(s.a0, iw));
+    s.v = __saturatef(xmul(s.a1, iw));
+    const float z = xadd(xadd(xmul(s.c0[2], s.a0), xmul(s.c1[2], s.a1)), xmul(s.c2[2], s.a2));
+    const float w = xadd(xadd(xmul(s.c0[3], s.a0), xmul(s.c1[3], s.a1)), xmul(s.c2[3], s.a2));
+    s.zw = xdiv(z, w);
+}
+
+// d(u,v) -> d clip (x,y,w) of the three vertices -> accumulate dL/dMVP rows x,y,w
+// (nvdiffrast RasterizeGradKernel followed by xfm_bwd_mtx, diffdope/c_src/mesh.cu:165-214).
+__device__ __forceinline__ void raster_grad_accum(const SceneDev& S, const Shade& s, float gu, float gv, float* acc) {
+    const float at = (s.a0 + s.a1) + s.a2;
+    const float iw = 1.f / (at + copysignf(1e-6f, at));
+    const float b0 = s.a0 * iw, b1 = s.a1 * iw;
+    const float gb0 = gu * iw, gb1 = gv * iw;
+    const float gbb = gb0 * b0 + gb1 * b1;
+    float gx[3], gy[3], gw[3];
+    gx[0] = gbb * (s.p2y - s.p1y) - gb1 * s.p2y;
+    gx[1] = gbb * (s.p0y - s.p2y) + gb0 * s.p2y;
+    gx[2] = gbb * (s.p1y - s.p0y) - gb0 * s.p1y + gb1 * s.p0y;
+    gy[0] = gbb * (s.p1x - s.p2x) + gb1 * s.p2x;
+    gy[1] = gbb * (s.p2x - s.p0x) - gb0 * s.p2x;
+    gy[2] = gbb * (s.p0x - s.p1x) + gb0 * s.p1x - gb1 * s.p0x;
+    const int vi[3] = {s.i0, s.i1, s.i2};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        gw[k] = -s.fx * gx[k] - s.fy * gy[k];
+        const float x = S.pos[3 * vi[k]], y = S.pos[3 * vi[k] + 1], z = S.pos[3 * vi[k] + 2];
+        acc[0] += gx[k] * x; acc[1] += gx[k] * y; acc[2] += gx[k] * z; acc[3] += gx[k];
+        acc[4] += gy[k] * x; acc[5] += gy[k] * y; acc[6] += gy[k] * z; acc[7] += gy[k];
+        acc[8] += gw[k] * x; acc[9] += gw[k] * y; acc[10] += gw[k] * z; acc[11] += gw[k];
+    }
+}
+
+struct AARes {
+    bool valid;
+    float alpha;
+    int di;
+};
+
+// nvdiffrast AntialiasFwdAnalysisKernel for one pixel pair; `tri` is the closer (here: the only
+// covered) triangle, (qx,qy) its pixel, d = 0 horizontal pair / 1 vertical pair, ds = +1 if that
+// pixel is the pair's first (left / lower) pixel else -1. Exact ops, same order as oracle/nvdr.py.
+__device__ AARes aa_analyse(const SceneDev& S, const float* mvp, int tri, int qx, int qy, int d, float ds) {
+    AARes r;
+    r.valid = false; r.alpha = 0.f; r.di = 0;
+    int vi[3] = {S.tri[3 * tri], S.tri[3 * tri + 1], S.tri[3 * tri + 2]};
+    float x[3], y[3], ox[3], oy[3];
+    const float xh = xmul((float)S.W, 0.5f), yh = xmul((float)S.H, 0.5f);
+    const float fx = xsub(xadd((float)qx, 0.5f), xh), fy = xsub(xadd((float)qy, 0.5f), yh);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float c[4];
+        xfm_exact(mvp, S.pos[3 * vi[k]], S.pos[3 * vi[k] + 1], S.pos[3 * vi[k] + 2], c);
+        float w = xdiv(1.f, c[3]);
+        x[k] = xsub(xmul(xmul(c[0], w), xh), fx);
+        y[k] = xsub(xmul(xmul(c[1], w), yh), fy);
+        int o = S.opp[3 * tri + k];
+        if (o < 0) {
+            ox[k] = x[k]; oy[k] = y[k];
+        } else {
+            xfm_exact(mvp, S.pos[3 * o], S.pos[3 * o + 1], S.pos[3 * o + 2], c);
+            w = xdiv(1.f, c[3]);
+            ox[k] = xsub(xmul(xmul(c[0], w), xh), fx);
+            oy[k] = xsub(xmul(xmul(c[1], w), yh), fy);
+        }
+    }
+    float x0 = x[0], x1 = x[1], x2 = x[2], y0 = y[0], y1 = y[1], y2 = y[2];
+    const float bb = xsub(xmul(xsub(x1, x0), xsub(y2, y0)), xmul(xsub(x2, x0), xsub(y1, y0)));
+    const float a0 = xsub(xmul(xsub(x1, ox[0]), xsub(y2, oy[0])), xmul(xsub(x2, ox[0]), xsub(y1, oy[0])));
+    const float a1 = xsub(xmul(xsub(x2, ox[1]), xsub(y0, oy[1])), xmul(xsub(x0, ox[1]), xsub(y2, oy[1])));
+    const float a2 = xsub(xmul(xsub(x0, ox[2]), xsub(y1, oy[2])), xmul(xsub(x1, ox[2]), xsub(y0, oy[2])));
+    const bool s0 = same_sign(a0, bb), s1 = same_sign(a1, bb), s2 = same_sign(a2, bb);
+    if (!(s0 || s1 || s2)) return r;
+    if (d) {
+        float t;
+        t = x0; x0 = y0; y0 = t;
+        t = x1; x1 = y1; y1 = t;
+        t = x2; x2 = y2; y2 = t;
+    }
+    const float dx0 = xsub(x2, x1), dx1 = xsub(x0, x2), dx2 = xsub(x1, x0);
+    const float dy0 = xsub(y2, y1), dy1 = xsub(y0, y2), dy2 = xsub(y1, y0);
+    const float d0 = xmul(ds, xsub(xmul(x1, dy0), xmul(y1, dx0)));
+    const float d1 = xmul(ds, xsub(xmul(x2, dy1), xmul(y2, dx1)));
+    const float d2 = xmul(ds, xsub(xmul(x0, dy2), xmul(y0, dx2)));
+    const bool k0 = same_sign(y1, y2), k1 = same_sign(y2, y0), k2 = same_sign(y0, y1);
+    const float NEG = -3.402823466e+38f;
+    const float r0 = k0 ? NEG : xdiv(d0, dy0);
+    const float r1 = k1 ? NEG : xdiv(d1, dy1);
+    const float r2 = k2 ? NEG : xdiv(d2, dy2);
+    const bool g10 = r1 > r0, g20 = r2 > r0, g21 = r2 > r1;
+    const int di = (g20 && g21) ? 2 : (g10 ? 1 : 0);
+    float dc = NEG;
+    if (di == 0 && s0 && (k0 ? 1.f : fabsf(dy0)) >= fabsf(dx0)) dc = r0;
+    if (di == 1 && s1 && (k1 ? 1.f : fabsf(dy1)) >= fabsf(dx1)) dc = r1;
+    if (di == 2 && s2 && (k2 ? 1.f : fabsf(dy2)) >= fabsf(dx2)) dc = r2;
+    const float eps = 0.0625f;
+    if (dc > -eps && dc < 1.f + eps) {
+        dc = fminf(fmaxf(dc, 0.f), 1.f);
+        r.valid = true;
+        r.alpha = xmul(ds, xsub(0.5f, dc));
+        r.di = di;
+    }
+    return r;
+}
+
+// nvdiffrast AntialiasGradKernel, position part: gradient of the crossing point w.r.t. the active
+// edge's two vertices, pushed into dL/dMVP. dd = sum_c dL/dout_c[target] * (color1_c - color0_c).
+__device__ void aa_grad_accum(const SceneDev& S, const float* mvp, int tri, int qx, int qy, int d, int di, float alpha,
+                              float dd, float* acc) {
+    if (dd == 0.f || fabsf(alpha) >= 0.5f) return;
+    const int i1 = (di < 2) ? di + 1 : 0;
+    const int i2 = (i1 < 2) ? i1 + 1 : 0;
+    const int v1 = S.tri[3 * tri + i1], v2 = S.tri[3 * tri + i2];
+    float p1[4], p2[4];
+    const float q1[3] = {S.pos[3 * v1], S.pos[3 * v1 + 1], S.pos[3 * v1 + 2]};
+    const float q2[3] = {S.pos[3 * v2], S.pos[3 * v2 + 1], S.pos[3 * v2 + 2]};
+    xfm_exact(mvp, q1[0], q1[1], q1[2], p1);
+    xfm_exact(mvp, q2[0], q2[1], q2[2], p2);
+    float pxh = (float)S.W * 0.5f, pyh = (float)S.H * 0.5f;
+    float fx = ((float)qx + 0.5f) - pxh, fy = ((float)qy + 0.5f) - pyh;
+    if (d) {
+        float t;
+        t = p1[0]; p1[0] = p1[1]; p1[1] = t;
+        t = p2[0]; p2[0] = p2[1]; p2[1] = t;
+        t = pxh; pxh = pyh; pyh = t;
+        t = fx; fx = fy; fy = t;
+    }
+    const float w1 = 1.f / p1[3], w2 = 1.f / p2[3];
+    const float x1 = p1[0] * w1 * pxh - fx, y1 = p1[1] * w1 * pyh - fy;
+    const float x2 = p2[0] * w2 * pxh - fx, y2 = p2[1] * w2 * pyh - fy;
+    const float dx = x2 - x1, dy = y2 - y1;
+    const float db = x1 * dy - y1 * dx;
+    const float iy = 1.f / (dy + copysignf(1e-3f, dy));
+    const float dby = db * iy;
+    const float iw1 = -w1 * iy * dd, iw2 = w2 * iy * dd;
+    float g1x = iw1 * pxh * y2, g2x = iw2 * pxh * y1;
+    float g1y = iw1 * pyh * (dby - x2), g2y = iw2 * pyh * (dby - x1);
+    const float g1w = -(p1[0] * g1x + p1[1] * g1y) * w1;
+    const float g2w = -(p2[0] * g2x + p2[1] * g2y) * w2;
+    if (d) {
+        float t;
+        t = g1x; g1x = g1y; g1y = t;
+        t = g2x; g2x = g2y; g2y = t;
+    }
+    acc[0] += g1x * q1[0] + g2x * q2[0]; acc[1] += g1x * q1[1] + g2x * q2[1]; acc[2] += g1x * q1[2] + g2x * q2[2]; acc[3] += g1x + g2x;
+    acc[4] += g1y * q1[0] + g2y * q2[0]; acc[5] += g1y * q1[1] + g2y * q2[1]; acc[6] += g1y * q1[2] + g2y * q2[2]; acc[7] += g1y + g2y;
+    acc[8] += g1w * q1[0] + g2w * q2[0]; acc[9] += g1w * q1[1] + g2w * q2[1]; acc[10] += g1w * q1[2] + g2w * q2[2]; acc[11] += g1w + g2w;
+}
+
+struct PairInfo {
+    bool exists;  // both pixels in the frame and exactly one of them covered
+    int tri, qx, qy;
+    float ds, dcol;  // dcol = coverage(second pixel) - coverage(first pixel)
+};
+
+// pair between (x,y) and its neighbour in direction d on side `side` (0: neighbour is x-1 / y-1, the
+// pair's first pixel; 1: neighbour is x+1 / y+1, the pair's second pixel)
+__device__ __forceinline__ PairInfo make_pair(int id_self, int id_nb, int x, int y, int d, int side) {
+    PairInfo p;
+    p.exists = false;
+    if (id_nb == ID_OUTSIDE || id_self == ID_OUTSIDE) return p;
+    const bool cs = id_self >= 0, cn = id_nb >= 0;
+    if (cs == cn) return p;  // equal coverage: the blend adds alpha * (1-1) or alpha * (0-0) = 0
+    p.exists = true;
+    const int nx = x + (d ? 0 : (side ? 1 : -1)), ny = y + (d ? (side ? 1 : -1) : 0);
+    const bool self_first = (side == 1);  // self is the pair's first (left/lower) pixel when the neighbour is +1
+    p.tri = cs ? id_self : id_nb;
+    p.qx = cs ? x : nx;
+    p.qy = cs ? y : ny;
+    const bool covered_is_first = (cs == self_first);
+    p.ds = covered_is_first ? 1.f : -1.f;
+    p.dcol = covered_is_first ? -1.f : 1.f;  // second - first
+    return p;
+}
+
+// contribution of a pair to the antialiased mask of pixel `self`; is_first: self is the pair's first pixel
+__device__ __forceinline__ float pair_contrib(const SceneDev& S, const float* mvp, const PairInfo& p, int d, bool self_first) {
+    if (!p.exists) return 0.f;
+    AARes r = aa_analyse(S, mvp, p.tri, p.qx, p.qy, d, p.ds);
+    if (!r.valid) return 0.f;
+    const bool target_first = r.alpha > 0.f;
+    if (target_first != self_first) return 0.f;
+    return xmul(r.alpha, p.dcol);
+}
+
+__device__ __forceinline__ float mask_aa_pixel(const SceneDev& S, const float* mvp, const int* ids, int lx, int ly, int x, int y) {
+    // ids indexed with the 2 px halo: local (lx,ly) in [-2, TILE+2)
+    const int idc = ids[(ly + 2) * IDS_W + (lx + 2)];
+    const int idl = ids[(ly + 2) * IDS_W + (lx + 1)], idr = ids[(ly + 2) * IDS_W + (lx + 3)];
+    const int idd = ids[(ly + 1) * IDS_W + (lx + 2)], idu = ids[(ly + 3) * IDS_W + (lx + 2)];
+    float m = (idc >= 0) ? 1.f : 0.f;
+    if (idc == ID_OUTSIDE) return 0.f;
+    const bool c = idc >= 0;
+    if ((idl >= 0) == c && (idr >= 0) == c && (idd >= 0) == c && (idu >= 0) == c) return m;
+    m = xadd(m, pair_contrib(S, mvp, make_pair(idc, idl, x, y, 0, 0), 0, false));
+    m = xadd(m, pair_contrib(S, mvp, make_pair(idc, idr, x, y, 0, 1), 0, true));
+    m = xadd(m, pair_contrib(S, mvp, make_pair(idc, idd, x, y, 1, 0), 1, false));
+    m = xadd(m, pair_contrib(S, mvp, make_pair(idc, idu, x, y, 1, 1), 1, true));
+    return m;
+}
+
+__device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+template <bool LOSS>
+__global__ void __launch_bounds__(TILE_THREADS) pixel_kernel(SceneDev S, const HypState* __restrict__ hyp,
+                                                             const int* __restrict__ total_tiles, int B,
+                                                             LossCfgDev cfg,
+                                                             const unsigned long long* __restrict__ zbuf,
+                                                             float* __restrict__ partials, RenderOut out) {
+    __shared__ int s_ids[IDS_W * IDS_H];
+    __shared__ float s_maa[MAA_W * MAA_H];
+    __shared__ float s_mvp[16];
+    __shared__ float s_m2[4];
+    __shared__ float s_red[TILE_THREADS / 32][NACC];
+    __shared__ int s_b;
+
+    const int total = *total_tiles;
+    const int tid = threadIdx.x;
+    const int lx = tid % TILE_W, ly = tid / TILE_W;
+
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        // locate the hypothesis: last b with tile_base <= item
+        if (tid == 0) {
+            int lo = 0, hi = B - 1;
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (hyp[mid].tile_base <= item) lo = mid; else hi = mid - 1;
+            }
+            s_b = lo;
+        }
+        __syncthreads();
+        const int b = s_b;
+        const HypState& h = hyp[b];
+        if (tid < 16) s_mvp[tid] = h.mvp[tid];
+        if (tid < 4) s_m2[tid] = h.m[8 + tid];
+        const int local = item - h.tile_base;
+        const int tx = local % h.tiles_x, ty = local / h.tiles_x;
+        const int ox = h.rx0 + tx * TILE_W, oy = h.ry0 + ty * TILE_H;  // tile origin, frame pixels
+        // valid z-buffer region of this hypothesis
+        const int vx0 = max(h.rx0 - 1, S.zx0), vx1 = min(h.rx1 + 1, S.zx0 + S.zw);
+        const int vy0 = max(h.ry0 - 1, S.zy0), vy1 = min(h.ry1 + 1, S.zy0 + S.zh);
+        const unsigned long long* zb = zbuf + (size_t)b * S.zh * S.zw;
+        for (int i = tid; i < IDS_W * IDS_H; i += TILE_THREADS) {
+            const int x = ox - 2 + i % IDS_W, y = oy - 2 + i / IDS_W;
+            int id;
+            if (x < 0 || y < 0 || x >= S.W || y >= S.H) id = ID_OUTSIDE;
+            else if (x < vx0 || x >= vx1 || y < vy0 || y >= vy1) id = ID_NONE;
+            else {
+                const unsigned long long k = zb[(size_t)(y - S.zy0) * S.zw + (x - S.zx0)];
+                id = (k == EMPTY_KEY) ? ID_NONE : (int)(unsigned int)(k & 0xFFFFFFFFull);
+            }
+            s_ids[i] = id;
+        }
+        __syncthreads();
+        // antialiased mask over tile + 1 px halo (only where it can matter: inside the loss ROI)
+        for (int i = tid; i < MAA_W * MAA_H; i += TILE_THREADS) {
+            const int mx = i % MAA_W - 1, my = i / MAA_W - 1;
+            const int x = ox + mx, y = oy + my;
+            float m = 0.f;
+            if (x >= h.rx0 && x < h.rx1 && y >= h.ry0 && y < h.ry1) m = mask_aa_pixel(S, s_mvp, s_ids, mx, my, x, y);
+            s_maa[i] = m;
+        }
+        __syncthreads();
+
+        float acc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; k++) acc[k] = 0.f;
+
+        const int x = ox + lx, y = oy + ly;
+        const bool inroi = (x < h.rx1 && y < h.ry1);
+        if (inroi) {
+            const int id = s_ids[(ly + 2) * IDS_W + (lx + 2)];
+            const float maa = s_maa[(ly + 1) * MAA_W + (lx + 1)];
+            const size_t gpix = (size_t)y * S.W + x;
+            float seg[3] = {1.f, 1.f, 1.f};
+            if (LOSS && S.gt_seg) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) seg[c] = S.gt_seg[gpix * S.seg_pix_stride + c * S.seg_ch_stride];
+            }
+            float rgb[3] = {0.f, 0.f, 0.f};
+            float depth = -s_m2[3];
+            float ru = 0.f, rv = 0.f, rzw = 0.f;
+            float gu = 0.f, gv = 0.f;  // dL/d(u,v)
+            Shade sh;
+            if (id >= 0) {
+                shade_setup(S, s_mvp, id, x, y, sh);
+                ru = sh.u; rv = sh.v; rzw = sh.zw;
+                const float b0 = sh.u, b1 = sh.v, b2 = xsub(xsub(1.f, sh.u), sh.v);
+                const float* P0 = S.pos + 3 * sh.i0;
+                const float* P1 = S.pos + 3 * sh.i1;
+                const float* P2 = S.pos + 3 * sh.i2;
+                const float p0[3] = {P0[0], P0[1], P0[2]}, p1[3] = {P1[0], P1[1], P1[2]}, p2[3] = {P2[0], P2[1], P2[2]};
+                // forward values use separately rounded ops in the oracle's order (bit-equal outputs)
+                float g[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) g[k] = xadd(xadd(xmul(b0, p0[k]), xmul(b1, p1[k])), xmul(b2, p2[k]));
+                depth = -xadd(xadd(xadd(xmul(s_m2[0], g[0]), xmul(s_m2[1], g[1])), xmul(s_m2[2], g[2])), s_m2[3]);
+
+                float gd = 0.f;  // dL/d depth
+                if (LOSS && cfg.use_depth) {
+                    const float diff = (depth - S.gt_depth[gpix]) * seg[0];
+                    acc[17] += fabsf(diff);
+                    gd = h.k_depth * sgn(diff) * seg[0];
+                    acc[12] -= gd * g[0]; acc[13] -= gd * g[1]; acc[14] -= gd * g[2]; acc[15] -= gd;
+                    // through g = sum b_i p_i
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const float dg = -gd * s_m2[k];
+                        gu += dg * (p0[k] - p2[k]);
+                        gv += dg * (p1[k] - p2[k]);
+                    }
+                }
+                if (S.tex) {
+                    const float2 t0 = *reinterpret_cast<const float2*>(S.uv + 2 * sh.i0);
+                    const float2 t1 = *reinterpret_cast<const float2*>(S.uv + 2 * sh.i1);
+                    const float2 t2 = *reinterpret_cast<const float2*>(S.uv + 2 * sh.i2);
+                    float tu = xadd(xadd(xmul(b0, t0.x), xmul(b1, t1.x)), xmul(b2, t2.x));
+                    float tv = xadd(xadd(xmul(b0, t0.y), xmul(b1, t1.y)), xmul(b2, t2.y));
+                    tu = xsub(tu, floorf(tu)); tv = xsub(tv, floorf(tv));
+                    tu = xsub(xmul(tu, (float)S.tex_w), 0.5f); tv = xsub(xmul(tv, (float)S.tex_h), 0.5f);
+                    int iu0 = (int)floorf(tu), iv0 = (int)floorf(tv);
+                    const float fu = xsub(tu, (float)iu0), fv = xsub(tv, (float)iv0);
+                    int iu1 = iu0 + 1, iv1 = iv0 + 1;
+                    if (iu0 < 0) iu0 += S.tex_w;
+                    if (iv0 < 0) iv0 += S.tex_h;
+                    if (iu1 >= S.tex_w) iu1 -= S.tex_w;
+                    if (iv1 >= S.tex_h) iv1 -= S.tex_h;
+                    const float* a00 = S.tex + ((size_t)iv0 * S.tex_w + iu0) * 3;
+                    const float* a10 = S.tex + ((size_t)iv0 * S.tex_w + iu1) * 3;
+                    const float* a01 = S.tex + ((size_t)iv1 * S.tex_w + iu0) * 3;
+                    const float* a11 = S.tex + ((size_t)iv1 * S.tex_w + iu1) * 3;
+                    float gtu = 0.f, gtv = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float v00 = a00[c], v10 = a10[c], v01 = a01[c], v11 = a11[c];
+                        const float top = xadd(v00, xmul(xsub(v10, v00), fu)), bot = xadd(v01, xmul(xsub(v11, v01), fu));
+                        rgb[c] = xadd(top, xmul(xsub(bot, top), fv));
+                        if (LOSS && cfg.use_rgb) {
+                            const float diff = (rgb[c] - S.gt_rgb[gpix * 3 + c]) * seg[c];
+                            acc[16] += fabsf(diff);
+                            const float dy = h.k_rgb * sgn(diff) * seg[c];
+                            const float ad = (v11 + v00) - (v10 + v01);
+                            gtu += dy * ((v10 - v00) + fv * ad);
+                            gtv += dy * ((v01 - v00) + fu * ad);
+                        }
+                    }
+                    if (LOSS && cfg.use_rgb) {
+                        gtu *= (float)S.tex_w; gtv *= (float)S.tex_h;
+                        gu += gtu * (t0.x - t2.x) + gtv * (t0.y - t2.y);
+                        gv += gtu * (t1.x - t2.x) + gtv * (t1.y - t2.y);
+                    }
+                } else if (S.vcol) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float k0 = S.vcol[3 * sh.i0 + c], k1 = S.vcol[3 * sh.i1 + c], k2 = S.vcol[3 * sh.i2 + c];
+                        rgb[c] = xadd(xadd(xmul(b0, k0), xmul(b1, k1)), xmul(b2, k2));
+                        if (LOSS && cfg.use_rgb) {
+                            const float diff = (rgb[c] - S.gt_rgb[gpix * 3 + c]) * seg[c];
+                            acc[16] += fabsf(diff);
+                            const float dy = h.k_rgb * sgn(diff) * seg[c];
+                            gu += dy * (k0 - k2);
+                            gv += dy * (k1 - k2);
+                        }
+                    }
+                }
+                if (LOSS && (gu != 0.f || gv != 0.f)) raster_grad_accum(S, sh, gu, gv, acc);
+            } else if (LOSS) {
+                // background: rgb = 0, depth = -t_z (interpolate yields 0 where tri_id == 0)
+                if (cfg.use_depth) {
+                    const float diff = (depth - S.gt_depth[gpix]) * seg[0];
+                    acc[17] += fabsf(diff);
+                    const float gd = h.k_depth * sgn(diff) * seg[0];
+                    acc[15] -= gd;
+                }
+                if (cfg.use_rgb) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) acc[16] += fabsf((0.f - S.gt_rgb[gpix * 3 + c]) * seg[c]);
+                }
+            }
+
+            if (LOSS && cfg.use_mask) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) acc[18] += fabsf(maa - seg[c]);
+                // pairs owned by this pixel: (self, right), (self, upper); plus (left, self) / (lower, self)
+                // when that neighbour lies outside the loss ROI (nobody else owns them)
+                for (int e = 0; e < 4; e++) {
+                    const int d = e >> 1, side = (e & 1);  // e: 0 left, 1 right, 2 lower, 3 upper
+                    const int nx = x + (d ? 0 : (side ? 1 : -1)), ny = y + (d ? (side ? 1 : -1) : 0);
+                    const bool nb_in_roi = (nx >= h.rx0 && nx < h.rx1 && ny >= h.ry0 && ny < h.ry1);
+                    if (side == 0 && nb_in_roi) continue;
+                    const int idn = s_ids[(ly + 2 + (ny - y)) * IDS_W + (lx + 2 + (nx - x))];
+                    PairInfo p = make_pair(id, idn, x, y, d, side);
+                    if (!p.exists) continue;
+                    AARes r = aa_analyse(S, s_mvp, p.tri, p.qx, p.qy, d, p.ds);
+                    if (!r.valid) continue;
+                    const bool target_first = r.alpha > 0.f;
+                    const bool self_first = (side == 1);
+                    const bool target_self = (target_first == self_first);
+                    const int txp = target_self ? x : nx, typ = target_self ? y : ny;
+                    if (!(txp >= h.rx0 && txp < h.rx1 && typ >= h.ry0 && typ < h.ry1)) continue;  // no loss there
+                    const float mt = target_self ? maa : s_maa[(ly + 1 + (ny - y)) * MAA_W + (lx + 1 + (nx - x))];
+                    float dd = 0.f;
+                    const size_t tp = (size_t)typ * S.W + txp;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float sg = S.gt_seg ? S.gt_seg[tp * S.seg_pix_stride + c * S.seg_ch_stride] : 1.f;
+                        dd += h.k_mask * sgn(mt - sg) * p.dcol;
+                    }
+                    aa_grad_accum(S, s_mvp, p.tri, p.qx, p.qy, d, r.di, r.alpha, dd, acc);
+                }
+            }
+
+            if (!LOSS) {
+                const size_t wp = ((size_t)b * S.wh + (y - S.wy0)) * S.ww + (x - S.wx0);
+                if (out.rgb) { out.rgb[wp * 3] = rgb[0]; out.rgb[wp * 3 + 1] = rgb[1]; out.rgb[wp * 3 + 2] = rgb[2]; }
+                if (out.depth) out.depth[wp] = depth;
+                if (out.mask) out.mask[wp] = maa;
+                if (out.rast) {
+                    float4 r4 = make_float4(ru, rv, rzw, (id >= 0) ? (float)(id + 1) : 0.f);
+                    if (id < 0) r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    reinterpret_cast<float4*>(out.rast)[wp] = r4;
+                }
+            }
+        }
+
+        if (LOSS) {
+            // CTA reduction of the 19 accumulators, one partial row per tile (deterministic)
+#pragma unroll
+            for (int k = 0; k < NACC - 1; k++) {
+                float v = acc[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if ((tid & 31) == 0) s_red[tid >> 5][k] = v;
+            }
+            __syncthreads();
+            if (tid < NACC) {
+                float v = 0.f;
+                if (tid < NACC - 1)
+#pragma unroll
+                    for (int w = 0; w < TILE_THREADS / 32; w++) v += s_red[w][tid];
+                partials[(size_t)item * NACC + tid] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static int pixel_grid(int max_tiles, int num_sms) {
+    int g = num_sms * 6;
+    if (g > max_tiles) g = max_tiles;
+    return g < 1 ? 1 : g;
+}
+
+void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
+                       LossCfgDev cfg, const unsigned long long* zbuf, float* partials, int num_sms, cudaStream_t st) {
+    RenderOut none = {nullptr, nullptr, nullptr, nullptr};
+    pixel_kernel<true><<<pixel_grid(max_tiles, num_sms), TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf, partials, none);
+}
+
+void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
+                         const unsigned long long* zbuf, RenderOut out, int num_sms, cudaStream_t st) {
+    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f};
+    pixel_kernel<false><<<pixel_grid(max_tiles, num_sms), TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf, nullptr, out);
+}
+
+}  // namespace ddope

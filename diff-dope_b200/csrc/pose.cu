@@ -1,0 +1,269 @@
+// Per-hypothesis serial math: pose -> matrices -> loss ROI (before the pixel passes) and
+// gradient chain -> SGD step (after them). One CTA handles what the reference spends ~40 tiny
+// torch kernels on (diffdope/diffdope.py:46-89,195,1085-1098,1666,1714).
+#include "ddope_launch.h"
+
+namespace ddope {
+
+// q/|q| and M = [[R(q^),t],[0,0,0,1]] in the oracle's operation order (oracle/nvdr.py canonical_pose).
+__device__ void canonical_pose(const float* q, const float* t, float* qh, float* qnorm, float* M) {
+    float n = __fsqrt_rn(xadd(xadd(xadd(xmul(q[0], q[0]), xmul(q[1], q[1])), xmul(q[2], q[2])), xmul(q[3], q[3])));
+    float q0 = xdiv(q[0], n), q1 = xdiv(q[1], n), q2 = xdiv(q[2], n), q3 = xdiv(q[3], n);
+    qh[0] = q0; qh[1] = q1; qh[2] = q2; qh[3] = q3;
+    *qnorm = n;
+    const float one = 1.f, two = 2.f;
+    M[0] = xsub(xsub(one, xmul(two, xmul(q1, q1))), xmul(two, xmul(q2, q2)));
+    M[1] = xsub(xmul(xmul(two, q0), q1), xmul(xmul(two, q2), q3));
+    M[2] = xadd(xmul(xmul(two, q0), q2), xmul(xmul(two, q1), q3));
+    M[3] = t[0];
+    M[4] = xadd(xmul(xmul(two, q0), q1), xmul(xmul(two, q2), q3));
+    M[5] = xsub(xsub(one, xmul(two, xmul(q0, q0))), xmul(two, xmul(q2, q2)));
+    M[6] = xsub(xmul(xmul(two, q1), q2), xmul(xmul(two, q0), q3));
+    M[7] = t[1];
+    M[8] = xsub(xmul(xmul(two, q0), q2), xmul(xmul(two, q1), q3));
+    M[9] = xadd(xmul(xmul(two, q1), q2), xmul(xmul(two, q0), q3));
+    M[10] = xsub(xsub(one, xmul(two, xmul(q0, q0))), xmul(two, xmul(q1, q1)));
+    M[11] = t[2];
+    M[12] = 0.f; M[13] = 0.f; M[14] = 0.f; M[15] = 1.f;
+}
+
+__device__ void canonical_mvp(const float* P, const float* M, float* out) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            out[4 * r + c] = xadd(xadd(xadd(xmul(P[4 * r + 0], M[c]), xmul(P[4 * r + 1], M[4 + c])),
+                                       xmul(P[4 * r + 2], M[8 + c])),
+                                  xmul(P[4 * r + 3], M[12 + c]));
+}
+
+__global__ void __launch_bounds__(256) pose_kernel(SceneDev S, const float* __restrict__ quat,
+                                                   const float* __restrict__ trans,
+                                                   const float* __restrict__ lr_mult, int B, int B_global,
+                                                   LossCfgDev cfg, int roi_mode, HypState* __restrict__ hyp,
+                                                   int* __restrict__ total_tiles) {
+    __shared__ int s_warp[8];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+        int b = b0 + threadIdx.x;
+        int ntiles = 0;
+        if (b < B) {
+            HypState h;
+            float q[4] = {quat[4 * b], quat[4 * b + 1], quat[4 * b + 2], quat[4 * b + 3]};
+            float t[3] = {trans[3 * b], trans[3 * b + 1], trans[3 * b + 2]};
+            canonical_pose(q, t, h.qhat, &h.qnorm, h.m);
+            canonical_mvp(S.proj, h.m, h.mvp);
+
+            int x0 = S.wx0, y0 = S.wy0, x1 = S.wx0 + S.ww, y1 = S.wy0 + S.wh;  // window, exclusive end
+            if (roi_mode == 1) {
+                bool full = false;
+                float mnx = 1e30f, mny = 1e30f, mxx = -1e30f, mxy = -1e30f;
+                for (int c = 0; c < 8; c++) {
+                    float px = (c & 1) ? S.bbmax[0] : S.bbmin[0];
+                    float py = (c & 2) ? S.bbmax[1] : S.bbmin[1];
+                    float pz = (c & 4) ? S.bbmax[2] : S.bbmin[2];
+                    float cl[4];
+                    xfm_exact(h.mvp, px, py, pz, cl);
+                    if (!(cl[3] > 1e-6f)) { full = true; break; }
+                    float sx = (cl[0] / cl[3] * 0.5f + 0.5f) * (float)S.W;
+                    float sy = (cl[1] / cl[3] * 0.5f + 0.5f) * (float)S.H;
+                    if (!(fabsf(sx) < 1e6f) || !(fabsf(sy) < 1e6f)) { full = true; break; }
+                    mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx);
+                    mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
+                }
+                if (!full) {
+                    int ox0 = (int)floorf(mnx) - 2, ox1 = (int)ceilf(mxx) + 3;  // exclusive end
+                    int oy0 = (int)floorf(mny) - 2, oy1 = (int)ceilf(mxy) + 3;
+                    if (S.gt_seg != nullptr) {
+                        int sx0 = S.seg_bbox[0], sy0 = S.seg_bbox[1], sx1 = S.seg_bbox[2], sy1 = S.seg_bbox[3];
+                        if (sx0 <= sx1 && sy0 <= sy1) {
+                            ox0 = min(ox0, sx0); oy0 = min(oy0, sy0);
+                            ox1 = max(ox1, sx1 + 1); oy1 = max(oy1, sy1 + 1);
+                        }
+                    }
+                    x0 = max(x0, ox0); y0 = max(y0, oy0);
+                    x1 = min(x1, ox1); y1 = min(y1, oy1);
+                }
+            }
+            if (x1 <= x0 || y1 <= y0) { x0 = x1 = S.wx0; y0 = y1 = S.wy0; }
+            h.rx0 = x0; h.ry0 = y0; h.rx1 = x1; h.ry1 = y1;
+            h.tiles_x = (x1 - x0 + TILE_W - 1) / TILE_W;
+            h.tiles_y = (y1 - y0 + TILE_H - 1) / TILE_H;
+            ntiles = h.tiles_x * h.tiles_y;
+            h.pad0 = 0;
+            double P = (double)S.wh * (double)S.ww;
+            double lr = lr_mult ? (double)lr_mult[b] : 1.0;
+            h.k_rgb = (float)((double)cfg.w_rgb * lr / ((double)B_global * P * 3.0));
+            h.k_depth = (float)((double)cfg.w_depth * lr / ((double)B_global * P));
+            h.k_mask = (float)((double)cfg.w_mask * lr / ((double)B_global * P * 3.0));
+            h.tile_base = 0;
+            hyp[b] = h;
+        }
+        // block-wide exclusive scan of ntiles
+        int v = ntiles;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += n;
+        }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; w++) woff += s_warp[w];
+        int carry = s_carry;
+        if (b < B) hyp[b].tile_base = carry + woff + v - ntiles;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_tiles = s_carry;
+}
+
+void launch_pose(const SceneDev& S, const float* quat, const float* trans, const float* lr_mult, int B,
+                 int B_global, LossCfgDev cfg, int roi_mode, HypState* hyp, int* total_tiles, cudaStream_t st) {
+    pose_kernel<<<1, 256, 0, st>>>(S, quat, trans, lr_mult, B, B_global, cfg, roi_mode, hyp, total_tiles);
+}
+
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) step_kernel(SceneDev S, const HypState* __restrict__ hyp,
+                                                   const float* __restrict__ partials, int B, LossCfgDev cfg,
+                                                   float* __restrict__ quat, float* __restrict__ trans,
+                                                   const float* __restrict__ lr_sched, int it, int do_update,
+                                                   float* __restrict__ loss_table, float* __restrict__ grad_out,
+                                                   float* __restrict__ pose_hist, float* __restrict__ loss_hist) {
+    const int b = blockIdx.x;
+    const HypState& h = hyp[b];
+    const int n_items = h.tiles_x * h.tiles_y;
+    const float* base = partials + (size_t)h.tile_base * NACC;
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; k++) acc[k] = 0.f;
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+        const float4* p = reinterpret_cast<const float4*>(base + (size_t)i * NACC);
+#pragma unroll
+        for (int k = 0; k < NACC / 4; k++) {
+            float4 v = p[k];
+            acc[4 * k + 0] += v.x; acc[4 * k + 1] += v.y; acc[4 * k + 2] += v.z; acc[4 * k + 3] += v.w;
+        }
+    }
+    __shared__ float s_acc[4][NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; k++) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        acc[k] = v;
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < NACC; k++) s_acc[threadIdx.x >> 5][k] = acc[k];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    float a[NACC];
+    for (int k = 0; k < NACC; k++) a[k] = ((s_acc[0][k] + s_acc[1][k]) + s_acc[2][k]) + s_acc[3][k];
+
+    // dL/dM = P^T dL/dMVP (+ the direct depth term on row 2); rows x,y,w of dMVP are a[0..11]
+    const float* P = S.proj;
+    float dM[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            dM[k][c] = P[0 * 4 + k] * a[c] + P[1 * 4 + k] * a[4 + c] + P[3 * 4 + k] * a[8 + c];
+#pragma unroll
+    for (int c = 0; c < 4; c++) dM[2][c] += a[12 + c];
+
+    const float x = h.qhat[0], y = h.qhat[1], z = h.qhat[2], w = h.qhat[3];
+    float gx = 2.f * (y * dM[0][1] + z * dM[0][2] + y * dM[1][0] - 2.f * x * dM[1][1] - w * dM[1][2] + z * dM[2][0] + w * dM[2][1] - 2.f * x * dM[2][2]);
+    float gy = 2.f * (-2.f * y * dM[0][0] + x * dM[0][1] + w * dM[0][2] + x * dM[1][0] + z * dM[1][2] - w * dM[2][0] + z * dM[2][1] - 2.f * y * dM[2][2]);
+    float gz = 2.f * (-2.f * z * dM[0][0] - w * dM[0][1] + x * dM[0][2] + w * dM[1][0] - 2.f * z * dM[1][1] + y * dM[1][2] + x * dM[2][0] + y * dM[2][1]);
+    float gw = 2.f * (-z * dM[0][1] + y * dM[0][2] + z * dM[1][0] - x * dM[1][2] - y * dM[2][0] + x * dM[2][1]);
+    // through q^ = q/|q|
+    float dot = x * gx + y * gy + z * gz + w * gw;
+    float inv = 1.f / h.qnorm;
+    float g[7];
+    g[0] = (gx - x * dot) * inv;
+    g[1] = (gy - y * dot) * inv;
+    g[2] = (gz - z * dot) * inv;
+    g[3] = (gw - w * dot) * inv;
+    g[4] = dM[0][3]; g[5] = dM[1][3]; g[6] = dM[2][3];
+
+    const float P_px = (float)S.wh * (float)S.ww;
+    float l_rgb = cfg.use_rgb ? cfg.w_rgb * (a[16] / (P_px * 3.f)) : 0.f;
+    float l_dep = cfg.use_depth ? cfg.w_depth * (a[17] / P_px) : 0.f;
+    float l_msk = cfg.use_mask ? cfg.w_mask * (a[18] / (P_px * 3.f)) : 0.f;
+    if (loss_table) {
+        loss_table[3 * b + 0] = l_rgb; loss_table[3 * b + 1] = l_dep; loss_table[3 * b + 2] = l_msk;
+    }
+    if (loss_hist) {
+        float* lh = loss_hist + ((size_t)it * B + b) * 3;
+        lh[0] = l_rgb; lh[1] = l_dep; lh[2] = l_msk;
+    }
+    if (grad_out)
+        for (int k = 0; k < 7; k++) grad_out[7 * b + k] = g[k];
+    if (pose_hist) {
+        float* ph = pose_hist + ((size_t)it * B + b) * 7;
+        for (int k = 0; k < 4; k++) ph[k] = quat[4 * b + k];
+        for (int k = 0; k < 3; k++) ph[4 + k] = trans[3 * b + k];
+    }
+    if (do_update) {
+        const float lr = lr_sched[it];
+        for (int k = 0; k < 4; k++) quat[4 * b + k] -= lr * g[k];
+        for (int k = 0; k < 3; k++) trans[3 * b + k] -= lr * g[4 + k];
+    }
+}
+
+void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg,
+                 float* quat, float* trans, const float* lr_sched, int it, int do_update, float* loss_table,
+                 float* grad_out, float* pose_hist, float* loss_hist, cudaStream_t st) {
+    step_kernel<<<B, 128, 0, st>>>(S, hyp, partials, B, cfg, quat, trans, lr_sched, it, do_update, loss_table,
+                                   grad_out, pose_hist, loss_hist);
+}
+
+// ---------------------------------------------------------------------------------------------
+
+__global__ void seg_bbox_kernel(const float* __restrict__ seg, int H, int W, int seg_c, int* bbox4) {
+    int n = H * W;
+    int xmin = 1 << 30, ymin = 1 << 30, xmax = -1, ymax = -1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        bool nz = false;
+        for (int c = 0; c < seg_c; c++) nz |= (seg[(size_t)i * seg_c + c] != 0.f);
+        if (nz) {
+            int x = i % W, y = i / W;
+            xmin = min(xmin, x); xmax = max(xmax, x);
+            ymin = min(ymin, y); ymax = max(ymax, y);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = min(xmin, __shfl_down_sync(0xffffffffu, xmin, o));
+        ymin = min(ymin, __shfl_down_sync(0xffffffffu, ymin, o));
+        xmax = max(xmax, __shfl_down_sync(0xffffffffu, xmax, o));
+        ymax = max(ymax, __shfl_down_sync(0xffffffffu, ymax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && xmax >= 0) {
+        atomicMin(&bbox4[0], xmin); atomicMin(&bbox4[1], ymin);
+        atomicMax(&bbox4[2], xmax); atomicMax(&bbox4[3], ymax);
+    }
+}
+
+__global__ void seg_bbox_init(int* bbox4) {
+    bbox4[0] = 1 << 30; bbox4[1] = 1 << 30; bbox4[2] = -1; bbox4[3] = -1;
+}
+
+void launch_seg_bbox(const float* seg, int H, int W, int seg_c, int* bbox4, cudaStream_t st) {
+    seg_bbox_init<<<1, 1, 0, st>>>(bbox4);
+    seg_bbox_kernel<<<148, 256, 0, st>>>(seg, H, W, seg_c, bbox4);
+}
+
+__global__ void copy_mtx_kernel(const HypState* __restrict__ hyp, int B, float* __restrict__ mtx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * 16) mtx[i] = hyp[i >> 4].m[i & 15];
+}
+void launch_copy_mtx(const HypState* hyp, int B, float* mtx, cudaStream_t st) {
+    copy_mtx_kernel<<<(B * 16 + 255) / 256, 256, 0, st>>>(hyp, B, mtx);
+}
+
+}  // namespace ddope

@@ -1,0 +1,224 @@
+"""ctypes binding of libddope_b200.so (include/ddope_b200.h) for torch tensors.
+
+The library is plain C ABI: this module passes `tensor.data_ptr()` and the current
+CUDA stream. There is no CPU fallback: if the shared library is missing or a tensor
+is not on a CUDA device the call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_LIB = None
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libddope_b200.so")
+
+NUM_LOSSES = 3
+LOSS_KEYS = ("rgb", "depth", "mask_selection")  # reference add_loss_value keys, diffdope.py:559,577,605
+
+
+class LossCfg(ctypes.Structure):
+    _fields_ = [
+        ("use_rgb", ctypes.c_int32),
+        ("use_depth", ctypes.c_int32),
+        ("use_mask", ctypes.c_int32),
+        ("weight_rgb", ctypes.c_float),
+        ("weight_depth", ctypes.c_float),
+        ("weight_mask", ctypes.c_float),
+    ]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Load (once) and return the shared library; raise if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            "libddope_b200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C diff-dope_b200/csrc` (there is no CPU / PyTorch fallback for the hot path)" % _LIB_PATH
+        )
+    L = ctypes.CDLL(_LIB_PATH)
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    L.ddope_abi_version.restype = ci
+    L.ddope_last_error.restype = ctypes.c_char_p
+    L.ddope_last_launch_count.restype = ctypes.c_int64
+    L.ddope_last_launch_count.argtypes = [vp]
+    L.ddope_xfm_fwd.argtypes = [vp, ci, ci, vp, ci, ci, vp, vp]
+    L.ddope_xfm_bwd.argtypes = [vp, ci, ci, vp, ci, vp, vp]
+    L.ddope_xfm_bwd_mtx.argtypes = [vp, ci, ci, vp, ci, ci, vp, vp]
+    L.ddope_xfm_bwd_full.argtypes = [vp, ci, ci, vp, vp, ci, ci, vp, vp, vp]
+    L.ddope_scene_create.argtypes = [ctypes.POINTER(vp), vp, ci, vp, ci, vp, vp, ci, ci, vp]
+    L.ddope_scene_destroy.argtypes = [vp]
+    L.ddope_scene_set_camera.argtypes = [vp, vp, ci, ci]
+    L.ddope_scene_set_target.argtypes = [vp, vp, vp, vp, ci, vp]
+    L.ddope_scene_set_window.argtypes = [vp, ci, ci, ci, ci]
+    L.ddope_render.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
+    L.ddope_loss_grad.argtypes = [vp, vp, vp, vp, ci, ci, ctypes.POINTER(LossCfg), vp, vp, vp]
+    L.ddope_optimize.argtypes = [vp, vp, vp, vp, ci, ci, vp, ci, ctypes.POINTER(LossCfg), vp, vp, vp]
+    for name in (
+        "ddope_xfm_fwd", "ddope_xfm_bwd", "ddope_xfm_bwd_mtx", "ddope_xfm_bwd_full", "ddope_scene_create",
+        "ddope_scene_destroy", "ddope_scene_set_camera", "ddope_scene_set_target", "ddope_scene_set_window",
+        "ddope_render", "ddope_loss_grad", "ddope_optimize",
+    ):
+        getattr(L, name).restype = ci
+    if L.ddope_abi_version() != 1:
+        raise RuntimeError("libddope_b200.so ABI version mismatch")
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("ddope_b200: " + lib().ddope_last_error().decode("utf-8", "replace"))
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a cuda tensor" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32" % name)
+    return t.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _host(a, dtype):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _hptr(a):
+    return ctypes.c_void_p(0 if a is None else a.ctypes.data)
+
+
+def make_loss_cfg(use_rgb, use_depth, use_mask, w_rgb=1.0, w_depth=1.0, w_mask=1.0):
+    return LossCfg(int(bool(use_rgb)), int(bool(use_depth)), int(bool(use_mask)), float(w_rgb), float(w_depth), float(w_mask))
+
+
+class NativeScene:
+    """Owns one `ddope_scene`: a mesh uploaded once plus camera, target, window."""
+
+    def __init__(self, pos, tri, uv=None, tex=None, vtx_color=None):
+        L = lib()
+        pos = _host(pos, np.float32).reshape(-1, 3)
+        tri = _host(tri, np.int32).reshape(-1, 3)
+        uv = None if uv is None else _host(uv, np.float32).reshape(-1, 2)
+        tex = None if tex is None else _host(tex, np.float32)
+        if tex is not None:
+            if tex.ndim != 3 or tex.shape[2] < 3:
+                raise RuntimeError("tex must be [H,W,3]")
+            tex = np.ascontiguousarray(tex[:, :, :3])
+        vc = None if vtx_color is None else _host(vtx_color, np.float32).reshape(-1, 3)
+        self.V, self.T = pos.shape[0], tri.shape[0]
+        self.textured = uv is not None and tex is not None
+        h = ctypes.c_void_p()
+        th, tw = (tex.shape[0], tex.shape[1]) if self.textured else (0, 0)
+        _check(L.ddope_scene_create(ctypes.byref(h), _hptr(pos), self.V, _hptr(tri), self.T,
+                                    _hptr(uv if self.textured else None), _hptr(tex if self.textured else None), th, tw,
+                                    _hptr(None if self.textured else vc)))
+        self._h = h
+        self._keep = {}
+        self.H = self.W = None
+        self.window = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().ddope_scene_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def set_camera(self, proj, H, W):
+        p = _host(proj, np.float32).reshape(4, 4)
+        _check(lib().ddope_scene_set_camera(self._h, _hptr(p), int(H), int(W)))
+        self.H, self.W = int(H), int(W)
+        self.window = (0, 0, self.H, self.W)
+        self._keep.pop("target", None)
+
+    def set_window(self, y0, x0, h, w):
+        _check(lib().ddope_scene_set_window(self._h, int(y0), int(x0), int(h), int(w)))
+        self.window = (int(y0), int(x0), int(h), int(w))
+
+    def set_target(self, rgb=None, depth=None, seg=None):
+        """rgb [H,W,3], depth [H,W], seg [H,W,3] or [H,W] or [H,W,1]; cuda float32, borrowed."""
+        seg_c = 0
+        if rgb is not None:
+            rgb = _dev_f32(rgb, "rgb")
+            assert tuple(rgb.shape) == (self.H, self.W, 3), "rgb target must be [H,W,3]"
+        if depth is not None:
+            depth = _dev_f32(depth, "depth")
+            assert tuple(depth.shape) == (self.H, self.W), "depth target must be [H,W]"
+        if seg is not None:
+            seg = _dev_f32(seg, "seg")
+            if seg.dim() == 2:
+                seg_c = 1
+            else:
+                seg_c = seg.shape[2]
+            assert tuple(seg.shape[:2]) == (self.H, self.W) and seg_c in (1, 3), "seg target must be [H,W] or [H,W,1|3]"
+        self._keep["target"] = (rgb, depth, seg)
+        _check(lib().ddope_scene_set_target(self._h, _ptr(rgb), _ptr(depth), _ptr(seg), seg_c, _stream()))
+
+    def render(self, quat, trans, want=("rgb", "depth", "mask", "rast", "mtx")):
+        quat, trans = _dev_f32(quat, "quat"), _dev_f32(trans, "trans")
+        B = quat.shape[0]
+        _, _, h, w = self.window
+        dev = quat.device
+        out = {}
+        if "rgb" in want:
+            out["rgb"] = torch.empty(B, h, w, 3, device=dev)
+        if "depth" in want:
+            out["depth"] = torch.empty(B, h, w, device=dev)
+        if "mask" in want:
+            out["mask"] = torch.empty(B, h, w, device=dev)
+        if "rast" in want:
+            out["rast"] = torch.empty(B, h, w, 4, device=dev)
+        if "mtx" in want:
+            out["mtx"] = torch.empty(B, 4, 4, device=dev)
+        _check(lib().ddope_render(self._h, _ptr(quat), _ptr(trans), B, _ptr(out.get("rgb")), _ptr(out.get("depth")),
+                                  _ptr(out.get("mask")), _ptr(out.get("rast")), _ptr(out.get("mtx")), _stream()))
+        return out
+
+    def loss_grad(self, quat, trans, lr_mult, cfg, b_global=None):
+        quat, trans = _dev_f32(quat, "quat"), _dev_f32(trans, "trans")
+        lr_mult = _dev_f32(lr_mult, "lr_mult")
+        B = quat.shape[0]
+        loss = torch.empty(B, NUM_LOSSES, device=quat.device)
+        grad = torch.empty(B, 7, device=quat.device)
+        _check(lib().ddope_loss_grad(self._h, _ptr(quat), _ptr(trans), _ptr(lr_mult), B, int(b_global or B),
+                                     ctypes.byref(cfg), _ptr(loss), _ptr(grad), _stream()))
+        return loss, grad
+
+    def optimize(self, quat, trans, lr_mult, lr_sched, cfg, b_global=None, keep_history=True):
+        """In-place SGD on quat [B,4] / trans [B,3]. Returns (pose_hist [n,B,7], loss_hist [n,B,3]) or (None, None)."""
+        for t, n in ((quat, "quat"), (trans, "trans")):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError("%s must be a contiguous cuda float32 tensor (updated in place)" % n)
+        lr_mult = _dev_f32(lr_mult, "lr_mult")
+        B = quat.shape[0]
+        sched = np.ascontiguousarray(lr_sched, dtype=np.float32)
+        n = sched.shape[0]
+        pose_hist = loss_hist = None
+        if keep_history:
+            pose_hist = torch.empty(n, B, 7, device=quat.device)
+            loss_hist = torch.empty(n, B, NUM_LOSSES, device=quat.device)
+        _check(lib().ddope_optimize(self._h, _ptr(quat), _ptr(trans), _ptr(lr_mult), B, int(b_global or B), _hptr(sched), n,
+                                    ctypes.byref(cfg), _ptr(pose_hist), _ptr(loss_hist), _stream()))
+        return pose_hist, loss_hist
+
+    def last_launch_count(self):
+        return int(lib().ddope_last_launch_count(self._h))

@@ -1,0 +1,152 @@
+/*
+ * ddope_b200 -- C ABI of the B200-native Diff-DOPE hot path (libddope_b200.so).
+ *
+ * Drop-in boundary for the one path the reference runs per optimisation iteration
+ * (reference: diffdope/diffdope.py:1634-1714 and everything it calls). The reference
+ * reaches native code in two places:
+ *   (1) its own pybind11 plugin `renderutils_plugin`
+ *       (diffdope/c_src/torch_bindings.cpp:142-284, bound from diffdope/ops.py:104-125);
+ *   (2) `nvdiffrast.torch` (diffdope/diffdope.py:147,198,212-214,218-226,230,1312),
+ *       an external dependency this library replaces outright.
+ * Every entry point below names the reference interface it stands in for.
+ *
+ * Conventions
+ *   - plain C, no torch types; "dev" pointers are CUDA device pointers, "host" pointers
+ *     are ordinary host memory; all arrays are contiguous, float32 / int32.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). Calls
+ *     enqueue work and return; they do not synchronise unless stated.
+ *   - return value 0 = success, negative = error; `ddope_last_error()` returns the
+ *     message of the last failing call on the calling thread.
+ *   - matrices are row-major 4x4 acting on column vectors, quaternions are (x,y,z,w),
+ *     images are [H,W,C] with row 0 = bottom of the picture (the reference flips its
+ *     ground-truth images on load, diffdope/diffdope.py:1131-1132).
+ */
+#ifndef DDOPE_B200_H
+#define DDOPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDOPE_ABI_VERSION 1
+
+typedef struct ddope_scene ddope_scene; /* opaque: one mesh + camera + target + work buffers */
+
+/* Which losses run, and their weights: `cfg.losses.*` of configs/diffdope.yaml as read by
+ * l1_rgb_with_mask / l1_depth_with_mask / l1_mask (diffdope/diffdope.py:547-613). */
+typedef struct ddope_loss_cfg {
+    int32_t use_rgb;
+    int32_t use_depth;
+    int32_t use_mask;
+    float weight_rgb;
+    float weight_depth;
+    float weight_mask;
+} ddope_loss_cfg;
+
+/* Columns of the per-hypothesis loss table written by ddope_loss_grad / ddope_optimize:
+ * the values the reference logs through add_loss_value under the keys "rgb", "depth",
+ * "mask_selection" (diffdope/diffdope.py:558-560,576-578,604-608). */
+#define DDOPE_LOSS_RGB 0
+#define DDOPE_LOSS_DEPTH 1
+#define DDOPE_LOSS_MASK 2
+#define DDOPE_NUM_LOSSES 3
+
+int ddope_abi_version(void);
+const char* ddope_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) renderutils_plugin replacements. Same four operations, same tensor meaning.
+ * points [Bp,N,3] with Bp == B or Bp == 1 (broadcast, c_src/tensor.h:35); matrix [B,4,4];
+ * is_points != 0: out [B,N,4] = M [p,1]; is_points == 0: out [B,N,3] = M3x3 v.
+ * ---------------------------------------------------------------------------------------- */
+
+/* xfm_fwd  (c_src/torch_bindings.cpp:142-175, kernel c_src/mesh.cu:22-54) */
+int ddope_xfm_fwd(const float* points_dev, int Bp, int N, const float* matrix_dev, int B,
+                  int is_points, float* out_dev, void* stream);
+
+/* xfm_bwd  (torch_bindings.cpp:177-203, mesh.cu:56-94): d_points [B,N,3] = M^T d_out */
+int ddope_xfm_bwd(const float* matrix_dev, int B, int N, const float* grad_out_dev,
+                  int is_points, float* d_points_dev, void* stream);
+
+/* xfm_bwd_mtx (torch_bindings.cpp:242-277, mesh.cu:165-214): d_matrix [B,4,4] =
+ * sum_n d_out (x) [p,1]; reduced deterministically, no padded atomic buffer. */
+int ddope_xfm_bwd_mtx(const float* points_dev, int Bp, int N, const float* grad_out_dev, int B,
+                      int is_points, float* d_matrix_dev, void* stream);
+
+/* xfm_bwd_full (torch_bindings.cpp:205-239, mesh.cu:96-163): both of the above */
+int ddope_xfm_bwd_full(const float* points_dev, int Bp, int N, const float* matrix_dev,
+                       const float* grad_out_dev, int B, int is_points, float* d_points_dev,
+                       float* d_matrix_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) scene: what Mesh / Camera / Scene hold on the GPU in the reference
+ * (diffdope/diffdope.py:621-935,1101-1264), stored ONCE instead of stacked B times
+ * (Mesh.set_batchsize, diffdope.py:875-881).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Mesh.__init__ arrays (diffdope.py:784-851), host pointers, copied.
+ * pos [V,3] (already scaled), tri [T,3]; textured: uv [V,2] (v already flipped) + tex
+ * [tex_h,tex_w,3] in [0,1]; untextured: vcol [V,3]. Exactly one of (uv,tex) / vcol.
+ * Builds the edge -> opposite-vertex table once (nvdiffrast rebuilds its hash on every
+ * dr.antialias call because the reference passes no topology_hash, diffdope.py:214). */
+int ddope_scene_create(ddope_scene** out, const float* pos_host, int V, const int32_t* tri_host,
+                       int T, const float* uv_host, const float* tex_host, int tex_h, int tex_w,
+                       const float* vcol_host);
+int ddope_scene_destroy(ddope_scene* s);
+
+/* Camera.cam_proj (diffdope.py:679-742) and the render resolution
+ * (Scene.get_resolution, diffdope.py:1231-1252). proj16 row-major, host. */
+int ddope_scene_set_camera(ddope_scene* s, const float* proj16_host, int frame_h, int frame_w);
+
+/* gt_tensors (diffdope.py:1646-1651): device pointers, BORROWED (must outlive the calls that
+ * use them), one image shared by all hypotheses: rgb [H,W,3], depth [H,W], seg [H,W,seg_c]
+ * with seg_c = 3 (as the reference loads it) or 1 (channels identical). Any may be NULL if
+ * the loss that needs it is off. Runs one small kernel (bounding box of seg != 0). */
+int ddope_scene_set_target(ddope_scene* s, const float* rgb_dev, const float* depth_dev,
+                           const float* seg_dev, int seg_c, void* stream);
+
+/* Loss window (y0,x0,h,w) in frame pixels: "render the full frame, then slice render and
+ * ground truth" (the reference always uses the full frame; default after set_camera). */
+int ddope_scene_set_window(ddope_scene* s, int y0, int x0, int h, int w);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) the hot path
+ * ---------------------------------------------------------------------------------------- */
+
+/* Object3D.forward + matrix_batch_44_from_position_quat + render_texture_batch
+ * (diffdope.py:1085-1098,46-89,156-234) for B hypotheses, window-sized outputs (any NULL):
+ * rgb [B,h,w,3], depth [B,h,w], mask [B,h,w] (the reference's 3 mask channels are equal),
+ * rast [B,h,w,4] = (u, v, z/w, tri_id+1), mtx [B,4,4].
+ * quat [B,4] raw (un-normalised) parameters, trans [B,3]. */
+int ddope_render(ddope_scene* s, const float* quat_dev, const float* trans_dev, int B,
+                 float* rgb_dev, float* depth_dev, float* mask_dev, float* rast_dev,
+                 float* mtx_dev, void* stream);
+
+/* One forward + loss + backward without a parameter update: the gradient autograd
+ * produces at diffdope.py:1713 for loss = sum_k w_k * mean_b(lr_b * mean_px |.|)
+ * (diffdope.py:534-613). B_global is the divisor of mean_b (the whole job's hypothesis
+ * count when B is one rank's shard). loss_table [B,3], grad [B,7] = d/d(qx,qy,qz,qw,x,y,z). */
+int ddope_loss_grad(ddope_scene* s, const float* quat_dev, const float* trans_dev,
+                    const float* lr_mult_dev, int B, int B_global, const ddope_loss_cfg* cfg,
+                    float* loss_table_dev, float* grad_dev, void* stream);
+
+/* DiffDope.run_optimization's loop (diffdope.py:1656-1714): n_iters iterations of
+ * forward, loss, backward, SGD step theta -= lr_sched[it] * grad, in place on quat/trans.
+ * lr_sched_host [n_iters] (diffdope.py:1657-1664, computed by the caller in double).
+ * pose_hist [n_iters,B,7] = parameters each iteration rendered with (or NULL);
+ * loss_hist [n_iters,B,3] = logged loss values per iteration (or NULL). */
+int ddope_optimize(ddope_scene* s, float* quat_dev, float* trans_dev, const float* lr_mult_dev,
+                   int B, int B_global, const float* lr_sched_host, int n_iters,
+                   const ddope_loss_cfg* cfg, float* pose_hist_dev, float* loss_hist_dev,
+                   void* stream);
+
+/* Number of kernels the last ddope_optimize / ddope_loss_grad / ddope_render call on this
+ * scene launched (for bench.py's gpu_launches). */
+int64_t ddope_last_launch_count(const ddope_scene* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDOPE_B200_H */
