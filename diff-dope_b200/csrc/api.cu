@@ -289,16 +289,15 @@ static int check_loss_inputs(const ddope_scene* s, const ddope_loss_cfg* cfg, co
     return 0;
 }
 
-extern "C" int ddope_render(ddope_scene* s, const float* quat, const float* trans, int B, float* rgb, float* depth,
-                            float* mask, float* rast, float* mtx, void* stream) {
-    if (!s || !quat || !trans) return fail("ddope_render: null pointer");
-    if (B <= 0 || B > 65535) return fail("ddope_render: B must be in [1, 65535]");
-    if (!s->have_camera) return fail("ddope_render: set the camera first");
+static int render_common(ddope_scene* s, const float* quat, const float* trans, const float* mtx_in, int B, float* rgb,
+                         float* depth, float* mask, float* rast, float* mtx, void* stream, const char* who) {
+    if (!s || (!mtx_in && (!quat || !trans))) return fail(std::string(who) + ": null pointer");
+    if (B <= 0 || B > 65535) return fail(std::string(who) + ": B must be in [1, 65535]");
+    if (!s->have_camera) return fail(std::string(who) + ": set the camera first");
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, false)) return r;
     LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f};
-    s->launches = 0;
-    launch_pose(s->dev, quat, trans, nullptr, B, B, cfg, 0, s->hyp, s->total_tiles, st);
+    launch_pose(s->dev, quat, trans, mtx_in, nullptr, B, B, cfg, 0, s->hyp, s->total_tiles, st);
     launch_clear(s->dev, s->hyp, B, s->zbuf, st);
     launch_raster(s->dev, s->hyp, B, s->zbuf, st);
     RenderOut out = {rgb, depth, mask, rast};
@@ -312,15 +311,45 @@ extern "C" int ddope_render(ddope_scene* s, const float* quat, const float* tran
     return 0;
 }
 
+extern "C" int ddope_render(ddope_scene* s, const float* quat, const float* trans, int B, float* rgb, float* depth,
+                            float* mask, float* rast, float* mtx, void* stream) {
+    return render_common(s, quat, trans, nullptr, B, rgb, depth, mask, rast, mtx, stream, "ddope_render");
+}
+
+extern "C" int ddope_render_mtx(ddope_scene* s, const float* mtx_in, int B, float* rgb, float* depth, float* mask,
+                                float* rast, void* stream) {
+    return render_common(s, nullptr, nullptr, mtx_in, B, rgb, depth, mask, rast, nullptr, stream, "ddope_render_mtx");
+}
+
+extern "C" int ddope_render_bwd(ddope_scene* s, const float* mtx_in, int B, const float* d_rgb, const float* d_depth,
+                                const float* d_mask, float* d_mtx, void* stream) {
+    if (!s || !mtx_in || !d_mtx) return fail("ddope_render_bwd: null pointer");
+    if (B <= 0 || B > 65535) return fail("ddope_render_bwd: B must be in [1, 65535]");
+    if (!s->have_camera) return fail("ddope_render_bwd: set the camera first");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = ensure_buffers(s, B, true)) return r;
+    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f};
+    launch_pose(s->dev, nullptr, nullptr, mtx_in, nullptr, B, B, cfg, 0, s->hyp, s->total_tiles, st);
+    launch_clear(s->dev, s->hyp, B, s->zbuf, st);
+    launch_raster(s->dev, s->hyp, B, s->zbuf, st);
+    ExtGrad ext = {d_rgb, d_depth, d_mask};
+    launch_pixel_ext(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), s->zbuf, ext, s->partials, s->num_sms, st);
+    launch_step(s->dev, s->hyp, s->partials, B, cfg, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                nullptr, d_mtx, st);
+    s->launches = 5;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 static void enqueue_iteration(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
                               LossCfgDev cfg, int it, int do_update, float* loss_table, float* grad,
                               float* pose_hist, float* loss_hist, cudaStream_t st) {
-    launch_pose(s->dev, quat, trans, lr_mult, B, B_global, cfg, 1, s->hyp, s->total_tiles, st);
+    launch_pose(s->dev, quat, trans, nullptr, lr_mult, B, B_global, cfg, 1, s->hyp, s->total_tiles, st);
     launch_clear(s->dev, s->hyp, B, s->zbuf, st);
     launch_raster(s->dev, s->hyp, B, s->zbuf, st);
     launch_pixel_loss(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), cfg, s->zbuf, s->partials, s->num_sms, st);
     launch_step(s->dev, s->hyp, s->partials, B, cfg, quat, trans, s->lr_sched, it, do_update, loss_table, grad,
-                pose_hist, loss_hist, st);
+                pose_hist, loss_hist, nullptr, st);
     s->launches += 5;
 }
 

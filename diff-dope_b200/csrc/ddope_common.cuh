@@ -6,8 +6,8 @@
 namespace ddope {
 
 constexpr int TILE_W = 32;
-constexpr int TILE_H = 8;
-constexpr int TILE_THREADS = TILE_W * TILE_H;
+constexpr int TILE_H = 32;        // one work item of the pixel pass: 32x32 px, 4 px per thread
+constexpr int TILE_THREADS = 256;
 constexpr int NACC = 20;  // 12 dMVP(rows x,y,w) + 4 dM(row z) + 3 loss sums + 1 pad
 constexpr unsigned long long EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
 constexpr int SUBPIX = 256;

@@ -6,12 +6,13 @@ namespace ddope {
 
 // pose.cu
 // quat/trans -> HypState (M, MVP, loss ROI, tile prefix). roi_mode: 0 = window (render), 1 = tight (loss).
-void launch_pose(const SceneDev& S, const float* quat, const float* trans, const float* lr_mult, int B,
-                 int B_global, LossCfgDev cfg, int roi_mode, HypState* hyp, int* total_tiles, cudaStream_t st);
+// mtx_in != null: take M = mtx_in[b] instead of building it from quat/trans.
+void launch_pose(const SceneDev& S, const float* quat, const float* trans, const float* mtx_in, const float* lr_mult,
+                 int B, int B_global, LossCfgDev cfg, int roi_mode, HypState* hyp, int* total_tiles, cudaStream_t st);
 // Reduce tile partials per hypothesis, chain to d(quat,trans), optionally apply the SGD step.
 void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg,
                  float* quat, float* trans, const float* lr_sched, int it, int do_update, float* loss_table,
-                 float* grad_out, float* pose_hist, float* loss_hist, cudaStream_t st);
+                 float* grad_out, float* pose_hist, float* loss_hist, float* dmtx_out, cudaStream_t st);
 void launch_seg_bbox(const float* seg, int H, int W, int seg_c, int* bbox4, cudaStream_t st);
 void launch_copy_mtx(const HypState* hyp, int B, float* mtx, cudaStream_t st);
 
@@ -26,6 +27,13 @@ struct RenderOut {
     float* mask;   // [B,wh,ww]
     float* rast;   // [B,wh,ww,4]
 };
+struct ExtGrad {          // dL/d(render outputs), window-sized, any may be null
+    const float* d_rgb;    // [B,wh,ww,3]
+    const float* d_depth;  // [B,wh,ww]
+    const float* d_mask;   // [B,wh,ww]
+};
+void launch_pixel_ext(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
+                      const unsigned long long* zbuf, ExtGrad ext, float* partials, int num_sms, cudaStream_t st);
 void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                        LossCfgDev cfg, const unsigned long long* zbuf, float* partials, int num_sms, cudaStream_t st);
 void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,

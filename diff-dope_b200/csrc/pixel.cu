@@ -186,83 +186,41 @@ __device__ void aa_grad_accum(const SceneDev& S, const float* mvp, int tri, int 
     acc[8] += g1w * q1[0] + g2w * q2[0]; acc[9] += g1w * q1[1] + g2w * q2[1]; acc[10] += g1w * q1[2] + g2w * q2[2]; acc[11] += g1w + g2w;
 }
 
-struct PairInfo {
-    bool exists;  // both pixels in the frame and exactly one of them covered
-    int tri, qx, qy;
-    float ds, dcol;  // dcol = coverage(second pixel) - coverage(first pixel)
-};
-
-// pair between (x,y) and its neighbour in direction d on side `side` (0: neighbour is x-1 / y-1, the
-// pair's first pixel; 1: neighbour is x+1 / y+1, the pair's second pixel)
-__device__ __forceinline__ PairInfo make_pair(int id_self, int id_nb, int x, int y, int d, int side) {
-    PairInfo p;
-    p.exists = false;
-    if (id_nb == ID_OUTSIDE || id_self == ID_OUTSIDE) return p;
-    const bool cs = id_self >= 0, cn = id_nb >= 0;
-    if (cs == cn) return p;  // equal coverage: the blend adds alpha * (1-1) or alpha * (0-0) = 0
-    p.exists = true;
-    const int nx = x + (d ? 0 : (side ? 1 : -1)), ny = y + (d ? (side ? 1 : -1) : 0);
-    const bool self_first = (side == 1);  // self is the pair's first (left/lower) pixel when the neighbour is +1
-    p.tri = cs ? id_self : id_nb;
-    p.qx = cs ? x : nx;
-    p.qy = cs ? y : ny;
-    const bool covered_is_first = (cs == self_first);
-    p.ds = covered_is_first ? 1.f : -1.f;
-    p.dcol = covered_is_first ? -1.f : 1.f;  // second - first
-    return p;
-}
-
-// contribution of a pair to the antialiased mask of pixel `self`; is_first: self is the pair's first pixel
-__device__ __forceinline__ float pair_contrib(const SceneDev& S, const float* mvp, const PairInfo& p, int d, bool self_first) {
-    if (!p.exists) return 0.f;
-    AARes r = aa_analyse(S, mvp, p.tri, p.qx, p.qy, d, p.ds);
-    if (!r.valid) return 0.f;
-    const bool target_first = r.alpha > 0.f;
-    if (target_first != self_first) return 0.f;
-    return xmul(r.alpha, p.dcol);
-}
-
-__device__ __forceinline__ float mask_aa_pixel(const SceneDev& S, const float* mvp, const int* ids, int lx, int ly, int x, int y) {
-    // ids indexed with the 2 px halo: local (lx,ly) in [-2, TILE+2)
-    const int idc = ids[(ly + 2) * IDS_W + (lx + 2)];
-    const int idl = ids[(ly + 2) * IDS_W + (lx + 1)], idr = ids[(ly + 2) * IDS_W + (lx + 3)];
-    const int idd = ids[(ly + 1) * IDS_W + (lx + 2)], idu = ids[(ly + 3) * IDS_W + (lx + 2)];
-    float m = (idc >= 0) ? 1.f : 0.f;
-    if (idc == ID_OUTSIDE) return 0.f;
-    const bool c = idc >= 0;
-    if ((idl >= 0) == c && (idr >= 0) == c && (idd >= 0) == c && (idu >= 0) == c) return m;
-    m = xadd(m, pair_contrib(S, mvp, make_pair(idc, idl, x, y, 0, 0), 0, false));
-    m = xadd(m, pair_contrib(S, mvp, make_pair(idc, idr, x, y, 0, 1), 0, true));
-    m = xadd(m, pair_contrib(S, mvp, make_pair(idc, idd, x, y, 1, 0), 1, false));
-    m = xadd(m, pair_contrib(S, mvp, make_pair(idc, idu, x, y, 1, 1), 1, true));
-    return m;
-}
-
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
-template <bool LOSS>
-__global__ void __launch_bounds__(TILE_THREADS) pixel_kernel(SceneDev S, const HypState* __restrict__ hyp,
+constexpr int MODE_RENDER = 0;  // write rgb / depth / mask / rast images (ddope_render*)
+constexpr int MODE_LOSS = 1;    // fused reference losses + backward (ddope_loss_grad / ddope_optimize)
+constexpr int MODE_EXT = 2;     // backward of externally supplied image gradients (ddope_render_bwd)
+
+constexpr int NPAIR = IDS_W * IDS_H;  // pair slots per direction, indexed by the pair's first pixel
+constexpr int DI_NONE = 3;            // no pair here / analysis found no usable edge
+
+template <int MODE>
+__global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(SceneDev S, const HypState* __restrict__ hyp,
                                                              const int* __restrict__ total_tiles, int B,
                                                              LossCfgDev cfg,
                                                              const unsigned long long* __restrict__ zbuf,
-                                                             float* __restrict__ partials, RenderOut out) {
-    __shared__ int s_ids[IDS_W * IDS_H];
+                                                             float* __restrict__ partials, RenderOut out, ExtGrad ext) {
+    __shared__ int s_ids[NPAIR];
+    __shared__ float s_alpha[2][NPAIR];
+    __shared__ unsigned char s_di[2][NPAIR];
+    __shared__ unsigned short s_queue[2 * NPAIR];
     __shared__ float s_maa[MAA_W * MAA_H];
     __shared__ float s_mvp[16];
     __shared__ float s_m2[4];
     __shared__ float s_red[TILE_THREADS / 32][NACC];
-    __shared__ int s_b;
+    __shared__ unsigned long long s_cov[IDS_H], s_inf[IDS_H];
+    __shared__ int s_b, s_nq;
 
     const int total = *total_tiles;
     const int tid = threadIdx.x;
-    const int lx = tid % TILE_W, ly = tid / TILE_W;
+    const int lx = tid % TILE_W, ly0 = tid / TILE_W;  // this thread's pixels: (lx, ly0 + 8k), k = 0..3
 
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        // locate the hypothesis: last b with tile_base <= item
-        if (tid == 0) {
+        if (tid == 0) {  // locate the hypothesis: last b with tile_base <= item
             int lo = 0, hi = B - 1;
             while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
+                const int mid = (lo + hi + 1) >> 1;
                 if (hyp[mid].tile_base <= item) lo = mid; else hi = mid - 1;
             }
             s_b = lo;
@@ -272,31 +230,155 @@ __global__ void __launch_bounds__(TILE_THREADS) pixel_kernel(SceneDev S, const H
         const HypState& h = hyp[b];
         if (tid < 16) s_mvp[tid] = h.mvp[tid];
         if (tid < 4) s_m2[tid] = h.m[8 + tid];
+        const int rx0 = h.rx0, ry0 = h.ry0, rx1 = h.rx1, ry1 = h.ry1;
         const int local = item - h.tile_base;
         const int tx = local % h.tiles_x, ty = local / h.tiles_x;
-        const int ox = h.rx0 + tx * TILE_W, oy = h.ry0 + ty * TILE_H;  // tile origin, frame pixels
+        const int ox = rx0 + tx * TILE_W, oy = ry0 + ty * TILE_H;  // tile origin, frame pixels
+        const float k_rgb = h.k_rgb, k_depth = h.k_depth, k_mask = h.k_mask;
         // valid z-buffer region of this hypothesis
-        const int vx0 = max(h.rx0 - 1, S.zx0), vx1 = min(h.rx1 + 1, S.zx0 + S.zw);
-        const int vy0 = max(h.ry0 - 1, S.zy0), vy1 = min(h.ry1 + 1, S.zy0 + S.zh);
+        const int vx0 = max(rx0 - 1, S.zx0), vx1 = min(rx1 + 1, S.zx0 + S.zw);
+        const int vy0 = max(ry0 - 1, S.zy0), vy1 = min(ry1 + 1, S.zy0 + S.zh);
         const unsigned long long* zb = zbuf + (size_t)b * S.zh * S.zw;
-        for (int i = tid; i < IDS_W * IDS_H; i += TILE_THREADS) {
-            const int x = ox - 2 + i % IDS_W, y = oy - 2 + i / IDS_W;
-            int id;
-            if (x < 0 || y < 0 || x >= S.W || y >= S.H) id = ID_OUTSIDE;
-            else if (x < vx0 || x >= vx1 || y < vy0 || y >= vy1) id = ID_NONE;
-            else {
-                const unsigned long long k = zb[(size_t)(y - S.zy0) * S.zw + (x - S.zx0)];
-                id = (k == EMPTY_KEY) ? ID_NONE : (int)(unsigned int)(k & 0xFFFFFFFFull);
+
+        // 1. triangle ids of tile + 2 px halo, one warp per row (row loads coalesce; all of a warp's
+        //    z-buffer loads are issued before any is consumed), plus per-row coverage / in-frame bitmasks
+        {
+            const int lane = tid & 31, warp = tid >> 5;
+            constexpr int ROWS_PER_WARP = (IDS_H + 7) / 8;
+            int idr[ROWS_PER_WARP][2];
+#pragma unroll
+            for (int k = 0; k < ROWS_PER_WARP; k++) {
+                const int iy = warp + 8 * k;
+                const int y = oy - 2 + iy;
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const int ix = lane + 32 * half;
+                    const int x = ox - 2 + ix;
+                    int id = ID_OUTSIDE;
+                    if (iy < IDS_H && ix < IDS_W && x >= 0 && y >= 0 && x < S.W && y < S.H) {
+                        id = ID_NONE;
+                        if (x >= vx0 && x < vx1 && y >= vy0 && y < vy1) {
+                            const unsigned long long key = zb[(size_t)(y - S.zy0) * S.zw + (x - S.zx0)];
+                            if (key != EMPTY_KEY) id = (int)(unsigned int)(key & 0xFFFFFFFFull);
+                        }
+                    }
+                    idr[k][half] = id;
+                }
             }
-            s_ids[i] = id;
+#pragma unroll
+            for (int k = 0; k < ROWS_PER_WARP; k++) {
+                const int iy = warp + 8 * k;
+                if (iy >= IDS_H) break;  // warp-uniform
+                const unsigned int c0 = __ballot_sync(0xffffffffu, idr[k][0] >= 0);
+                const unsigned int c1 = __ballot_sync(0xffffffffu, idr[k][1] >= 0);
+                const unsigned int f0 = __ballot_sync(0xffffffffu, idr[k][0] != ID_OUTSIDE);
+                const unsigned int f1 = __ballot_sync(0xffffffffu, idr[k][1] != ID_OUTSIDE);
+                s_ids[iy * IDS_W + lane] = idr[k][0];
+                s_di[0][iy * IDS_W + lane] = DI_NONE;
+                s_di[1][iy * IDS_W + lane] = DI_NONE;
+                if (lane < IDS_W - 32) {
+                    s_ids[iy * IDS_W + 32 + lane] = idr[k][1];
+                    s_di[0][iy * IDS_W + 32 + lane] = DI_NONE;
+                    s_di[1][iy * IDS_W + 32 + lane] = DI_NONE;
+                }
+                if (lane == 0) {
+                    s_cov[iy] = ((unsigned long long)c1 << 32) | c0;
+                    s_inf[iy] = ((unsigned long long)f1 << 32) | f0;
+                }
+            }
         }
         __syncthreads();
-        // antialiased mask over tile + 1 px halo (only where it can matter: inside the loss ROI)
+
+        // 2. silhouette pairs (exactly one pixel covered, both in the frame, at least one within the
+        //    1 px halo) -> queue, from the row bitmasks. Equal-coverage pairs blend alpha*(1-1) or
+        //    alpha*(0-0) = 0 and are skipped. One warp; the queue order is fixed (row-major, H then V).
+        if (tid < 32) {
+            constexpr unsigned long long HMASK = (1ull << (IDS_W - 1)) - 1;           // first pixel ix in [0, W-2]
+            constexpr unsigned long long VMASK = ((1ull << (IDS_W - 1)) - 1) & ~1ull;  // ix in [1, W-2]
+            unsigned long long hm[2], vm[2];
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int iy = tid + 32 * k;
+                hm[k] = vm[k] = 0ull;
+                if (iy < IDS_H) {
+                    const unsigned long long c = s_cov[iy], f = s_inf[iy];
+                    if (iy >= 1 && iy <= IDS_H - 2) hm[k] = (c ^ (c >> 1)) & f & (f >> 1) & HMASK;
+                    if (iy <= IDS_H - 2) vm[k] = (c ^ s_cov[iy + 1]) & f & s_inf[iy + 1] & VMASK;
+                }
+                cnt += __popcll(hm[k]) + __popcll(vm[k]);
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += n;
+            }
+            int pos = incl - cnt;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int iy = tid + 32 * k;
+                unsigned long long m = hm[k];
+                while (m) {
+                    const int ix = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    s_queue[pos++] = (unsigned short)(iy * IDS_W + ix);
+                }
+                m = vm[k];
+                while (m) {
+                    const int ix = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    s_queue[pos++] = (unsigned short)(0x8000 | (iy * IDS_W + ix));
+                }
+            }
+            if (tid == 31) s_nq = incl;
+        }
+        __syncthreads();
+        const int nq = s_nq;
+
+        // 3. analyse every queued pair once, one pair per thread
+        for (int q = tid; q < nq; q += TILE_THREADS) {
+            const int e = s_queue[q];
+            const int d = e >> 15, idx = e & 0x7FFF;
+            const int ix = idx % IDS_W, iy = idx / IDS_W;
+            const int jdx = d ? idx + IDS_W : idx + 1;
+            const int ida = s_ids[idx], idb = s_ids[jdx];
+            const bool first_cov = ida >= 0;
+            const int tri = first_cov ? ida : idb;
+            const int qx = ox - 2 + ix + ((first_cov || d) ? 0 : 1), qy = oy - 2 + iy + ((first_cov || !d) ? 0 : 1);
+            const AARes r = aa_analyse(S, s_mvp, tri, qx, qy, d, first_cov ? 1.f : -1.f);
+            s_alpha[d][idx] = r.alpha;
+            s_di[d][idx] = r.valid ? (unsigned char)r.di : (unsigned char)DI_NONE;
+        }
+        __syncthreads();
+
+        // 4. antialiased mask over tile + 1 px halo: coverage + the up-to-four pair blends that
+        //    target the pixel, summed in the oracle's order (left, right, lower, upper pair)
         for (int i = tid; i < MAA_W * MAA_H; i += TILE_THREADS) {
-            const int mx = i % MAA_W - 1, my = i / MAA_W - 1;
-            const int x = ox + mx, y = oy + my;
+            const int ix = i % MAA_W + 1, iy = i / MAA_W + 1;  // ids coordinates
+            const int idx = iy * IDS_W + ix;
+            const int idc = s_ids[idx];
             float m = 0.f;
-            if (x >= h.rx0 && x < h.rx1 && y >= h.ry0 && y < h.ry1) m = mask_aa_pixel(S, s_mvp, s_ids, mx, my, x, y);
+            if (idc != ID_OUTSIDE) {
+                const float c = (idc >= 0) ? 1.f : 0.f;
+                m = c;
+                if (s_di[0][idx - 1] != DI_NONE) {  // (left, self): self is second
+                    const float a = s_alpha[0][idx - 1];
+                    if (!(a > 0.f)) m = xadd(m, xmul(a, c - ((s_ids[idx - 1] >= 0) ? 1.f : 0.f)));
+                }
+                if (s_di[0][idx] != DI_NONE) {  // (self, right): self is first
+                    const float a = s_alpha[0][idx];
+                    if (a > 0.f) m = xadd(m, xmul(a, ((s_ids[idx + 1] >= 0) ? 1.f : 0.f) - c));
+                }
+                if (s_di[1][idx - IDS_W] != DI_NONE) {  // (lower, self)
+                    const float a = s_alpha[1][idx - IDS_W];
+                    if (!(a > 0.f)) m = xadd(m, xmul(a, c - ((s_ids[idx - IDS_W] >= 0) ? 1.f : 0.f)));
+                }
+                if (s_di[1][idx] != DI_NONE) {  // (self, upper)
+                    const float a = s_alpha[1][idx];
+                    if (a > 0.f) m = xadd(m, xmul(a, ((s_ids[idx + IDS_W] >= 0) ? 1.f : 0.f) - c));
+                }
+            }
             s_maa[i] = m;
         }
         __syncthreads();
@@ -305,25 +387,26 @@ __global__ void __launch_bounds__(TILE_THREADS) pixel_kernel(SceneDev S, const H
 #pragma unroll
         for (int k = 0; k < NACC; k++) acc[k] = 0.f;
 
-        const int x = ox + lx, y = oy + ly;
-        const bool inroi = (x < h.rx1 && y < h.ry1);
-        if (inroi) {
+        // 5. shading, losses and their backward, 4 pixels per thread
+        for (int rep = 0; rep < TILE_H / 8; rep++) {
+            const int ly = ly0 + 8 * rep;
+            const int x = ox + lx, y = oy + ly;
+            if (!(x < rx1 && y < ry1)) continue;
             const int id = s_ids[(ly + 2) * IDS_W + (lx + 2)];
             const float maa = s_maa[(ly + 1) * MAA_W + (lx + 1)];
             const size_t gpix = (size_t)y * S.W + x;
+            const size_t wp = ((size_t)b * S.wh + (y - S.wy0)) * S.ww + (x - S.wx0);
             float seg[3] = {1.f, 1.f, 1.f};
-            if (LOSS && S.gt_seg) {
+            if (MODE == MODE_LOSS && S.gt_seg) {
 #pragma unroll
                 for (int c = 0; c < 3; c++) seg[c] = S.gt_seg[gpix * S.seg_pix_stride + c * S.seg_ch_stride];
             }
             float rgb[3] = {0.f, 0.f, 0.f};
             float depth = -s_m2[3];
-            float ru = 0.f, rv = 0.f, rzw = 0.f;
             float gu = 0.f, gv = 0.f;  // dL/d(u,v)
-            Shade sh;
             if (id >= 0) {
+                Shade sh;
                 shade_setup(S, s_mvp, id, x, y, sh);
-                ru = sh.u; rv = sh.v; rzw = sh.zw;
                 const float b0 = sh.u, b1 = sh.v, b2 = xsub(xsub(1.f, sh.u), sh.v);
                 const float* P0 = S.pos + 3 * sh.i0;
                 const float* P1 = S.pos + 3 * sh.i1;
@@ -336,19 +419,22 @@ __global__ void __launch_bounds__(TILE_THREADS) pixel_kernel(SceneDev S, const H
                 depth = -xadd(xadd(xadd(xmul(s_m2[0], g[0]), xmul(s_m2[1], g[1])), xmul(s_m2[2], g[2])), s_m2[3]);
 
                 float gd = 0.f;  // dL/d depth
-                if (LOSS && cfg.use_depth) {
+                if (MODE == MODE_LOSS && cfg.use_depth) {
                     const float diff = (depth - S.gt_depth[gpix]) * seg[0];
                     acc[17] += fabsf(diff);
-                    gd = h.k_depth * sgn(diff) * seg[0];
+                    gd = k_depth * sgn(diff) * seg[0];
+                }
+                if (MODE == MODE_EXT && ext.d_depth) gd = ext.d_depth[wp];
+                if (MODE != MODE_RENDER && gd != 0.f) {
                     acc[12] -= gd * g[0]; acc[13] -= gd * g[1]; acc[14] -= gd * g[2]; acc[15] -= gd;
-                    // through g = sum b_i p_i
 #pragma unroll
-                    for (int k = 0; k < 3; k++) {
+                    for (int k = 0; k < 3; k++) {  // through g = sum b_i p_i
                         const float dg = -gd * s_m2[k];
                         gu += dg * (p0[k] - p2[k]);
                         gv += dg * (p1[k] - p2[k]);
                     }
                 }
+                const bool want_rgb_grad = (MODE == MODE_LOSS && cfg.use_rgb) || (MODE == MODE_EXT && ext.d_rgb);
                 if (S.tex) {
                     const float2 t0 = *reinterpret_cast<const float2*>(S.uv + 2 * sh.i0);
                     const float2 t1 = *reinterpret_cast<const float2*>(S.uv + 2 * sh.i1);
@@ -374,16 +460,21 @@ __global__ void __launch_bounds__(TILE_THREADS) pixel_kernel(SceneDev S, const H
                         const float v00 = a00[c], v10 = a10[c], v01 = a01[c], v11 = a11[c];
                         const float top = xadd(v00, xmul(xsub(v10, v00), fu)), bot = xadd(v01, xmul(xsub(v11, v01), fu));
                         rgb[c] = xadd(top, xmul(xsub(bot, top), fv));
-                        if (LOSS && cfg.use_rgb) {
-                            const float diff = (rgb[c] - S.gt_rgb[gpix * 3 + c]) * seg[c];
-                            acc[16] += fabsf(diff);
-                            const float dy = h.k_rgb * sgn(diff) * seg[c];
+                        if (want_rgb_grad) {
+                            float dy;
+                            if (MODE == MODE_LOSS) {
+                                const float diff = (rgb[c] - S.gt_rgb[gpix * 3 + c]) * seg[c];
+                                acc[16] += fabsf(diff);
+                                dy = k_rgb * sgn(diff) * seg[c];
+                            } else {
+                                dy = ext.d_rgb[wp * 3 + c];
+                            }
                             const float ad = (v11 + v00) - (v10 + v01);
                             gtu += dy * ((v10 - v00) + fv * ad);
                             gtv += dy * ((v01 - v00) + fu * ad);
                         }
                     }
-                    if (LOSS && cfg.use_rgb) {
+                    if (want_rgb_grad) {
                         gtu *= (float)S.tex_w; gtv *= (float)S.tex_h;
                         gu += gtu * (t0.x - t2.x) + gtv * (t0.y - t2.y);
                         gv += gtu * (t1.x - t2.x) + gtv * (t1.y - t2.y);
@@ -393,77 +484,94 @@ __global__ void __launch_bounds__(TILE_THREADS) pixel_kernel(SceneDev S, const H
                     for (int c = 0; c < 3; c++) {
                         const float k0 = S.vcol[3 * sh.i0 + c], k1 = S.vcol[3 * sh.i1 + c], k2 = S.vcol[3 * sh.i2 + c];
                         rgb[c] = xadd(xadd(xmul(b0, k0), xmul(b1, k1)), xmul(b2, k2));
-                        if (LOSS && cfg.use_rgb) {
-                            const float diff = (rgb[c] - S.gt_rgb[gpix * 3 + c]) * seg[c];
-                            acc[16] += fabsf(diff);
-                            const float dy = h.k_rgb * sgn(diff) * seg[c];
+                        if (want_rgb_grad) {
+                            float dy;
+                            if (MODE == MODE_LOSS) {
+                                const float diff = (rgb[c] - S.gt_rgb[gpix * 3 + c]) * seg[c];
+                                acc[16] += fabsf(diff);
+                                dy = k_rgb * sgn(diff) * seg[c];
+                            } else {
+                                dy = ext.d_rgb[wp * 3 + c];
+                            }
                             gu += dy * (k0 - k2);
                             gv += dy * (k1 - k2);
                         }
                     }
                 }
-                if (LOSS && (gu != 0.f || gv != 0.f)) raster_grad_accum(S, sh, gu, gv, acc);
-            } else if (LOSS) {
+                if (MODE != MODE_RENDER && (gu != 0.f || gv != 0.f)) raster_grad_accum(S, sh, gu, gv, acc);
+                if (MODE == MODE_RENDER && out.rast)
+                    reinterpret_cast<float4*>(out.rast)[wp] = make_float4(sh.u, sh.v, sh.zw, (float)(id + 1));
+            } else {
                 // background: rgb = 0, depth = -t_z (interpolate yields 0 where tri_id == 0)
-                if (cfg.use_depth) {
-                    const float diff = (depth - S.gt_depth[gpix]) * seg[0];
-                    acc[17] += fabsf(diff);
-                    const float gd = h.k_depth * sgn(diff) * seg[0];
-                    acc[15] -= gd;
-                }
-                if (cfg.use_rgb) {
+                if (MODE == MODE_LOSS) {
+                    if (cfg.use_depth) {
+                        const float diff = (depth - S.gt_depth[gpix]) * seg[0];
+                        acc[17] += fabsf(diff);
+                        acc[15] -= k_depth * sgn(diff) * seg[0];
+                    }
+                    if (cfg.use_rgb) {
 #pragma unroll
-                    for (int c = 0; c < 3; c++) acc[16] += fabsf((0.f - S.gt_rgb[gpix * 3 + c]) * seg[c]);
+                        for (int c = 0; c < 3; c++) acc[16] += fabsf((0.f - S.gt_rgb[gpix * 3 + c]) * seg[c]);
+                    }
                 }
+                if (MODE == MODE_EXT && ext.d_depth) acc[15] -= ext.d_depth[wp];
+                if (MODE == MODE_RENDER && out.rast) reinterpret_cast<float4*>(out.rast)[wp] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-
-            if (LOSS && cfg.use_mask) {
+            if (MODE == MODE_LOSS && cfg.use_mask) {
 #pragma unroll
                 for (int c = 0; c < 3; c++) acc[18] += fabsf(maa - seg[c]);
-                // pairs owned by this pixel: (self, right), (self, upper); plus (left, self) / (lower, self)
-                // when that neighbour lies outside the loss ROI (nobody else owns them)
-                for (int e = 0; e < 4; e++) {
-                    const int d = e >> 1, side = (e & 1);  // e: 0 left, 1 right, 2 lower, 3 upper
-                    const int nx = x + (d ? 0 : (side ? 1 : -1)), ny = y + (d ? (side ? 1 : -1) : 0);
-                    const bool nb_in_roi = (nx >= h.rx0 && nx < h.rx1 && ny >= h.ry0 && ny < h.ry1);
-                    if (side == 0 && nb_in_roi) continue;
-                    const int idn = s_ids[(ly + 2 + (ny - y)) * IDS_W + (lx + 2 + (nx - x))];
-                    PairInfo p = make_pair(id, idn, x, y, d, side);
-                    if (!p.exists) continue;
-                    AARes r = aa_analyse(S, s_mvp, p.tri, p.qx, p.qy, d, p.ds);
-                    if (!r.valid) continue;
-                    const bool target_first = r.alpha > 0.f;
-                    const bool self_first = (side == 1);
-                    const bool target_self = (target_first == self_first);
-                    const int txp = target_self ? x : nx, typ = target_self ? y : ny;
-                    if (!(txp >= h.rx0 && txp < h.rx1 && typ >= h.ry0 && typ < h.ry1)) continue;  // no loss there
-                    const float mt = target_self ? maa : s_maa[(ly + 1 + (ny - y)) * MAA_W + (lx + 1 + (nx - x))];
-                    float dd = 0.f;
-                    const size_t tp = (size_t)typ * S.W + txp;
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const float sg = S.gt_seg ? S.gt_seg[tp * S.seg_pix_stride + c * S.seg_ch_stride] : 1.f;
-                        dd += h.k_mask * sgn(mt - sg) * p.dcol;
-                    }
-                    aa_grad_accum(S, s_mvp, p.tri, p.qx, p.qy, d, r.di, r.alpha, dd, acc);
-                }
             }
-
-            if (!LOSS) {
-                const size_t wp = ((size_t)b * S.wh + (y - S.wy0)) * S.ww + (x - S.wx0);
+            if (MODE == MODE_RENDER) {
                 if (out.rgb) { out.rgb[wp * 3] = rgb[0]; out.rgb[wp * 3 + 1] = rgb[1]; out.rgb[wp * 3 + 2] = rgb[2]; }
                 if (out.depth) out.depth[wp] = depth;
                 if (out.mask) out.mask[wp] = maa;
-                if (out.rast) {
-                    float4 r4 = make_float4(ru, rv, rzw, (id >= 0) ? (float)(id + 1) : 0.f);
-                    if (id < 0) r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    reinterpret_cast<float4*>(out.rast)[wp] = r4;
-                }
             }
         }
 
-        if (LOSS) {
-            // CTA reduction of the 19 accumulators, one partial row per tile (deterministic)
+        // 6. silhouette gradients, one pair per thread. A pair is owned by the tile holding its first
+        //    pixel, or its second pixel when the first lies outside the loss ROI.
+        if ((MODE == MODE_LOSS && cfg.use_mask) || (MODE == MODE_EXT && ext.d_mask)) {
+            for (int q = tid; q < nq; q += TILE_THREADS) {
+                const int e = s_queue[q];
+                const int d = e >> 15, idx = e & 0x7FFF;
+                const int di = s_di[d][idx];
+                if (di == DI_NONE) continue;
+                const int ix = idx % IDS_W, iy = idx / IDS_W;
+                const int fx = ox - 2 + ix, fy = oy - 2 + iy;          // first pixel
+                const int sx = fx + (d ? 0 : 1), sy = fy + (d ? 1 : 0);  // second pixel
+                const bool f_roi = fx >= rx0 && fx < rx1 && fy >= ry0 && fy < ry1;
+                const bool s_roi = sx >= rx0 && sx < rx1 && sy >= ry0 && sy < ry1;
+                const bool f_tile = f_roi && fx >= ox && fx < ox + TILE_W && fy >= oy && fy < oy + TILE_H;
+                const bool s_tile = s_roi && sx >= ox && sx < ox + TILE_W && sy >= oy && sy < oy + TILE_H;
+                if (!(f_roi ? f_tile : s_tile)) continue;
+                const float alpha = s_alpha[d][idx];
+                const bool tfirst = alpha > 0.f;
+                if (!(tfirst ? f_roi : s_roi)) continue;  // target outside the window: no loss there
+                const int tx_ = tfirst ? fx : sx, ty_ = tfirst ? fy : sy;
+                const int jdx = d ? idx + IDS_W : idx + 1;
+                const int ida = s_ids[idx], idb = s_ids[jdx];
+                const bool first_cov = ida >= 0;
+                const float dcol = first_cov ? -1.f : 1.f;  // coverage(second) - coverage(first)
+                const float mt = s_maa[(ty_ - oy + 1) * MAA_W + (tx_ - ox + 1)];
+                float dd = 0.f;
+                if (MODE == MODE_LOSS) {
+                    const size_t tp = (size_t)ty_ * S.W + tx_;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float sg = S.gt_seg ? S.gt_seg[tp * S.seg_pix_stride + c * S.seg_ch_stride] : 1.f;
+                        dd += k_mask * sgn(mt - sg) * dcol;
+                    }
+                } else {
+                    dd = ext.d_mask[((size_t)b * S.wh + (ty_ - S.wy0)) * S.ww + (tx_ - S.wx0)] * dcol;
+                }
+                const int tri = first_cov ? ida : idb;
+                const int qx = first_cov ? fx : sx, qy = first_cov ? fy : sy;
+                aa_grad_accum(S, s_mvp, tri, qx, qy, d, di, alpha, dd, acc);
+            }
+        }
+
+        if (MODE != MODE_RENDER) {
+            // 7. CTA reduction of the accumulators, one partial row per tile (fixed order: deterministic)
 #pragma unroll
             for (int k = 0; k < NACC - 1; k++) {
                 float v = acc[k];
@@ -485,7 +593,7 @@ __global__ void __launch_bounds__(TILE_THREADS) pixel_kernel(SceneDev S, const H
 }
 
 static int pixel_grid(int max_tiles, int num_sms) {
-    int g = num_sms * 6;
+    int g = num_sms * 4;
     if (g > max_tiles) g = max_tiles;
     return g < 1 ? 1 : g;
 }
@@ -493,13 +601,25 @@ static int pixel_grid(int max_tiles, int num_sms) {
 void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                        LossCfgDev cfg, const unsigned long long* zbuf, float* partials, int num_sms, cudaStream_t st) {
     RenderOut none = {nullptr, nullptr, nullptr, nullptr};
-    pixel_kernel<true><<<pixel_grid(max_tiles, num_sms), TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf, partials, none);
+    ExtGrad noext = {nullptr, nullptr, nullptr};
+    pixel_kernel<MODE_LOSS><<<pixel_grid(max_tiles, num_sms), TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf,
+                                                                                    partials, none, noext);
 }
 
 void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                          const unsigned long long* zbuf, RenderOut out, int num_sms, cudaStream_t st) {
     LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f};
-    pixel_kernel<false><<<pixel_grid(max_tiles, num_sms), TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf, nullptr, out);
+    ExtGrad noext = {nullptr, nullptr, nullptr};
+    pixel_kernel<MODE_RENDER><<<pixel_grid(max_tiles, num_sms), TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf,
+                                                                                      nullptr, out, noext);
+}
+
+void launch_pixel_ext(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
+                      const unsigned long long* zbuf, ExtGrad ext, float* partials, int num_sms, cudaStream_t st) {
+    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f};
+    RenderOut none = {nullptr, nullptr, nullptr, nullptr};
+    pixel_kernel<MODE_EXT><<<pixel_grid(max_tiles, num_sms), TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf,
+                                                                                   partials, none, ext);
 }
 
 }  // namespace ddope

@@ -39,6 +39,7 @@ __device__ void canonical_mvp(const float* P, const float* M, float* out) {
 
 __global__ void __launch_bounds__(256) pose_kernel(SceneDev S, const float* __restrict__ quat,
                                                    const float* __restrict__ trans,
+                                                   const float* __restrict__ mtx_in,
                                                    const float* __restrict__ lr_mult, int B, int B_global,
                                                    LossCfgDev cfg, int roi_mode, HypState* __restrict__ hyp,
                                                    int* __restrict__ total_tiles) {
@@ -52,9 +53,14 @@ __global__ void __launch_bounds__(256) pose_kernel(SceneDev S, const float* __re
         int ntiles = 0;
         if (b < B) {
             HypState h;
-            float q[4] = {quat[4 * b], quat[4 * b + 1], quat[4 * b + 2], quat[4 * b + 3]};
-            float t[3] = {trans[3 * b], trans[3 * b + 1], trans[3 * b + 2]};
-            canonical_pose(q, t, h.qhat, &h.qnorm, h.m);
+            if (mtx_in) {
+                for (int k = 0; k < 16; k++) h.m[k] = mtx_in[16 * b + k];
+                h.qhat[0] = h.qhat[1] = h.qhat[2] = 0.f; h.qhat[3] = 1.f; h.qnorm = 1.f;
+            } else {
+                float q[4] = {quat[4 * b], quat[4 * b + 1], quat[4 * b + 2], quat[4 * b + 3]};
+                float t[3] = {trans[3 * b], trans[3 * b + 1], trans[3 * b + 2]};
+                canonical_pose(q, t, h.qhat, &h.qnorm, h.m);
+            }
             canonical_mvp(S.proj, h.m, h.mvp);
 
             int x0 = S.wx0, y0 = S.wy0, x1 = S.wx0 + S.ww, y1 = S.wy0 + S.wh;  // window, exclusive end
@@ -122,9 +128,9 @@ __global__ void __launch_bounds__(256) pose_kernel(SceneDev S, const float* __re
     if (threadIdx.x == 0) *total_tiles = s_carry;
 }
 
-void launch_pose(const SceneDev& S, const float* quat, const float* trans, const float* lr_mult, int B,
-                 int B_global, LossCfgDev cfg, int roi_mode, HypState* hyp, int* total_tiles, cudaStream_t st) {
-    pose_kernel<<<1, 256, 0, st>>>(S, quat, trans, lr_mult, B, B_global, cfg, roi_mode, hyp, total_tiles);
+void launch_pose(const SceneDev& S, const float* quat, const float* trans, const float* mtx_in, const float* lr_mult,
+                 int B, int B_global, LossCfgDev cfg, int roi_mode, HypState* hyp, int* total_tiles, cudaStream_t st) {
+    pose_kernel<<<1, 256, 0, st>>>(S, quat, trans, mtx_in, lr_mult, B, B_global, cfg, roi_mode, hyp, total_tiles);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -134,7 +140,8 @@ __global__ void __launch_bounds__(128) step_kernel(SceneDev S, const HypState* _
                                                    float* __restrict__ quat, float* __restrict__ trans,
                                                    const float* __restrict__ lr_sched, int it, int do_update,
                                                    float* __restrict__ loss_table, float* __restrict__ grad_out,
-                                                   float* __restrict__ pose_hist, float* __restrict__ loss_hist) {
+                                                   float* __restrict__ pose_hist, float* __restrict__ loss_hist,
+                                                   float* __restrict__ dmtx_out) {
     const int b = blockIdx.x;
     const HypState& h = hyp[b];
     const int n_items = h.tiles_x * h.tiles_y;
@@ -176,6 +183,12 @@ __global__ void __launch_bounds__(128) step_kernel(SceneDev S, const HypState* _
 #pragma unroll
     for (int c = 0; c < 4; c++) dM[2][c] += a[12 + c];
 
+    if (dmtx_out) {  // gradient w.r.t. an explicitly given M (ddope_render_bwd); the bottom row is constant
+        for (int k = 0; k < 3; k++)
+            for (int c = 0; c < 4; c++) dmtx_out[16 * b + 4 * k + c] = dM[k][c];
+        for (int c = 0; c < 4; c++) dmtx_out[16 * b + 12 + c] = 0.f;
+        return;
+    }
     const float x = h.qhat[0], y = h.qhat[1], z = h.qhat[2], w = h.qhat[3];
     float gx = 2.f * (y * dM[0][1] + z * dM[0][2] + y * dM[1][0] - 2.f * x * dM[1][1] - w * dM[1][2] + z * dM[2][0] + w * dM[2][1] - 2.f * x * dM[2][2]);
     float gy = 2.f * (-2.f * y * dM[0][0] + x * dM[0][1] + w * dM[0][2] + x * dM[1][0] + z * dM[1][2] - w * dM[2][0] + z * dM[2][1] - 2.f * y * dM[2][2]);
@@ -218,9 +231,9 @@ __global__ void __launch_bounds__(128) step_kernel(SceneDev S, const HypState* _
 
 void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg,
                  float* quat, float* trans, const float* lr_sched, int it, int do_update, float* loss_table,
-                 float* grad_out, float* pose_hist, float* loss_hist, cudaStream_t st) {
+                 float* grad_out, float* pose_hist, float* loss_hist, float* dmtx_out, cudaStream_t st) {
     step_kernel<<<B, 128, 0, st>>>(S, hyp, partials, B, cfg, quat, trans, lr_sched, it, do_update, loss_table,
-                                   grad_out, pose_hist, loss_hist);
+                                   grad_out, pose_hist, loss_hist, dmtx_out);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,58 @@
+"""Hypothesis sharding across the GPUs of one box.
+
+Hypotheses are independent, so rank r of G refines the contiguous block
+[lo, hi) of the B hypotheses with the *global* B kept in the loss-mean divisor; the only
+communication is one all-gather of the per-hypothesis tables at the end of the run, after
+which every rank holds the same full tables and computes the same argmin.
+With `torch.distributed` uninitialised (or world_size 1) everything is a no-op."""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(B, rank, world_size):
+    """Contiguous block of ceil(B/G) hypotheses per rank, in hypothesis order (so the
+    reference's sequential random.uniform learning-rate draws map identically)."""
+    per = (B + world_size - 1) // world_size
+    lo = min(rank * per, B)
+    return lo, min(lo + per, B)
+
+
+def shard_range(B):
+    rank, ws = world()
+    return shard_bounds(B, rank, ws)
+
+
+def _gather_dim(t_local, B, dim, per, ws):
+    """all_gather equally padded shards along `dim`, trim to B."""
+    pad = per - t_local.shape[dim]
+    if pad > 0:
+        shape = list(t_local.shape)
+        shape[dim] = pad
+        t_local = torch.cat([t_local, t_local.new_zeros(shape)], dim=dim)
+    t_local = t_local.contiguous()
+    parts = [torch.empty_like(t_local) for _ in range(ws)]
+    dist.all_gather(parts, t_local)
+    return torch.cat(parts, dim=dim).narrow(dim, 0, B).contiguous()
+
+
+def gather_hypotheses(B, pose_hist, loss_hist, final):
+    """pose_hist [n,Bl,7], loss_hist [n,Bl,3], final [Bl,7] -> global [n,B,7], [n,B,3], [B,7]."""
+    rank, ws = world()
+    if ws == 1:
+        return pose_hist, loss_hist, final
+    per = (B + ws - 1) // ws
+    return (_gather_dim(pose_hist, B, 1, per, ws), _gather_dim(loss_hist, B, 1, per, ws), _gather_dim(final, B, 0, per, ws))
+
+
+def broadcast_from_rank0(t):
+    """Make rank 0's tensor (e.g. the randomly drawn learning-rate multipliers) the job's."""
+    rank, ws = world()
+    if ws > 1:
+        dist.broadcast(t, src=0)
+    return t

@@ -58,12 +58,14 @@ def lib():
     L.ddope_scene_set_target.argtypes = [vp, vp, vp, vp, ci, vp]
     L.ddope_scene_set_window.argtypes = [vp, ci, ci, ci, ci]
     L.ddope_render.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
+    L.ddope_render_mtx.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
+    L.ddope_render_bwd.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
     L.ddope_loss_grad.argtypes = [vp, vp, vp, vp, ci, ci, ctypes.POINTER(LossCfg), vp, vp, vp]
     L.ddope_optimize.argtypes = [vp, vp, vp, vp, ci, ci, vp, ci, ctypes.POINTER(LossCfg), vp, vp, vp]
     for name in (
         "ddope_xfm_fwd", "ddope_xfm_bwd", "ddope_xfm_bwd_mtx", "ddope_xfm_bwd_full", "ddope_scene_create",
         "ddope_scene_destroy", "ddope_scene_set_camera", "ddope_scene_set_target", "ddope_scene_set_window",
-        "ddope_render", "ddope_loss_grad", "ddope_optimize",
+        "ddope_render", "ddope_render_mtx", "ddope_render_bwd", "ddope_loss_grad", "ddope_optimize",
     ):
         getattr(L, name).restype = ci
     if L.ddope_abi_version() != 1:
@@ -192,6 +194,29 @@ class NativeScene:
         _check(lib().ddope_render(self._h, _ptr(quat), _ptr(trans), B, _ptr(out.get("rgb")), _ptr(out.get("depth")),
                                   _ptr(out.get("mask")), _ptr(out.get("rast")), _ptr(out.get("mtx")), _stream()))
         return out
+
+    def render_mtx(self, mtx, want_rast=True):
+        """Render from explicit model matrices [B,4,4]. Returns rgb, depth, mask [B,h,w], rast."""
+        mtx = _dev_f32(mtx, "mtx")
+        B = mtx.shape[0]
+        _, _, h, w = self.window
+        dev = mtx.device
+        rgb = torch.empty(B, h, w, 3, device=dev)
+        depth = torch.empty(B, h, w, device=dev)
+        mask = torch.empty(B, h, w, device=dev)
+        rast = torch.empty(B, h, w, 4, device=dev) if want_rast else None
+        _check(lib().ddope_render_mtx(self._h, _ptr(mtx), B, _ptr(rgb), _ptr(depth), _ptr(mask), _ptr(rast), _stream()))
+        return rgb, depth, mask, rast
+
+    def render_bwd(self, mtx, d_rgb=None, d_depth=None, d_mask=None):
+        mtx = _dev_f32(mtx, "mtx")
+        B = mtx.shape[0]
+        d_rgb = None if d_rgb is None else _dev_f32(d_rgb, "d_rgb")
+        d_depth = None if d_depth is None else _dev_f32(d_depth, "d_depth")
+        d_mask = None if d_mask is None else _dev_f32(d_mask, "d_mask")
+        d_mtx = torch.empty(B, 4, 4, device=mtx.device)
+        _check(lib().ddope_render_bwd(self._h, _ptr(mtx), B, _ptr(d_rgb), _ptr(d_depth), _ptr(d_mask), _ptr(d_mtx), _stream()))
+        return d_mtx
 
     def loss_grad(self, quat, trans, lr_mult, cfg, b_global=None):
         quat, trans = _dev_f32(quat, "quat"), _dev_f32(trans, "trans")

@@ -124,6 +124,19 @@ int ddope_render(ddope_scene* s, const float* quat_dev, const float* trans_dev, 
                  float* rgb_dev, float* depth_dev, float* mask_dev, float* rast_dev,
                  float* mtx_dev, void* stream);
 
+/* render_texture_batch itself (diffdope.py:156-234): same as ddope_render but from explicit model
+ * matrices mtx [B,4,4] (the function's `mtx` argument), for callers that build the pose matrix in
+ * torch and write their own losses (the reference invites that, diffdope.py:1280-1283). */
+int ddope_render_mtx(ddope_scene* s, const float* mtx_dev, int B, float* rgb_dev, float* depth_dev,
+                     float* mask_dev, float* rast_dev, void* stream);
+
+/* Backward of ddope_render_mtx: what loss.backward() runs through dr.antialias / dr.texture /
+ * dr.interpolate / dr.rasterize / xfm_points down to `mtx` (diffdope.py:1713). Inputs are
+ * dL/d rgb [B,h,w,3], dL/d depth [B,h,w], dL/d mask [B,h,w] (sum over the reference's three equal
+ * mask channels); any may be NULL. Output d_mtx [B,4,4] (bottom row zero). */
+int ddope_render_bwd(ddope_scene* s, const float* mtx_dev, int B, const float* d_rgb_dev,
+                     const float* d_depth_dev, const float* d_mask_dev, float* d_mtx_dev, void* stream);
+
 /* One forward + loss + backward without a parameter update: the gradient autograd
  * produces at diffdope.py:1713 for loss = sum_k w_k * mean_b(lr_b * mean_px |.|)
  * (diffdope.py:534-613). B_global is the divisor of mean_b (the whole job's hypothesis

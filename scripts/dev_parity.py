@@ -34,3 +34,18 @@ print('loss gpu',loss.cpu().numpy()); print('loss ora',np.stack([logged['rgb'].n
 print('grad gpu',grad.cpu().numpy()); print('grad ora',np.concatenate([gq,gtr],1))
 go=np.concatenate([gq,gtr],1); gg=grad.cpu().numpy()
 print('grad rel err', np.abs(go-gg).max()/np.abs(go).max())
+# --- autograd path: render_texture_batch + torch losses vs oracle gradient
+import diffdope as dd
+qt=torch.from_numpy(qs).to(dev).requires_grad_(True); tt=torch.from_numpy(ts).to(dev).requires_grad_(True)
+qn=qt/torch.norm(qt,dim=1).reshape(-1,1)
+mtx=dd.matrix_batch_44_from_position_quat(qn,tt)
+proj=torch.from_numpy(P.astype(np.float32)).to(dev)
+rr=dd.render_texture_batch(None,proj,mtx,torch.from_numpy(arr['pos']).to(dev),torch.from_numpy(arr['tri']).to(dev),[H,W],uv=torch.from_numpy(arr['uv']).to(dev),tex=torch.from_numpy(arr['tex']).to(dev))
+lrt=torch.from_numpy(lr).to(dev)
+seg=g['segmentation'][None]
+l=(torch.mean(torch.abs((rr['rgb']-g['rgb'][None])*seg),(1,2,3))*lrt).mean()*0.7
+l=l+(torch.mean(torch.abs((rr['depth']-g['depth'][None])*seg[...,0]),(1,2))*lrt).mean()
+l=l+(torch.mean(torch.abs(rr['mask']-seg),(1,2,3))*lrt).mean()
+l.backward()
+ga=torch.cat([qt.grad,tt.grad],1).cpu().numpy()
+print('autograd-path grad rel err', np.abs(go-ga).max()/np.abs(go).max())
