@@ -46,6 +46,8 @@ struct ddope_scene {
     float* xfm_scratch = nullptr;
     int num_sms = 148;
     int64_t launches = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // 6 per iteration: before pose, after pose, clear, raster, pixel, step
 };
 
 extern "C" int ddope_abi_version(void) { return DDOPE_ABI_VERSION; }
@@ -344,12 +346,25 @@ extern "C" int ddope_render_bwd(ddope_scene* s, const float* mtx_in, int B, cons
 static void enqueue_iteration(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
                               LossCfgDev cfg, int it, int do_update, float* loss_table, float* grad,
                               float* pose_hist, float* loss_hist, cudaStream_t st) {
+    auto mark = [&]() {
+        if (!s->profiling) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        s->prof_events.push_back(e);
+    };
+    mark();
     launch_pose(s->dev, quat, trans, nullptr, lr_mult, B, B_global, cfg, 1, s->hyp, s->total_tiles, st);
+    mark();
     launch_clear(s->dev, s->hyp, B, s->zbuf, st);
+    mark();
     launch_raster(s->dev, s->hyp, B, s->zbuf, st);
+    mark();
     launch_pixel_loss(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), cfg, s->zbuf, s->partials, s->num_sms, st);
+    mark();
     launch_step(s->dev, s->hyp, s->partials, B, cfg, quat, trans, s->lr_sched, it, do_update, loss_table, grad,
                 pose_hist, loss_hist, nullptr, st);
+    mark();
     s->launches += 5;
 }
 
@@ -388,5 +403,34 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     for (int it = 0; it < n_iters; it++)
         enqueue_iteration(s, quat, trans, lr_mult, B, B_global, c, it, 1, nullptr, nullptr, pose_hist, loss_hist, st);
     CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers)
+
+extern "C" int ddope_profile_begin(ddope_scene* s) {
+    if (!s) return fail("ddope_profile_begin: null scene");
+    for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
+    s->prof_events.clear();
+    s->profiling = true;
+    return 0;
+}
+
+extern "C" int ddope_profile_end(ddope_scene* s, float* ms_out5, int* iterations_out) {
+    if (!s || !ms_out5) return fail("ddope_profile_end: null pointer");
+    s->profiling = false;
+    const size_t n = s->prof_events.size() / 6;
+    for (int k = 0; k < 5; k++) ms_out5[k] = 0.f;
+    if (n > 0) CK(cudaEventSynchronize(s->prof_events.back()));
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < 5; k++) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, s->prof_events[6 * i + k], s->prof_events[6 * i + k + 1]));
+            ms_out5[k] += ms;
+        }
+    for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
+    s->prof_events.clear();
+    if (iterations_out) *iterations_out = (int)n;
     return 0;
 }

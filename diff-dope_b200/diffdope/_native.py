@@ -60,12 +60,15 @@ def lib():
     L.ddope_render.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
     L.ddope_render_mtx.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
     L.ddope_render_bwd.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
+    L.ddope_profile_begin.argtypes = [vp]
+    L.ddope_profile_end.argtypes = [vp, vp, vp]
     L.ddope_loss_grad.argtypes = [vp, vp, vp, vp, ci, ci, ctypes.POINTER(LossCfg), vp, vp, vp]
     L.ddope_optimize.argtypes = [vp, vp, vp, vp, ci, ci, vp, ci, ctypes.POINTER(LossCfg), vp, vp, vp]
     for name in (
         "ddope_xfm_fwd", "ddope_xfm_bwd", "ddope_xfm_bwd_mtx", "ddope_xfm_bwd_full", "ddope_scene_create",
         "ddope_scene_destroy", "ddope_scene_set_camera", "ddope_scene_set_target", "ddope_scene_set_window",
         "ddope_render", "ddope_render_mtx", "ddope_render_bwd", "ddope_loss_grad", "ddope_optimize",
+        "ddope_profile_begin", "ddope_profile_end",
     ):
         getattr(L, name).restype = ci
     if L.ddope_abi_version() != 1:
@@ -178,6 +181,8 @@ class NativeScene:
     def render(self, quat, trans, want=("rgb", "depth", "mask", "rast", "mtx")):
         quat, trans = _dev_f32(quat, "quat"), _dev_f32(trans, "trans")
         B = quat.shape[0]
+        if self.window is None:
+            raise RuntimeError("ddope_b200: set the camera first")
         _, _, h, w = self.window
         dev = quat.device
         out = {}
@@ -199,6 +204,8 @@ class NativeScene:
         """Render from explicit model matrices [B,4,4]. Returns rgb, depth, mask [B,h,w], rast."""
         mtx = _dev_f32(mtx, "mtx")
         B = mtx.shape[0]
+        if self.window is None:
+            raise RuntimeError("ddope_b200: set the camera first")
         _, _, h, w = self.window
         dev = mtx.device
         rgb = torch.empty(B, h, w, 3, device=dev)
@@ -244,6 +251,18 @@ class NativeScene:
         _check(lib().ddope_optimize(self._h, _ptr(quat), _ptr(trans), _ptr(lr_mult), B, int(b_global or B), _hptr(sched), n,
                                     ctypes.byref(cfg), _ptr(pose_hist), _ptr(loss_hist), _stream()))
         return pose_hist, loss_hist
+
+    KERNELS = ("pose_kernel", "clear_kernel", "raster_kernel", "pixel_kernel", "step_kernel")
+
+    def profile_begin(self):
+        _check(lib().ddope_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> ({kernel: total ms}, iterations) for the iterations enqueued since profile_begin()."""
+        ms = (ctypes.c_float * 5)()
+        n = ctypes.c_int(0)
+        _check(lib().ddope_profile_end(self._h, ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(ctypes.byref(n), ctypes.c_void_p)))
+        return {k: float(ms[i]) for i, k in enumerate(self.KERNELS)}, int(n.value)
 
     def last_launch_count(self):
         return int(lib().ddope_last_launch_count(self._h))

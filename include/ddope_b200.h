@@ -159,6 +159,14 @@ int ddope_optimize(ddope_scene* s, float* quat_dev, float* trans_dev, const floa
  * scene launched (for bench.py's gpu_launches). */
 int64_t ddope_last_launch_count(const ddope_scene* s);
 
+/* Measurement hook (no reference counterpart; the reference has no timing code):
+ * between begin and end, every iteration enqueued by ddope_loss_grad / ddope_optimize is bracketed
+ * by CUDA events on the launching stream, per kernel. end() synchronises and returns the summed
+ * milliseconds of the five kernels of an iteration in launch order
+ * {pose, clear, raster, pixel, step} and the number of iterations covered. */
+int ddope_profile_begin(ddope_scene* s);
+int ddope_profile_end(ddope_scene* s, float* ms_out5, int* iterations_out);
+
 #ifdef __cplusplus
 }
 #endif

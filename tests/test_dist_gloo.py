@@ -1,0 +1,45 @@
+"""CPU, world_size 2, gloo: the multi-GPU host logic (shard, all-gather of the result tables)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import scene_util as su
+
+
+def _worker(rank, world, port, B, out_dir):
+    sys.path.insert(0, os.path.join(su.ROOT, "diff-dope_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from diffdope import _dist
+
+    lo, hi = _dist.shard_range(B)
+    n = 3
+    pose = torch.arange(n * B * 7, dtype=torch.float32).reshape(n, B, 7)[:, lo:hi].contiguous()
+    loss = torch.arange(n * B * 3, dtype=torch.float32).reshape(n, B, 3)[:, lo:hi].contiguous() * 0.5
+    final = torch.arange(B * 7, dtype=torch.float32).reshape(B, 7)[lo:hi].contiguous() + 100
+    P, L, F = _dist.gather_hypotheses(B, pose, loss, final)
+    lr = torch.full((B,), float(rank + 1))
+    _dist.broadcast_from_rank0(lr)
+    torch.save({"P": P, "L": L, "F": F, "lr": lr, "range": (lo, hi)}, os.path.join(out_dir, "r%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_gather_hypotheses_world2(tmp_path):
+    for B in (8, 7):
+        port = 29500 + (os.getpid() + B) % 2000
+        mp.spawn(_worker, args=(2, port, B, str(tmp_path)), nprocs=2, join=True)
+        res = [torch.load(os.path.join(tmp_path, "r%d.pt" % r)) for r in range(2)]
+        n = 3
+        P = torch.arange(n * B * 7, dtype=torch.float32).reshape(n, B, 7)
+        L = torch.arange(n * B * 3, dtype=torch.float32).reshape(n, B, 3) * 0.5
+        F = torch.arange(B * 7, dtype=torch.float32).reshape(B, 7) + 100
+        for r in res:
+            assert torch.equal(r["P"], P) and torch.equal(r["L"], L) and torch.equal(r["F"], F)
+            assert torch.all(r["lr"] == 1.0)  # rank 0's draw is the job's
+        assert res[0]["range"][0] == 0 and res[0]["range"][1] == res[1]["range"][0] and res[1]["range"][1] == B
+        # every rank computes the same argmin from the gathered table
+        assert int(res[0]["L"][-1].mean(-1).argmin()) == int(res[1]["L"][-1].mean(-1).argmin())

@@ -1,0 +1,161 @@
+"""GPU (-m gpu): the reference-facing Python API end to end (DiffDope / Scene / Object3D / Camera,
+Hydra-style config), the autograd path for user-written losses, and the example script."""
+import os
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import scene_util as su
+
+pytestmark = pytest.mark.gpu
+ROOT = su.ROOT
+
+
+def _cfg(**over):
+    import diffdope  # noqa: F401
+    from omegaconf import OmegaConf
+
+    cfg = OmegaConf.load(os.path.join(ROOT, "configs", "diffdope.yaml"))
+    for k in ("path_img", "path_depth", "path_segmentation"):
+        cfg.scene[k] = os.path.join(ROOT, cfg.scene[k])
+    cfg.object3d.model_path = os.path.join(ROOT, cfg.object3d.model_path)
+    for k, v in over.items():
+        OmegaConf.update(cfg, k, v)
+    return cfg
+
+
+def test_diffdope_default_config_matches_oracle():
+    """configs/diffdope.yaml as shipped (mask loss only, B=8 -> here 3, 960x540), 10 iterations,
+    learning-rate multipliers seeded like SURVEY.md 8(d): per-iteration losses and final pose vs the oracle."""
+    import diffdope as dd
+    from oracle import refpath
+
+    cfg = _cfg(**{"hyperparameters.batchsize": 3, "hyperparameters.nb_iterations": 9})
+    random.seed(0)
+    ddope = dd.DiffDope(cfg=cfg)
+    assert np.allclose(ddope.learning_rates.cpu().numpy(), su.lr_multipliers(3))
+    ddope.run_optimization()
+    assert list(ddope.losses_values.keys()) == ["mask_selection"] and tuple(ddope.losses_values["mask_selection"].shape) == (10, 3)
+    assert len(ddope.optimization_results) == 10
+    arr, (q, t), gt = su.example_mesh_arrays(), su.example_pose(), su.example_targets(0.5)
+    mesh = refpath.Mesh(arr["pos"], arr["tri"], arr["uv"], arr["tex"])
+    hyper = dict(nb_iterations=9, base_lr=20, lr_decay=0.1, learning_rate_base=1)
+    o = refpath.run_optimization(mesh, su.projection(), np.tile(q, (3, 1)), np.tile(t, (3, 1)), {k: torch.from_numpy(v) for k, v in gt.items()},
+                                 su.lr_multipliers(3), dict(l1_mask=True, weight_mask=1), hyper, 540, 960)
+    ours, ref = ddope.losses_values["mask_selection"].numpy(), o["losses"]["mask_selection"]
+    # the multipliers are 84x / 76x / 42x: late iterations of the large-step hypotheses are chaotic (the
+    # reference itself is not run-to-run reproducible there: unordered atomics),
+    # so the trajectory is compared tightly while it is well conditioned and by final pose after that
+    assert np.allclose(ours[:6], ref[:6], rtol=5e-4)
+    assert np.allclose(ours, ref, rtol=0.06)
+    assert int(ddope.get_argmin()) == refpath.argmin_hypothesis(o["losses"])
+    best = int(ddope.get_argmin())
+    assert np.allclose(ddope.get_pose(), o["mtx"][-1][best], atol=1e-3)
+    qf, tf = ddope.object3d.pose_tensors()
+    assert np.abs(tf.cpu().numpy()[best] - o["final"][best, 4:]).max() < 1e-3  # 0.1 mm
+    qo = o["final"][best, :4]
+    qg = qf.cpu().numpy()[best]
+    cosang = abs(float((qo / np.linalg.norm(qo)) @ (qg / np.linalg.norm(qg))))
+    assert np.degrees(2 * np.arccos(min(cosang, 1.0))) < 0.1
+    # lazily re-rendered history entry equals a direct render of that iteration's pose
+    res = ddope.optimization_results[-1]
+    assert tuple(res["rgb"].shape) == (3, 540, 960, 3) and tuple(res["depth"].shape) == (3, 540, 960) and tuple(res["mask"].shape) == (3, 540, 960, 3)
+    img = ddope.render_img()
+    assert img.ndim == 3 and img.shape[2] == 3 and img.dtype == np.uint8
+    single = ddope.render_img(index=3, batch_index=1)
+    assert single.ndim == 3
+    plot = ddope.plot_losses()
+    assert plot.shape == (600, 1000, 3)
+
+
+def test_user_loss_through_autograd_matches_fused_path():
+    """A hand-written torch loss equal to the built-in stack, appended as a custom function, goes
+    through render_texture_batch's CUDA backward and must give the fused path's trajectory."""
+    import diffdope as dd
+
+    cfg = _cfg(**{"hyperparameters.batchsize": 2, "hyperparameters.nb_iterations": 5, "losses.l1_rgb_with_mask": True, "losses.l1_depth_with_mask": True,
+                  "hyperparameters.learning_rates_bound": [0.1, 0.3]})  # non-chaotic regime, see test_gpu_parity
+    random.seed(0)
+    a = dd.DiffDope(cfg=cfg)
+    a.run_optimization()
+    random.seed(0)
+    b = dd.DiffDope(cfg=cfg)
+
+    def my_loss(d):
+        seg = d.gt_tensors["segmentation"]
+        l = dd.dist_batch_lr(torch.abs((d.renders["rgb"] - d.gt_tensors["rgb"]) * seg), d.learning_rates).mean() * 0.7
+        l = l + dd.dist_batch_lr(torch.abs((d.renders["depth"] - d.gt_tensors["depth"]) * seg[..., 0]), d.learning_rates, [1, 2]).mean()
+        diff = torch.abs(d.renders["mask"] - seg)
+        d.add_loss_value("mine", torch.mean(diff.detach(), (1, 2, 3)))
+        return l + dd.dist_batch_lr(diff, d.learning_rates).mean()
+
+    b.loss_functions = [my_loss]
+    b.run_optimization()
+    qa, ta = a.object3d.pose_tensors()
+    qb, tb = b.object3d.pose_tensors()
+    assert np.abs((ta - tb).cpu().numpy()).max() < 1e-3 and np.abs((qa - qb).cpu().numpy()).max() < 1e-3
+    assert np.allclose(b.losses_values["mine"].numpy(), a.losses_values["mask_selection"].numpy(), rtol=2e-3)
+    assert isinstance(b.optimization_results[-1], dict) and tuple(b.optimization_results[-1]["rgb"].shape) == (2, 540, 960, 3)
+
+
+def test_render_texture_batch_gradient_matches_oracle():
+    import diffdope as dd
+    from oracle import refpath
+
+    arr, (q, t), gt = su.example_mesh_arrays(), su.example_pose(), su.example_targets(0.25)
+    H, W = gt["rgb"].shape[:2]
+    qs, ts = su.perturbed_poses(q, t, 2)
+    # feed the canonical matrices so both sides rasterise exactly the same geometry
+    from oracle import nvdr
+
+    _, M = nvdr.canonical_pose(qs, ts)
+    mtx = torch.from_numpy(M).cuda().requires_grad_(True)
+    dev = "cuda"
+    rr = dd.render_texture_batch(None, torch.from_numpy(su.projection().astype(np.float32)).to(dev), mtx, torch.from_numpy(arr["pos"]).to(dev),
+                                 torch.from_numpy(arr["tri"]).to(dev), [H, W], uv=torch.from_numpy(arr["uv"]).to(dev), tex=torch.from_numpy(arr["tex"]).to(dev))
+    g = {k: torch.from_numpy(v).to(dev) for k, v in gt.items()}
+    wr, wd, wm = torch.rand(2, H, W, 3, device=dev), torch.rand(2, H, W, device=dev), torch.rand(2, H, W, 3, device=dev)
+    ((rr["rgb"] * wr).sum() + (rr["depth"] * wd).sum() + (rr["mask"] * wm).sum()).backward()
+    mt = torch.from_numpy(M).requires_grad_(True)
+    mesh = refpath.Mesh(arr["pos"], arr["tri"], arr["uv"], arr["tex"])
+    # oracle with an explicit matrix: reuse its graph below the pose
+    proj_t = torch.from_numpy(su.projection().astype(np.float32))
+    mvp = refpath._with_value(torch.matmul(proj_t.expand(2, 4, 4), mt), nvdr.canonical_mvp(su.projection(), M))
+    pos = torch.from_numpy(mesh.pos)
+    pos_clip = refpath.xfm_points(pos[None].expand(2, -1, -1), mvp)
+    rast = refpath._Rasterize.apply(pos_clip, mesh.tri, H, W)
+    gb = refpath._Interpolate.apply(torch.cat([pos, torch.ones(pos.shape[0], 1)], 1), rast, mesh.tri)
+    depth = refpath.xfm_points(gb.reshape(2, -1, 4)[..., :3], mt).reshape(2, H, W, 4)[..., 2] * -1
+    mask = refpath._Antialias.apply(refpath._Interpolate.apply(torch.ones(pos.shape[0], 3), rast, mesh.tri), rast, pos_clip, mesh.tri, mesh.opp)
+    color = refpath._TextureLinear.apply(torch.from_numpy(mesh.tex), refpath._Interpolate.apply(torch.from_numpy(mesh.uv), rast, mesh.tri))
+    color = color * torch.clamp(rast[..., -1:], 0, 1)
+    ((color * wr.cpu()).sum() + (depth * wd.cpu()).sum() + (mask * wm.cpu()).sum()).backward()
+    go, gg = mt.grad.numpy(), mtx.grad.cpu().numpy()
+    assert np.abs(go - gg).max() <= 2e-4 * np.abs(go).max()
+    assert np.array_equal(rr["rgb"].detach().cpu().numpy(), color.detach().numpy())
+
+
+def test_example_script_runs(tmp_path):
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "diff-dope_b200"))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "simple_scene.py"), "hyperparameters.nb_iterations=6", "hyperparameters.batchsize=4",
+                          "hydra.run.dir=%s" % tmp_path], capture_output=True, text=True, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "best hypothesis" in out.stdout
+    for f in ("plot.png", "simple_scene.mp4"):
+        p = os.path.join(ROOT, f)
+        assert os.path.exists(p) and os.path.getsize(p) > 1000
+        os.remove(p)
+
+
+def test_reference_example_runs_unchanged_when_present():
+    ref = "/root/reference/examples/simple_scene.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not on this box")
+    # the reference script imports hydra before diffdope: the stand-ins must be importable up front
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "diff-dope_b200"), os.path.join(ROOT, "diff-dope_b200", "compat")]))
+    out = subprocess.run([sys.executable, ref, "hyperparameters.nb_iterations=3"], capture_output=True, text=True, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]

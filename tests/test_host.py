@@ -1,0 +1,219 @@
+"""CPU: host-side logic, the C-ABI library's exported surface, API import without a GPU."""
+import ctypes
+import os
+import re
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import scene_util as su
+
+ROOT = su.ROOT
+LIB = os.path.join(ROOT, "diff-dope_b200", "diffdope", "_lib", "libddope_b200.so")
+HEADER = os.path.join(ROOT, "include", "ddope_b200.h")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(LIB):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "diff-dope_b200", "csrc")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+    assert os.path.exists(LIB)
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ddope_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(LIB)
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), "libddope_b200.so does not export %s" % n
+    lib.ddope_abi_version.restype = ctypes.c_int
+    assert lib.ddope_abi_version() == 1
+
+
+def test_library_is_sm100a_with_lineinfo():
+    out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_error_reporting_without_gpu_compute():
+    lib = ctypes.CDLL(LIB)
+    lib.ddope_last_error.restype = ctypes.c_char_p
+    lib.ddope_xfm_fwd.restype = ctypes.c_int
+    rc = lib.ddope_xfm_fwd(None, 1, 4, None, 1, 1, None, None)
+    assert rc != 0 and b"null pointer" in lib.ddope_last_error()
+    lib.ddope_scene_set_window.restype = ctypes.c_int
+    assert lib.ddope_scene_set_window(None, 0, 0, 1, 1) != 0
+
+
+def test_python_binding_loads_and_has_no_cpu_fallback():
+    import diffdope as dd
+    from diffdope import _native
+
+    assert _native.lib() is not None
+    with pytest.raises(RuntimeError):
+        dd.xfm_points(torch.zeros(1, 4, 3), torch.eye(4)[None])  # CPU tensors are refused, not emulated
+    out = dd.xfm_points(torch.rand(2, 5, 3), torch.rand(2, 4, 4), use_python=True)  # the reference's torch validation path
+    assert out.shape == (2, 5, 4)
+
+
+def test_public_names_match_reference_api():
+    import diffdope as dd
+
+    for name in ("DiffDope", "Scene", "Object3D", "Camera", "Mesh", "Image", "xfm_points", "xfm_vectors", "render_texture_batch",
+                 "matrix_batch_44_from_position_quat", "opencv_2_opengl", "interpolate", "l1_rgb_with_mask", "l1_depth_with_mask",
+                 "l1_mask", "dist_batch_lr", "find_crop", "make_grid", "make_grid_image", "make_grid_overlay_batch"):
+        assert hasattr(dd, name), name
+    for meth in ("run_optimization", "get_argmin", "get_pose", "render_img", "plot_losses", "make_animation", "set_batchsize", "add_loss_value", "cuda"):
+        assert hasattr(dd.DiffDope, meth), meth
+
+
+# ---- PLY ---------------------------------------------------------------------------------------
+
+
+def test_ply_ascii_and_binary_roundtrip(tmp_path):
+    from diffdope._ply import load_ply
+
+    verts = np.array([[0, 0, 0, 0.1, 0.2, 255, 0, 0], [1, 0, 0, 0.3, 0.4, 0, 255, 0], [0, 1, 0, 0.5, 0.6, 0, 0, 255], [1, 1, 0, 0.7, 0.8, 9, 9, 9]], dtype=np.float64)
+    header = ("ply\nformat %s 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\nproperty float s\nproperty float t\n"
+              "property uchar red\nproperty uchar green\nproperty uchar blue\nelement face 2\nproperty list uchar int vertex_indices\nend_header\n")
+    pa = tmp_path / "a.ply"
+    with open(pa, "w") as f:
+        f.write(header % "ascii")
+        for v in verts:
+            f.write("%g %g %g %g %g %d %d %d\n" % tuple(v))
+        f.write("3 0 1 2\n4 0 1 3 2\n")
+    pb = tmp_path / "b.ply"
+    with open(pb, "wb") as f:
+        f.write((header % "binary_little_endian").encode())
+        for v in verts:
+            f.write(struct.pack("<5f3B", *v[:5], *[int(x) for x in v[5:]]))
+        f.write(struct.pack("<B3i", 3, 0, 1, 2))
+        f.write(struct.pack("<B4i", 4, 0, 1, 3, 2))
+    for p in (pa, pb):
+        m = load_ply(str(p))
+        assert np.allclose(m.vertices, verts[:, :3])
+        assert np.allclose(m.uv, verts[:, 3:5])
+        assert m.vertex_colors.tolist() == verts[:, 5:].astype(int).tolist()
+        assert m.faces.tolist() == [[0, 1, 2], [0, 1, 3], [0, 3, 2]]  # quad fan-triangulated
+
+
+def test_quaternion_helpers_match_scipy():
+    from scipy.spatial.transform import Rotation as R
+
+    from diffdope._quat import quat_from_matrix, quat_mul, quat_to_matrix33, rotation_to_quat
+
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        r = R.random(random_state=rng.integers(1 << 30))
+        q = quat_from_matrix(r.as_matrix())
+        s = r.as_quat()
+        assert np.allclose(q, s, atol=1e-9) or np.allclose(q, -s, atol=1e-9)
+        assert np.allclose(quat_to_matrix33(q * 3.0), r.as_matrix(), atol=1e-9)
+        assert np.allclose(rotation_to_quat(list(r.as_matrix().reshape(-1))), q)
+        r2 = R.random(random_state=rng.integers(1 << 30))
+        assert np.allclose(quat_to_matrix33(quat_mul(q, quat_from_matrix(r2.as_matrix()))), (r * r2).as_matrix(), atol=1e-9)
+
+
+def test_matrix_from_quat_matches_rotation():
+    from scipy.spatial.transform import Rotation as R
+
+    import diffdope as dd
+
+    r = R.random(random_state=5)
+    q = torch.tensor(r.as_quat()[None], dtype=torch.float32)
+    p = torch.tensor([[1.0, 2.0, 3.0]])
+    M = dd.matrix_batch_44_from_position_quat(q, p)[0].numpy()
+    assert np.allclose(M[:3, :3], r.as_matrix(), atol=1e-6) and np.allclose(M[:3, 3], [1, 2, 3]) and np.allclose(M[3], [0, 0, 0, 1])
+
+
+def test_compat_shims_and_config():
+    import diffdope  # noqa: F401  (activates the shims if the real packages are missing)
+    import hydra
+    from omegaconf import OmegaConf
+
+    cfg = OmegaConf.load(os.path.join(ROOT, "configs", "diffdope.yaml"))
+    assert cfg.camera.fx == 1390.53 and cfg.hyperparameters.nb_iterations == 60 and cfg.losses.l1_mask is True
+    assert set(cfg.keys()) == {"camera", "scene", "object3d", "losses", "hyperparameters", "render_images"}
+    assert dict(**cfg.camera)["im_height"] == 1080
+    assert len(cfg.object3d.rotation) == 9 and cfg.hyperparameters.learning_rates_bound[1] == 100
+    assert hasattr(hydra, "main") and hasattr(hydra.core.hydra_config, "HydraConfig")
+
+
+def test_hydra_shim_runs_a_main_with_overrides(tmp_path):
+    script = tmp_path / "m.py"
+    script.write_text(
+        "import sys\nsys.path.insert(0, %r)\nimport diffdope\nimport hydra\nfrom omegaconf import DictConfig\n"
+        "@hydra.main(version_base=None, config_path=%r, config_name='diffdope')\n"
+        "def main(cfg: DictConfig):\n"
+        "    import hydra as h\n"
+        "    print('B', cfg.hyperparameters.batchsize, cfg.losses.l1_rgb_with_mask, h.core.hydra_config.HydraConfig.get().runtime.output_dir)\n"
+        "main()\n" % (os.path.join(ROOT, "diff-dope_b200"), os.path.join(ROOT, "configs"))
+    )
+    out = subprocess.run([sys.executable, str(script), "hyperparameters.batchsize=3", "losses.l1_rgb_with_mask=true"], capture_output=True, text=True, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr
+    assert "B 3 True" in out.stdout and "outputs" in out.stdout
+
+
+def test_camera_and_image_loading_follow_reference():
+    import diffdope as dd
+
+    cam = dd.Camera(**su.CAMERA)
+    assert np.allclose(cam.cam_proj.numpy(), su.projection_native())
+    cam.set_batchsize(5)
+    assert tuple(cam.cam_proj.shape) == (5, 4, 4)
+    im = dd.Image(os.path.join(su.DATA, "scene", "seg.png"), img_resize=0.5)
+    assert np.array_equal(im.img_tensor.numpy(), su.example_targets(0.5)["segmentation"])
+    im.set_batchsize(4)
+    assert tuple(im.img_tensor.shape) == (4, 540, 960, 3) and im.img_tensor.stride(0) == 0  # a view, not 4 copies
+    d = dd.Image(os.path.join(su.DATA, "scene", "depth.png"), img_resize=0.5, depth=True)
+    assert np.array_equal(d.img_tensor.numpy(), su.example_targets(0.5)["depth"])
+
+
+def test_mesh_and_object3d_follow_reference():
+    import diffdope as dd
+
+    m = dd.Mesh(os.path.join(su.DATA, "mesh", "AlphabetSoup.ply"), scale=0.01)
+    a = su.example_mesh_arrays()
+    assert m.has_textured_map and np.allclose(m.pos.numpy(), a["pos"], atol=1e-7) and np.array_equal(m.pos_idx.numpy(), a["tri"])
+    assert np.allclose(m.uv.numpy(), a["uv"]) and tuple(m.tex.shape) == (2048, 2048, 3)
+    m.set_batchsize(6)
+    out = m()
+    assert tuple(out["pos"].shape) == (6, 8240, 3) and tuple(out["tex"].shape) == (6, 2048, 2048, 3)
+    assert out["tex"].stride(0) == 0, "texture must not be stacked B times"
+    o = dd.Object3D(su.POSITION, su.ROTATION, batchsize=4, scale=0.01)
+    q, t = su.example_pose()
+    assert tuple(o.qx.shape) == (4,) and np.allclose([o.qx[0].item(), o.qy[0].item(), o.qz[0].item(), o.qw[0].item()], q, atol=1e-6)
+    assert np.allclose([o.x[0].item(), o.y[0].item(), o.z[0].item()], t, atol=1e-6)
+    assert len(list(o.parameters())) == 7
+
+
+def test_shard_bounds_cover_every_hypothesis_once():
+    from diffdope import _dist
+
+    for B in (1, 7, 8, 64, 65):
+        for ws in (1, 2, 3, 8):
+            seen = []
+            for r in range(ws):
+                lo, hi = _dist.shard_bounds(B, r, ws)
+                seen += list(range(lo, hi))
+            assert seen == list(range(B))
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    import json
+
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "hyp*iter/s"
