@@ -14,7 +14,7 @@ constexpr int ID_NONE = -1;                             // inside the frame, not
 constexpr int ID_OUTSIDE = -2;                          // outside the frame: no pixel, no pair
 
 struct Shade {
-    float u, v, zw;
+    float u, v;
     float c0[4], c1[4], c2[4];  // clip verts
     float p0x, p0y, p1x, p1y, p2x, p2y, a0, a1, a2, fx, fy;
     int i0, i1, i2;
@@ -39,9 +39,12 @@ __device__ __forceinline__ void shade_setup(const SceneDev& S, const float* mvp,
     const float iw = xdiv(1.f, xadd(xadd(s.a0, s.a1), s.a2));
     s.u = __saturatef(xmul(s.a0, iw));
     s.v = __saturatef(xmul(s.a1, iw));
+}
+
+__device__ __forceinline__ float shade_zw(const Shade& s) {
     const float z = xadd(xadd(xmul(s.c0[2], s.a0), xmul(s.c1[2], s.a1)), xmul(s.c2[2], s.a2));
     const float w = xadd(xadd(xmul(s.c0[3], s.a0), xmul(s.c1[3], s.a1)), xmul(s.c2[3], s.a2));
-    s.zw = xdiv(z, w);
+    return xdiv(z, w);
 }
 
 // d(u,v) -> d clip (x,y,w) of the three vertices -> accumulate dL/dMVP rows x,y,w
@@ -217,13 +220,10 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
     const int lx = tid % TILE_W, ly0 = tid / TILE_W;  // this thread's pixels: (lx, ly0 + 8k), k = 0..3
 
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        if (tid == 0) {  // locate the hypothesis: last b with tile_base <= item
-            int lo = 0, hi = B - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (hyp[mid].tile_base <= item) lo = mid; else hi = mid - 1;
-            }
-            s_b = lo;
+        // locate the hypothesis owning this work item (one load per thread instead of a serial search)
+        for (int bb = tid; bb < B; bb += TILE_THREADS) {
+            const int base = hyp[bb].tile_base;
+            if (item >= base && item < base + hyp[bb].tiles_x * hyp[bb].tiles_y) s_b = bb;
         }
         __syncthreads();
         const int b = s_b;
@@ -401,6 +401,11 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
 #pragma unroll
                 for (int c = 0; c < 3; c++) seg[c] = S.gt_seg[gpix * S.seg_pix_stride + c * S.seg_ch_stride];
             }
+            float gt_rgb[3] = {0.f, 0.f, 0.f}, gt_d = 0.f;  // target loads issued before the dependent mesh gathers
+            if (MODE == MODE_LOSS) {
+                if (cfg.use_rgb) { gt_rgb[0] = S.gt_rgb[gpix * 3]; gt_rgb[1] = S.gt_rgb[gpix * 3 + 1]; gt_rgb[2] = S.gt_rgb[gpix * 3 + 2]; }
+                if (cfg.use_depth) gt_d = S.gt_depth[gpix];
+            }
             float rgb[3] = {0.f, 0.f, 0.f};
             float depth = -s_m2[3];
             float gu = 0.f, gv = 0.f;  // dL/d(u,v)
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
 
                 float gd = 0.f;  // dL/d depth
                 if (MODE == MODE_LOSS && cfg.use_depth) {
-                    const float diff = (depth - S.gt_depth[gpix]) * seg[0];
+                    const float diff = (depth - gt_d) * seg[0];
                     acc[17] += fabsf(diff);
                     gd = k_depth * sgn(diff) * seg[0];
                 }
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                         if (want_rgb_grad) {
                             float dy;
                             if (MODE == MODE_LOSS) {
-                                const float diff = (rgb[c] - S.gt_rgb[gpix * 3 + c]) * seg[c];
+                                const float diff = (rgb[c] - gt_rgb[c]) * seg[c];
                                 acc[16] += fabsf(diff);
                                 dy = k_rgb * sgn(diff) * seg[c];
                             } else {
@@ -487,7 +492,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                         if (want_rgb_grad) {
                             float dy;
                             if (MODE == MODE_LOSS) {
-                                const float diff = (rgb[c] - S.gt_rgb[gpix * 3 + c]) * seg[c];
+                                const float diff = (rgb[c] - gt_rgb[c]) * seg[c];
                                 acc[16] += fabsf(diff);
                                 dy = k_rgb * sgn(diff) * seg[c];
                             } else {
@@ -500,18 +505,18 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                 }
                 if (MODE != MODE_RENDER && (gu != 0.f || gv != 0.f)) raster_grad_accum(S, sh, gu, gv, acc);
                 if (MODE == MODE_RENDER && out.rast)
-                    reinterpret_cast<float4*>(out.rast)[wp] = make_float4(sh.u, sh.v, sh.zw, (float)(id + 1));
+                    reinterpret_cast<float4*>(out.rast)[wp] = make_float4(sh.u, sh.v, shade_zw(sh), (float)(id + 1));
             } else {
                 // background: rgb = 0, depth = -t_z (interpolate yields 0 where tri_id == 0)
                 if (MODE == MODE_LOSS) {
                     if (cfg.use_depth) {
-                        const float diff = (depth - S.gt_depth[gpix]) * seg[0];
+                        const float diff = (depth - gt_d) * seg[0];
                         acc[17] += fabsf(diff);
                         acc[15] -= k_depth * sgn(diff) * seg[0];
                     }
                     if (cfg.use_rgb) {
 #pragma unroll
-                        for (int c = 0; c < 3; c++) acc[16] += fabsf((0.f - S.gt_rgb[gpix * 3 + c]) * seg[c]);
+                        for (int c = 0; c < 3; c++) acc[16] += fabsf((0.f - gt_rgb[c]) * seg[c]);
                     }
                 }
                 if (MODE == MODE_EXT && ext.d_depth) acc[15] -= ext.d_depth[wp];

@@ -29,6 +29,10 @@ void launch_clear(const SceneDev& S, const HypState* hyp, int B, unsigned long l
 constexpr int RASTER_THREADS = 256;
 constexpr int SMALL_EXTENT = 64 * SUBPIX;  // bbox extent up to which int32 edge functions cannot overflow
 constexpr int REC_WORDS = 25;
+#ifndef OWN_CAP_N
+#define OWN_CAP_N 0
+#endif
+constexpr int OWN_CAP = OWN_CAP_N;  // candidates a lane walks on its own before the warp shares the work
 
 // Per-triangle record in shared memory (25 words: odd stride, so lanes reading different records
 // hit different banks). Small triangles: incremental int32 edge functions relative to the bbox
@@ -158,21 +162,68 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
         }
     }
 
-    // ---- small triangles: flatten the warp's (triangle, pixel) candidates -----------------------
-    int incl = npx;
+    // ---- small triangles --------------------------------------------------------------------------
+    // Stage 1 finds the candidates whose pixel centre is inside (integer edge functions) and pushes
+    // them into a per-warp queue; stage 2 runs whenever 32 are queued: float z/w + atomicMin with all
+    // lanes busy (only ~1 candidate in 4 is inside its triangle).
+    unsigned int* wq = s_queue + (threadIdx.x >> 5) * 64;
+    int nqueued = 0;
+    auto push_and_drain = [&](bool inside, unsigned int entry) {
+        const unsigned int m = __ballot_sync(0xffffffffu, inside);
+        if (inside) wq[nqueued + __popc(m & ((1u << lane) - 1))] = entry;
+        nqueued += __popc(m);
+        __syncwarp();
+        if (nqueued >= 32) {
+            const unsigned int e = wq[lane];
+            const unsigned int keep = wq[32 + lane];
+            __syncwarp();
+            const TriRec* r = reinterpret_cast<const TriRec*>(s_rec + (wbase + (e >> 16)) * REC_WORDS);
+            depth_test_write(S, r->c0, r->c1, r->c2, r->tri, r->pxmin + (int)(e & 0xFF), r->pymin + (int)((e >> 8) & 0xFF), zb,
+                             xs, xo, ys, yo);
+            nqueued -= 32;
+            if (lane < nqueued) wq[lane] = keep;
+            __syncwarp();
+        }
+    };
+
+    // (a) bounding boxes of up to OWN_CAP pixel centres (almost all of a dense mesh): each lane walks
+    //     its own triangle with incremental edge functions -- no search, three adds per candidate
+    {
+        const int own = (npx <= OWN_CAP) ? npx : 0;
+        int maxown = own;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxown = max(maxown, __shfl_xor_sync(0xffffffffu, maxown, o));
+        int e0 = 0, e1 = 0, e2 = 0, r0 = 0, r1 = 0, r2 = 0, bw = 1, col = 0, row = 0;
+        if (own > 0) {
+            r0 = e0 = my->k0; r1 = e1 = my->k1; r2 = e2 = my->k2;
+            bw = my->bw;
+        }
+        const int a0 = own > 0 ? my->a0 : 0, a1 = own > 0 ? my->a1 : 0, a2 = own > 0 ? my->a2 : 0;
+        const int b0 = own > 0 ? my->b0 : 0, b1 = own > 0 ? my->b1 : 0, b2 = own > 0 ? my->b2 : 0;
+        for (int it = 0; it < maxown; it++) {
+            const bool inside = (it < own) && ((e0 | e1 | e2) >= 0);
+            push_and_drain(inside, ((unsigned int)lane << 16) | ((unsigned int)row << 8) | (unsigned int)col);
+            col++;
+            e0 += a0; e1 += a1; e2 += a2;
+            if (col == bw) {
+                col = 0; row++;
+                r0 += b0; r1 += b1; r2 += b2;
+                e0 = r0; e1 = r1; e2 = r2;
+            }
+        }
+    }
+
+    // (b) bigger boxes (still within the int32 range): flatten their candidates across the warp
+    const int nbig = (npx > OWN_CAP) ? npx : 0;
+    int incl = nbig;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int n = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += n;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    s_off[threadIdx.x] = incl - npx;
+    s_off[threadIdx.x] = incl - nbig;
     __syncwarp();
-    // Two stages so both keep their lanes busy: (1) 32 candidates per step run the integer edge
-    // tests; the ones that pass are pushed into a per-warp queue; (2) whenever 32 are queued they run
-    // the float z/w evaluation + atomicMin together (only ~1 candidate in 4 is inside its triangle).
-    unsigned int* wq = s_queue + (threadIdx.x >> 5) * 64;
-    int nqueued = 0;
     for (int base = 0; base < total; base += 32) {
         const int j = base + lane;
         bool inside = false;
@@ -195,21 +246,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
             inside = (e0 | e1 | e2) >= 0;
             entry = ((unsigned int)lo << 16) | ((unsigned int)row << 8) | (unsigned int)col;
         }
-        const unsigned int m = __ballot_sync(0xffffffffu, inside);
-        if (inside) wq[nqueued + __popc(m & ((1u << lane) - 1))] = entry;
-        nqueued += __popc(m);
-        __syncwarp();
-        if (nqueued >= 32) {
-            const unsigned int e = wq[lane];
-            const unsigned int keep = wq[32 + lane];
-            __syncwarp();
-            const TriRec* r = reinterpret_cast<const TriRec*>(s_rec + (wbase + (e >> 16)) * REC_WORDS);
-            depth_test_write(S, r->c0, r->c1, r->c2, r->tri, r->pxmin + (int)(e & 0xFF), r->pymin + (int)((e >> 8) & 0xFF), zb,
-                             xs, xo, ys, yo);
-            nqueued -= 32;
-            if (lane < nqueued) wq[lane] = keep;
-            __syncwarp();
-        }
+        push_and_drain(inside, entry);
     }
     if (lane < nqueued) {
         const unsigned int e = wq[lane];

@@ -151,6 +151,17 @@ def test_example_script_runs(tmp_path):
         os.remove(p)
 
 
+def test_bop_style_object_loop(tmp_path):
+    """examples/run_bop_scene.py: the reference's per-object flow (run_bop_scene.py:48-93) -- Mesh built
+    and batched separately, Object3D without a model path, segmentation Image swapped into the scene."""
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "diff-dope_b200"))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "run_bop_scene.py"), "hyperparameters.nb_iterations=4", "hyperparameters.batchsize=3",
+                          "hydra.run.dir=%s" % tmp_path], capture_output=True, text=True, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "object 0: best hypothesis" in out.stdout
+    assert os.path.getsize(os.path.join(tmp_path, "00.png")) > 1000
+
+
 def test_reference_example_runs_unchanged_when_present():
     ref = "/root/reference/examples/simple_scene.py"
     if not os.path.exists(ref):
