@@ -47,7 +47,9 @@ struct ddope_scene {
     int num_sms = 148;
     int64_t launches = 0;
     bool profiling = false;
-    std::vector<cudaEvent_t> prof_events;  // 6 per iteration: before pose, after pose, clear, raster, pixel, step
+    std::vector<cudaEvent_t> prof_events;  // (start, stop) per launch
+    std::vector<int> prof_class;           // kernel class of each pair
+    unsigned int* arrive = nullptr;        // CTA arrival counter of iter_kernel's last-block scan
 };
 
 extern "C" int ddope_abi_version(void) { return DDOPE_ABI_VERSION; }
@@ -165,6 +167,8 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     int init_bbox[4] = {1 << 30, 1 << 30, -1, -1};
     CK(cudaMemcpy(s->seg_bbox, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&s->total_tiles, sizeof(int)));
+    CK(cudaMalloc(&s->arrive, sizeof(unsigned int)));
+    CK(cudaMemset(s->arrive, 0, sizeof(unsigned int)));
 
     SceneDev& d = s->dev;
     d.pos = s->pos; d.tri = s->tri; d.opp = s->opp; d.uv = s->uv; d.tex = s->tex; d.vcol = s->vcol;
@@ -188,7 +192,7 @@ extern "C" int ddope_scene_destroy(ddope_scene* s) {
     if (!s) return 0;
     cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex); cudaFree(s->vcol);
     cudaFree(s->seg_bbox); cudaFree(s->total_tiles); cudaFree(s->hyp); cudaFree(s->zbuf); cudaFree(s->partials);
-    cudaFree(s->lr_sched); cudaFree(s->xfm_scratch);
+    cudaFree(s->lr_sched); cudaFree(s->xfm_scratch); cudaFree(s->arrive);
     delete s;
     return 0;
 }
@@ -343,29 +347,57 @@ extern "C" int ddope_render_bwd(ddope_scene* s, const float* mtx_in, int B, cons
     return 0;
 }
 
-static void enqueue_iteration(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
-                              LossCfgDev cfg, int it, int do_update, float* loss_table, float* grad,
-                              float* pose_hist, float* loss_hist, cudaStream_t st) {
-    auto mark = [&]() {
+// kernel classes for the profiling hook
+enum { K_ITER = 0, K_RASTER = 1, K_PIXEL = 2 };
+
+struct ProfMark {
+    ddope_scene* s;
+    cudaStream_t st;
+    int cls;
+    cudaEvent_t e0;
+    ProfMark(ddope_scene* s_, cudaStream_t st_, int cls_) : s(s_), st(st_), cls(cls_), e0(nullptr) {
         if (!s->profiling) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, st);
-        s->prof_events.push_back(e);
-    };
-    mark();
-    launch_pose(s->dev, quat, trans, nullptr, lr_mult, B, B_global, cfg, 1, s->hyp, s->total_tiles, st);
-    mark();
-    launch_clear(s->dev, s->hyp, B, s->zbuf, st);
-    mark();
-    launch_raster(s->dev, s->hyp, B, s->zbuf, st);
-    mark();
-    launch_pixel_loss(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), cfg, s->zbuf, s->partials, s->num_sms, st);
-    mark();
-    launch_step(s->dev, s->hyp, s->partials, B, cfg, quat, trans, s->lr_sched, it, do_update, loss_table, grad,
-                pose_hist, loss_hist, nullptr, st);
-    mark();
-    s->launches += 5;
+        cudaEventCreate(&e0);
+        cudaEventRecord(e0, st);
+    }
+    ~ProfMark() {
+        if (!s->profiling) return;
+        cudaEvent_t e1;
+        cudaEventCreate(&e1);
+        cudaEventRecord(e1, st);
+        s->prof_events.push_back(e0);
+        s->prof_events.push_back(e1);
+        s->prof_class.push_back(cls);
+    }
+};
+
+// [pose + z clear + tile prefix] of the first iteration
+static void enqueue_prologue(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
+                             LossCfgDev cfg, cudaStream_t st) {
+    ProfMark m(s, st, K_ITER);
+    launch_iter(s->dev, s->hyp, s->partials, B, B_global, cfg, quat, trans, lr_mult, s->lr_sched, 0, 0, 0, 1, nullptr, nullptr,
+                nullptr, nullptr, s->zbuf, s->total_tiles, s->arrive, st);
+    s->launches += 1;
+}
+
+// raster + pixel of iteration `it`, then one launch that finishes it and (if more follow) sets up the next
+static void enqueue_iteration(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
+                              LossCfgDev cfg, int it, int do_update, int more, float* loss_table, float* grad,
+                              float* pose_hist, float* loss_hist, cudaStream_t st) {
+    {
+        ProfMark m(s, st, K_RASTER);
+        launch_raster(s->dev, s->hyp, B, s->zbuf, st);
+    }
+    {
+        ProfMark m(s, st, K_PIXEL);
+        launch_pixel_loss(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), cfg, s->zbuf, s->partials, s->num_sms, st);
+    }
+    {
+        ProfMark m(s, st, K_ITER);
+        launch_iter(s->dev, s->hyp, s->partials, B, B_global, cfg, quat, trans, lr_mult, s->lr_sched, it, 1, do_update, more,
+                    loss_table, grad, pose_hist, loss_hist, s->zbuf, s->total_tiles, s->arrive, st);
+    }
+    s->launches += 3;
 }
 
 extern "C" int ddope_loss_grad(ddope_scene* s, const float* quat, const float* trans, const float* lr_mult, int B,
@@ -377,7 +409,8 @@ extern "C" int ddope_loss_grad(ddope_scene* s, const float* quat, const float* t
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, true)) return r;
     s->launches = 0;
-    enqueue_iteration(s, const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B, B_global, to_dev(cfg), 0, 0,
+    enqueue_prologue(s, const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B, B_global, to_dev(cfg), st);
+    enqueue_iteration(s, const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B, B_global, to_dev(cfg), 0, 0, 0,
                       loss_table, grad, nullptr, nullptr, st);
     CK(cudaGetLastError());
     return 0;
@@ -400,8 +433,10 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     CK(cudaMemcpyAsync(s->lr_sched, lr_sched, sizeof(float) * n_iters, cudaMemcpyHostToDevice, st));
     LossCfgDev c = to_dev(cfg);
     s->launches = 0;
+    enqueue_prologue(s, quat, trans, lr_mult, B, B_global, c, st);
     for (int it = 0; it < n_iters; it++)
-        enqueue_iteration(s, quat, trans, lr_mult, B, B_global, c, it, 1, nullptr, nullptr, pose_hist, loss_hist, st);
+        enqueue_iteration(s, quat, trans, lr_mult, B, B_global, c, it, 1, it + 1 < n_iters, nullptr, nullptr, pose_hist,
+                          loss_hist, st);
     CK(cudaGetLastError());
     return 0;
 }
@@ -413,24 +448,27 @@ extern "C" int ddope_profile_begin(ddope_scene* s) {
     if (!s) return fail("ddope_profile_begin: null scene");
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     s->prof_events.clear();
+    s->prof_class.clear();
     s->profiling = true;
     return 0;
 }
 
-extern "C" int ddope_profile_end(ddope_scene* s, float* ms_out5, int* iterations_out) {
-    if (!s || !ms_out5) return fail("ddope_profile_end: null pointer");
+extern "C" int ddope_profile_end(ddope_scene* s, float* ms_out3, int* launches_out3) {
+    if (!s || !ms_out3) return fail("ddope_profile_end: null pointer");
     s->profiling = false;
-    const size_t n = s->prof_events.size() / 6;
-    for (int k = 0; k < 5; k++) ms_out5[k] = 0.f;
-    if (n > 0) CK(cudaEventSynchronize(s->prof_events.back()));
-    for (size_t i = 0; i < n; i++)
-        for (int k = 0; k < 5; k++) {
-            float ms = 0.f;
-            CK(cudaEventElapsedTime(&ms, s->prof_events[6 * i + k], s->prof_events[6 * i + k + 1]));
-            ms_out5[k] += ms;
-        }
+    for (int k = 0; k < 3; k++) {
+        ms_out3[k] = 0.f;
+        if (launches_out3) launches_out3[k] = 0;
+    }
+    if (!s->prof_events.empty()) CK(cudaEventSynchronize(s->prof_events.back()));
+    for (size_t i = 0; i < s->prof_class.size(); i++) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s->prof_events[2 * i], s->prof_events[2 * i + 1]));
+        ms_out3[s->prof_class[i]] += ms;
+        if (launches_out3) launches_out3[s->prof_class[i]]++;
+    }
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     s->prof_events.clear();
-    if (iterations_out) *iterations_out = (int)n;
+    s->prof_class.clear();
     return 0;
 }

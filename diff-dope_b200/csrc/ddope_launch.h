@@ -13,6 +13,11 @@ void launch_pose(const SceneDev& S, const float* quat, const float* trans, const
 void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg,
                  float* quat, float* trans, const float* lr_sched, int it, int do_update, float* loss_table,
                  float* grad_out, float* pose_hist, float* loss_hist, float* dmtx_out, cudaStream_t st);
+// Fused iteration boundary: [step of iteration it] + [pose, z clear, tile prefix of the next iteration].
+void launch_iter(const SceneDev& S, HypState* hyp, const float* partials, int B, int B_global, LossCfgDev cfg, float* quat,
+                 float* trans, const float* lr_mult, const float* lr_sched, int it, int do_step, int do_update, int do_pose,
+                 float* loss_table, float* grad_out, float* pose_hist, float* loss_hist, unsigned long long* zbuf,
+                 int* total_tiles, unsigned int* arrive, cudaStream_t st);
 void launch_seg_bbox(const float* seg, int H, int W, int seg_c, int* bbox4, cudaStream_t st);
 void launch_copy_mtx(const HypState* hyp, int B, float* mtx, cudaStream_t st);
 

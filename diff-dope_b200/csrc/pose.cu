@@ -37,6 +37,65 @@ __device__ void canonical_mvp(const float* P, const float* M, float* out) {
                                   xmul(P[4 * r + 3], M[12 + c]));
 }
 
+// Everything pixel/raster kernels need to know about one hypothesis, from its raw parameters (or an
+// explicit model matrix): q^, M, MVP, loss scales, loss ROI and its tile grid (tile_base is filled by
+// the scan that follows).
+__device__ void hyp_from_pose(const SceneDev& S, const float* qb, const float* tb, const float* mtx_b, float lr_b,
+                              int B_global, LossCfgDev cfg, int roi_mode, HypState& h) {
+    if (mtx_b) {
+        for (int k = 0; k < 16; k++) h.m[k] = mtx_b[k];
+        h.qhat[0] = h.qhat[1] = h.qhat[2] = 0.f; h.qhat[3] = 1.f; h.qnorm = 1.f;
+    } else {
+        float q[4] = {qb[0], qb[1], qb[2], qb[3]};
+        float t[3] = {tb[0], tb[1], tb[2]};
+        canonical_pose(q, t, h.qhat, &h.qnorm, h.m);
+    }
+    canonical_mvp(S.proj, h.m, h.mvp);
+
+    int x0 = S.wx0, y0 = S.wy0, x1 = S.wx0 + S.ww, y1 = S.wy0 + S.wh;  // window, exclusive end
+    if (roi_mode == 1) {
+        bool full = false;
+        float mnx = 1e30f, mny = 1e30f, mxx = -1e30f, mxy = -1e30f;
+        for (int c = 0; c < 8; c++) {
+            float px = (c & 1) ? S.bbmax[0] : S.bbmin[0];
+            float py = (c & 2) ? S.bbmax[1] : S.bbmin[1];
+            float pz = (c & 4) ? S.bbmax[2] : S.bbmin[2];
+            float cl[4];
+            xfm_exact(h.mvp, px, py, pz, cl);
+            if (!(cl[3] > 1e-6f)) { full = true; break; }
+            float sx = (cl[0] / cl[3] * 0.5f + 0.5f) * (float)S.W;
+            float sy = (cl[1] / cl[3] * 0.5f + 0.5f) * (float)S.H;
+            if (!(fabsf(sx) < 1e6f) || !(fabsf(sy) < 1e6f)) { full = true; break; }
+            mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx);
+            mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
+        }
+        if (!full) {
+            int ox0 = (int)floorf(mnx) - 2, ox1 = (int)ceilf(mxx) + 3;  // exclusive end
+            int oy0 = (int)floorf(mny) - 2, oy1 = (int)ceilf(mxy) + 3;
+            if (S.gt_seg != nullptr) {
+                int sx0 = S.seg_bbox[0], sy0 = S.seg_bbox[1], sx1 = S.seg_bbox[2], sy1 = S.seg_bbox[3];
+                if (sx0 <= sx1 && sy0 <= sy1) {
+                    ox0 = min(ox0, sx0); oy0 = min(oy0, sy0);
+                    ox1 = max(ox1, sx1 + 1); oy1 = max(oy1, sy1 + 1);
+                }
+            }
+            x0 = max(x0, ox0); y0 = max(y0, oy0);
+            x1 = min(x1, ox1); y1 = min(y1, oy1);
+        }
+    }
+    if (x1 <= x0 || y1 <= y0) { x0 = x1 = S.wx0; y0 = y1 = S.wy0; }
+    h.rx0 = x0; h.ry0 = y0; h.rx1 = x1; h.ry1 = y1;
+    h.tiles_x = (x1 - x0 + TILE_W - 1) / TILE_W;
+    h.tiles_y = (y1 - y0 + TILE_H - 1) / TILE_H;
+                h.pad0 = 0;
+    double P = (double)S.wh * (double)S.ww;
+    double lr = (double)lr_b;
+    h.k_rgb = (float)((double)cfg.w_rgb * lr / ((double)B_global * P * 3.0));
+    h.k_depth = (float)((double)cfg.w_depth * lr / ((double)B_global * P));
+    h.k_mask = (float)((double)cfg.w_mask * lr / ((double)B_global * P * 3.0));
+    h.tile_base = 0;
+}
+
 __global__ void __launch_bounds__(256) pose_kernel(SceneDev S, const float* __restrict__ quat,
                                                    const float* __restrict__ trans,
                                                    const float* __restrict__ mtx_in,
@@ -53,58 +112,9 @@ __global__ void __launch_bounds__(256) pose_kernel(SceneDev S, const float* __re
         int ntiles = 0;
         if (b < B) {
             HypState h;
-            if (mtx_in) {
-                for (int k = 0; k < 16; k++) h.m[k] = mtx_in[16 * b + k];
-                h.qhat[0] = h.qhat[1] = h.qhat[2] = 0.f; h.qhat[3] = 1.f; h.qnorm = 1.f;
-            } else {
-                float q[4] = {quat[4 * b], quat[4 * b + 1], quat[4 * b + 2], quat[4 * b + 3]};
-                float t[3] = {trans[3 * b], trans[3 * b + 1], trans[3 * b + 2]};
-                canonical_pose(q, t, h.qhat, &h.qnorm, h.m);
-            }
-            canonical_mvp(S.proj, h.m, h.mvp);
-
-            int x0 = S.wx0, y0 = S.wy0, x1 = S.wx0 + S.ww, y1 = S.wy0 + S.wh;  // window, exclusive end
-            if (roi_mode == 1) {
-                bool full = false;
-                float mnx = 1e30f, mny = 1e30f, mxx = -1e30f, mxy = -1e30f;
-                for (int c = 0; c < 8; c++) {
-                    float px = (c & 1) ? S.bbmax[0] : S.bbmin[0];
-                    float py = (c & 2) ? S.bbmax[1] : S.bbmin[1];
-                    float pz = (c & 4) ? S.bbmax[2] : S.bbmin[2];
-                    float cl[4];
-                    xfm_exact(h.mvp, px, py, pz, cl);
-                    if (!(cl[3] > 1e-6f)) { full = true; break; }
-                    float sx = (cl[0] / cl[3] * 0.5f + 0.5f) * (float)S.W;
-                    float sy = (cl[1] / cl[3] * 0.5f + 0.5f) * (float)S.H;
-                    if (!(fabsf(sx) < 1e6f) || !(fabsf(sy) < 1e6f)) { full = true; break; }
-                    mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx);
-                    mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
-                }
-                if (!full) {
-                    int ox0 = (int)floorf(mnx) - 2, ox1 = (int)ceilf(mxx) + 3;  // exclusive end
-                    int oy0 = (int)floorf(mny) - 2, oy1 = (int)ceilf(mxy) + 3;
-                    if (S.gt_seg != nullptr) {
-                        int sx0 = S.seg_bbox[0], sy0 = S.seg_bbox[1], sx1 = S.seg_bbox[2], sy1 = S.seg_bbox[3];
-                        if (sx0 <= sx1 && sy0 <= sy1) {
-                            ox0 = min(ox0, sx0); oy0 = min(oy0, sy0);
-                            ox1 = max(ox1, sx1 + 1); oy1 = max(oy1, sy1 + 1);
-                        }
-                    }
-                    x0 = max(x0, ox0); y0 = max(y0, oy0);
-                    x1 = min(x1, ox1); y1 = min(y1, oy1);
-                }
-            }
-            if (x1 <= x0 || y1 <= y0) { x0 = x1 = S.wx0; y0 = y1 = S.wy0; }
-            h.rx0 = x0; h.ry0 = y0; h.rx1 = x1; h.ry1 = y1;
-            h.tiles_x = (x1 - x0 + TILE_W - 1) / TILE_W;
-            h.tiles_y = (y1 - y0 + TILE_H - 1) / TILE_H;
+            hyp_from_pose(S, quat ? quat + 4 * b : nullptr, trans ? trans + 3 * b : nullptr, mtx_in ? mtx_in + 16 * b : nullptr,
+                          lr_mult ? lr_mult[b] : 1.f, B_global, cfg, roi_mode, h);
             ntiles = h.tiles_x * h.tiles_y;
-            h.pad0 = 0;
-            double P = (double)S.wh * (double)S.ww;
-            double lr = lr_mult ? (double)lr_mult[b] : 1.0;
-            h.k_rgb = (float)((double)cfg.w_rgb * lr / ((double)B_global * P * 3.0));
-            h.k_depth = (float)((double)cfg.w_depth * lr / ((double)B_global * P));
-            h.k_mask = (float)((double)cfg.w_mask * lr / ((double)B_global * P * 3.0));
             h.tile_base = 0;
             hyp[b] = h;
         }
@@ -135,43 +145,13 @@ void launch_pose(const SceneDev& S, const float* quat, const float* trans, const
 
 // ---------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) step_kernel(SceneDev S, const HypState* __restrict__ hyp,
-                                                   const float* __restrict__ partials, int B, LossCfgDev cfg,
-                                                   float* __restrict__ quat, float* __restrict__ trans,
-                                                   const float* __restrict__ lr_sched, int it, int do_update,
-                                                   float* __restrict__ loss_table, float* __restrict__ grad_out,
-                                                   float* __restrict__ pose_hist, float* __restrict__ loss_hist,
-                                                   float* __restrict__ dmtx_out) {
-    const int b = blockIdx.x;
-    const HypState& h = hyp[b];
-    const int n_items = h.tiles_x * h.tiles_y;
-    const float* base = partials + (size_t)h.tile_base * NACC;
-    float acc[NACC];
-#pragma unroll
-    for (int k = 0; k < NACC; k++) acc[k] = 0.f;
-    for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
-        const float4* p = reinterpret_cast<const float4*>(base + (size_t)i * NACC);
-#pragma unroll
-        for (int k = 0; k < NACC / 4; k++) {
-            float4 v = p[k];
-            acc[4 * k + 0] += v.x; acc[4 * k + 1] += v.y; acc[4 * k + 2] += v.z; acc[4 * k + 3] += v.w;
-        }
-    }
-    __shared__ float s_acc[4][NACC];
-#pragma unroll
-    for (int k = 0; k < NACC; k++) {
-        float v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        acc[k] = v;
-    }
-    if ((threadIdx.x & 31) == 0)
-        for (int k = 0; k < NACC; k++) s_acc[threadIdx.x >> 5][k] = acc[k];
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    float a[NACC];
-    for (int k = 0; k < NACC; k++) a[k] = ((s_acc[0][k] + s_acc[1][k]) + s_acc[2][k]) + s_acc[3][k];
-
+// Thread-level tail of an iteration for hypothesis b: tile sums a[0..18] -> dL/dM -> dL/d(q,t) ->
+// logged losses, history rows and (optionally) the SGD update.
+__device__ void step_from_sums(const SceneDev& S, const HypState& h, const float* a, int b, int B, LossCfgDev cfg,
+                               float* __restrict__ quat, float* __restrict__ trans, const float* __restrict__ lr_sched,
+                               int it, int do_update, float* __restrict__ loss_table, float* __restrict__ grad_out,
+                               float* __restrict__ pose_hist, float* __restrict__ loss_hist,
+                               float* __restrict__ dmtx_out) {
     // dL/dM = P^T dL/dMVP (+ the direct depth term on row 2); rows x,y,w of dMVP are a[0..11]
     const float* P = S.proj;
     float dM[3][4];
@@ -227,6 +207,144 @@ __global__ void __launch_bounds__(128) step_kernel(SceneDev S, const HypState* _
         for (int k = 0; k < 4; k++) quat[4 * b + k] -= lr * g[k];
         for (int k = 0; k < 3; k++) trans[3 * b + k] -= lr * g[4 + k];
     }
+}
+
+// Deterministic reduction of the per-tile partial rows of hypothesis b into s_out[NACC] (thread 0 valid).
+__device__ void reduce_tile_partials(const HypState& h, const float* __restrict__ partials, float* s_out) {
+    const int n_items = h.tiles_x * h.tiles_y;
+    const float* base = partials + (size_t)h.tile_base * NACC;
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; k++) acc[k] = 0.f;
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+        const float4* p = reinterpret_cast<const float4*>(base + (size_t)i * NACC);
+#pragma unroll
+        for (int k = 0; k < NACC / 4; k++) {
+            float4 v = p[k];
+            acc[4 * k + 0] += v.x; acc[4 * k + 1] += v.y; acc[4 * k + 2] += v.z; acc[4 * k + 3] += v.w;
+        }
+    }
+    __shared__ float s_acc[16][NACC];
+    const int nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NACC; k++) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        acc[k] = v;
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < NACC; k++) s_acc[threadIdx.x >> 5][k] = acc[k];
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int k = 0; k < NACC; k++) {
+            float v = 0.f;
+            for (int w = 0; w < nw; w++) v += s_acc[w][k];  // fixed order
+            s_out[k] = v;
+        }
+}
+
+__global__ void __launch_bounds__(128) step_kernel(SceneDev S, const HypState* __restrict__ hyp,
+                                                   const float* __restrict__ partials, int B, LossCfgDev cfg,
+                                                   float* __restrict__ quat, float* __restrict__ trans,
+                                                   const float* __restrict__ lr_sched, int it, int do_update,
+                                                   float* __restrict__ loss_table, float* __restrict__ grad_out,
+                                                   float* __restrict__ pose_hist, float* __restrict__ loss_hist,
+                                                   float* __restrict__ dmtx_out) {
+    __shared__ float s_sum[NACC];
+    const int b = blockIdx.x;
+    reduce_tile_partials(hyp[b], partials, s_sum);
+    if (threadIdx.x == 0)
+        step_from_sums(S, hyp[b], s_sum, b, B, cfg, quat, trans, lr_sched, it, do_update, loss_table, grad_out, pose_hist,
+                       loss_hist, dmtx_out);
+}
+
+constexpr int ITER_THREADS = 512;
+
+// One launch per iteration boundary: finish iteration `it` (reduce, gradient chain, SGD step) and
+// set up the next one (pose -> matrices -> ROI, z-buffer clear over the new ROI, tile prefix by the last
+// CTA to arrive). Replaces step_kernel + pose_kernel + clear_kernel (3 launches) inside ddope_optimize.
+__global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, HypState* __restrict__ hyp,
+                                                   const float* __restrict__ partials, int B, int B_global,
+                                                   LossCfgDev cfg, float* __restrict__ quat, float* __restrict__ trans,
+                                                   const float* __restrict__ lr_mult, const float* __restrict__ lr_sched,
+                                                   int it, int do_step, int do_update, int do_pose,
+                                                   float* __restrict__ loss_table, float* __restrict__ grad_out,
+                                                   float* __restrict__ pose_hist, float* __restrict__ loss_hist,
+                                                   unsigned long long* __restrict__ zbuf, int* __restrict__ total_tiles,
+                                                   unsigned int* __restrict__ arrive) {
+    __shared__ float s_sum[NACC];
+    __shared__ int s_roi[4];
+    __shared__ bool s_last;
+    const int b = blockIdx.x;
+    if (do_step) {
+        reduce_tile_partials(hyp[b], partials, s_sum);
+        if (threadIdx.x == 0)
+            step_from_sums(S, hyp[b], s_sum, b, B, cfg, quat, trans, lr_sched, it, do_update, loss_table, grad_out, pose_hist,
+                           loss_hist, nullptr);
+    }
+    if (!do_pose) return;
+    if (threadIdx.x == 0) {
+        HypState h;
+        hyp_from_pose(S, quat + 4 * b, trans + 3 * b, nullptr, lr_mult ? lr_mult[b] : 1.f, B_global, cfg, 1, h);
+        hyp[b] = h;
+        s_roi[0] = h.rx0; s_roi[1] = h.ry0; s_roi[2] = h.rx1; s_roi[3] = h.ry1;
+    }
+    __syncthreads();
+    if (s_roi[2] > s_roi[0]) {  // clear the z-buffer over the new ROI (+1 px ring)
+        const int x0 = max(s_roi[0] - 1, S.zx0), x1 = min(s_roi[2] + 1, S.zx0 + S.zw);
+        const int y0 = max(s_roi[1] - 1, S.zy0), y1 = min(s_roi[3] + 1, S.zy0 + S.zh);
+        unsigned long long* zb = zbuf + (size_t)b * S.zh * S.zw;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int y = y0 + warp; y < y1; y += nwarps) {  // one warp per row: 256 B coalesced stores, no division
+            unsigned long long* row = zb + (size_t)(y - S.zy0) * S.zw - S.zx0;
+            for (int x = x0 + lane; x < x1; x += 32) row[x] = EMPTY_KEY;
+        }
+    }
+    // tile prefix over all hypotheses, by whichever CTA arrives last
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(arrive, 1u) == (unsigned int)(B - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ int s_warp[16];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+        const int bb = b0 + threadIdx.x;
+        int ntiles = 0;
+        if (bb < B) ntiles = __ldcg(&hyp[bb].tiles_x) * __ldcg(&hyp[bb].tiles_y);
+        int v = ntiles;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += n;
+        }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; w++) woff += s_warp[w];
+        const int carry = s_carry;
+        if (bb < B) hyp[bb].tile_base = carry + woff + v - ntiles;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *total_tiles = s_carry;
+        *arrive = 0u;
+    }
+}
+
+void launch_iter(const SceneDev& S, HypState* hyp, const float* partials, int B, int B_global, LossCfgDev cfg, float* quat,
+                 float* trans, const float* lr_mult, const float* lr_sched, int it, int do_step, int do_update, int do_pose,
+                 float* loss_table, float* grad_out, float* pose_hist, float* loss_hist, unsigned long long* zbuf,
+                 int* total_tiles, unsigned int* arrive, cudaStream_t st) {
+    iter_kernel<<<B, ITER_THREADS, 0, st>>>(S, hyp, partials, B, B_global, cfg, quat, trans, lr_mult, lr_sched, it, do_step, do_update,
+                                   do_pose, loss_table, grad_out, pose_hist, loss_hist, zbuf, total_tiles, arrive);
 }
 
 void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg,

@@ -252,17 +252,17 @@ class NativeScene:
                                     ctypes.byref(cfg), _ptr(pose_hist), _ptr(loss_hist), _stream()))
         return pose_hist, loss_hist
 
-    KERNELS = ("pose_kernel", "clear_kernel", "raster_kernel", "pixel_kernel", "step_kernel")
+    KERNELS = ("iter_kernel", "raster_kernel", "pixel_kernel")
 
     def profile_begin(self):
         _check(lib().ddope_profile_begin(self._h))
 
     def profile_end(self):
-        """-> ({kernel: total ms}, iterations) for the iterations enqueued since profile_begin()."""
-        ms = (ctypes.c_float * 5)()
-        n = ctypes.c_int(0)
-        _check(lib().ddope_profile_end(self._h, ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(ctypes.byref(n), ctypes.c_void_p)))
-        return {k: float(ms[i]) for i, k in enumerate(self.KERNELS)}, int(n.value)
+        """-> ({kernel: total ms}, {kernel: launches}) for everything enqueued since profile_begin()."""
+        ms = (ctypes.c_float * 3)()
+        n = (ctypes.c_int * 3)()
+        _check(lib().ddope_profile_end(self._h, ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(n, ctypes.c_void_p)))
+        return {k: float(ms[i]) for i, k in enumerate(self.KERNELS)}, {k: int(n[i]) for i, k in enumerate(self.KERNELS)}
 
     def last_launch_count(self):
         return int(lib().ddope_last_launch_count(self._h))

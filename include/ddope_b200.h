@@ -160,12 +160,12 @@ int ddope_optimize(ddope_scene* s, float* quat_dev, float* trans_dev, const floa
 int64_t ddope_last_launch_count(const ddope_scene* s);
 
 /* Measurement hook (no reference counterpart; the reference has no timing code):
- * between begin and end, every iteration enqueued by ddope_loss_grad / ddope_optimize is bracketed
- * by CUDA events on the launching stream, per kernel. end() synchronises and returns the summed
- * milliseconds of the five kernels of an iteration in launch order
- * {pose, clear, raster, pixel, step} and the number of iterations covered. */
+ * between begin and end, every kernel launched by ddope_loss_grad / ddope_optimize is bracketed by
+ * CUDA events on the launching stream. end() synchronises and returns, per kernel class
+ * {0: iter_kernel (step + pose + clear), 1: raster_kernel, 2: pixel_kernel}, the summed milliseconds
+ * and the number of launches. */
 int ddope_profile_begin(ddope_scene* s);
-int ddope_profile_end(ddope_scene* s, float* ms_out5, int* iterations_out);
+int ddope_profile_end(ddope_scene* s, float* ms_out3, int* launches_out3);
 
 #ifdef __cplusplus
 }
