@@ -30,6 +30,8 @@ struct ddope_scene {
     float* uv = nullptr;
     float* tex = nullptr;
     float* vcol = nullptr;
+    float4* tripos = nullptr;
+    float4* tricol = nullptr;
     int* seg_bbox = nullptr;
     int* total_tiles = nullptr;
     SceneDev dev{};
@@ -163,6 +165,31 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
         CK(cudaMalloc(&s->vcol, sizeof(float) * 3 * V));
         CK(cudaMemcpy(s->vcol, vcol, sizeof(float) * 3 * V, cudaMemcpyHostToDevice));
     }
+    {   // per-triangle attribute records (see SceneDev::tripos)
+        std::vector<float4> rec((size_t)T * 4);
+        for (int t = 0; t < T; t++) {
+            float vv[3] = {0.f, 0.f, 0.f};
+            for (int k = 0; k < 3; k++) {
+                const int v = tri[3 * t + k];
+                float u = 0.f;
+                if (textured) { u = uv[2 * v]; vv[k] = uv[2 * v + 1]; }
+                rec[4 * (size_t)t + k] = make_float4(pos[3 * v], pos[3 * v + 1], pos[3 * v + 2], u);
+            }
+            rec[4 * (size_t)t + 3] = make_float4(vv[0], vv[1], vv[2], 0.f);
+        }
+        CK(cudaMalloc(&s->tripos, sizeof(float4) * rec.size()));
+        CK(cudaMemcpy(s->tripos, rec.data(), sizeof(float4) * rec.size(), cudaMemcpyHostToDevice));
+        if (!textured) {
+            std::vector<float4> col((size_t)T * 3);
+            for (int t = 0; t < T; t++)
+                for (int k = 0; k < 3; k++) {
+                    const int v = tri[3 * t + k];
+                    col[3 * (size_t)t + k] = make_float4(vcol[3 * v], vcol[3 * v + 1], vcol[3 * v + 2], 0.f);
+                }
+            CK(cudaMalloc(&s->tricol, sizeof(float4) * col.size()));
+            CK(cudaMemcpy(s->tricol, col.data(), sizeof(float4) * col.size(), cudaMemcpyHostToDevice));
+        }
+    }
     CK(cudaMalloc(&s->seg_bbox, sizeof(int) * 4));
     int init_bbox[4] = {1 << 30, 1 << 30, -1, -1};
     CK(cudaMemcpy(s->seg_bbox, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice));
@@ -171,7 +198,7 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     CK(cudaMemset(s->arrive, 0, sizeof(unsigned int)));
 
     SceneDev& d = s->dev;
-    d.pos = s->pos; d.tri = s->tri; d.opp = s->opp; d.uv = s->uv; d.tex = s->tex; d.vcol = s->vcol;
+    d.pos = s->pos; d.tri = s->tri; d.opp = s->opp; d.uv = s->uv; d.tex = s->tex; d.vcol = s->vcol; d.tripos = s->tripos; d.tricol = s->tricol;
     d.V = V; d.T = T; d.tex_h = textured ? tex_h : 0; d.tex_w = textured ? tex_w : 0;
     d.seg_bbox = s->seg_bbox;
     for (int k = 0; k < 3; k++) { d.bbmin[k] = 1e30f; d.bbmax[k] = -1e30f; }
@@ -190,7 +217,7 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
 
 extern "C" int ddope_scene_destroy(ddope_scene* s) {
     if (!s) return 0;
-    cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex); cudaFree(s->vcol);
+    cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex); cudaFree(s->vcol); cudaFree(s->tripos); cudaFree(s->tricol);
     cudaFree(s->seg_bbox); cudaFree(s->total_tiles); cudaFree(s->hyp); cudaFree(s->zbuf); cudaFree(s->partials);
     cudaFree(s->lr_sched); cudaFree(s->xfm_scratch); cudaFree(s->arrive);
     delete s;

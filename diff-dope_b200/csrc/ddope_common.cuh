@@ -30,6 +30,9 @@ struct SceneDev {
     const float* uv;     // [V,2] or null
     const float* tex;    // [tex_h,tex_w,3] or null
     const float* vcol;   // [V,3] or null
+    const float4* tripos;  // [T,4]: per-triangle (x,y,z,u) of its three vertices + (v0,v1,v2,0): one 64 B record,
+                           // so a pixel reaches its vertex data with one dependent load level instead of two
+    const float4* tricol;  // [T,3]: per-triangle vertex colours (untextured meshes) or null
     const float* gt_rgb;    // [H,W,3] or null
     const float* gt_depth;  // [H,W] or null
     const float* gt_seg;    // [H,W,seg_c] or null

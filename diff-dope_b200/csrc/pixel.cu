@@ -17,28 +17,48 @@ struct Shade {
     float u, v;
     float c0[4], c1[4], c2[4];  // clip verts
     float p0x, p0y, p1x, p1y, p2x, p2y, a0, a1, a2, fx, fy;
-    int i0, i1, i2;
+    float4 v0, v1, v2, vv;  // the triangle's attribute record: (x,y,z,u) per vertex, (v0,v1,v2,-)
 };
 
-// Barycentrics of pixel (px,py) w.r.t. triangle tri: nvdiffrast's fragment formula, exact ops.
-__device__ __forceinline__ void shade_setup(const SceneDev& S, const float* mvp, int tri, int px, int py, Shade& s) {
-    s.i0 = S.tri[3 * tri]; s.i1 = S.tri[3 * tri + 1]; s.i2 = S.tri[3 * tri + 2];
-    xfm_exact(mvp, S.pos[3 * s.i0], S.pos[3 * s.i0 + 1], S.pos[3 * s.i0 + 2], s.c0);
-    xfm_exact(mvp, S.pos[3 * s.i1], S.pos[3 * s.i1 + 1], S.pos[3 * s.i1 + 2], s.c1);
-    xfm_exact(mvp, S.pos[3 * s.i2], S.pos[3 * s.i2 + 1], S.pos[3 * s.i2 + 2], s.c2);
-    const float xs = xdiv(2.f, (float)S.W), xo = xsub(xdiv(1.f, (float)S.W), 1.f);
-    const float ys = xdiv(2.f, (float)S.H), yo = xsub(xdiv(1.f, (float)S.H), 1.f);
+// a op b with EXACT: separately rounded (bit-equal to the oracle, used when images are written);
+// without: plain expressions the compiler may contract into FMAs (loss / gradient passes, where the
+// coverage decision is already made and 1e-7 differences are far inside the 1e-4 budget).
+template <bool EXACT> __device__ __forceinline__ float mul_(float a, float b) { return EXACT ? __fmul_rn(a, b) : a * b; }
+template <bool EXACT> __device__ __forceinline__ float add_(float a, float b) { return EXACT ? __fadd_rn(a, b) : a + b; }
+template <bool EXACT> __device__ __forceinline__ float sub_(float a, float b) { return EXACT ? __fsub_rn(a, b) : a - b; }
+template <bool EXACT> __device__ __forceinline__ float msub_(float a, float b, float c) {  // a - b*c
+    return EXACT ? __fsub_rn(a, __fmul_rn(b, c)) : fmaf(-b, c, a);
+}
+template <bool EXACT> __device__ __forceinline__ void xfm_(const float* __restrict__ m, float x, float y, float z, float* c) {
+    if (EXACT) {
+        xfm_exact(m, x, y, z, c);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; r++) c[r] = fmaf(m[4 * r + 2], z, fmaf(m[4 * r + 1], y, fmaf(m[4 * r], x, m[4 * r + 3])));
+    }
+}
+
+// Barycentrics of pixel (px,py) w.r.t. triangle tri: nvdiffrast's fragment formula.
+template <bool EXACT>
+__device__ __forceinline__ void shade_setup(const SceneDev& S, const float* mvp, int tri, int px, int py, float xs, float xo,
+                                            float ys, float yo, Shade& s) {
+    const float4* rec = S.tripos + 4 * (size_t)tri;
+    s.v0 = rec[0]; s.v1 = rec[1]; s.v2 = rec[2]; s.vv = rec[3];
+    xfm_<EXACT>(mvp, s.v0.x, s.v0.y, s.v0.z, s.c0);
+    xfm_<EXACT>(mvp, s.v1.x, s.v1.y, s.v1.z, s.c1);
+    xfm_<EXACT>(mvp, s.v2.x, s.v2.y, s.v2.z, s.c2);
     s.fx = xadd(xmul(xs, (float)px), xo);
     s.fy = xadd(xmul(ys, (float)py), yo);
-    s.p0x = xsub(s.c0[0], xmul(s.fx, s.c0[3])); s.p0y = xsub(s.c0[1], xmul(s.fy, s.c0[3]));
-    s.p1x = xsub(s.c1[0], xmul(s.fx, s.c1[3])); s.p1y = xsub(s.c1[1], xmul(s.fy, s.c1[3]));
-    s.p2x = xsub(s.c2[0], xmul(s.fx, s.c2[3])); s.p2y = xsub(s.c2[1], xmul(s.fy, s.c2[3]));
-    s.a0 = xsub(xmul(s.p1x, s.p2y), xmul(s.p1y, s.p2x));
-    s.a1 = xsub(xmul(s.p2x, s.p0y), xmul(s.p2y, s.p0x));
-    s.a2 = xsub(xmul(s.p0x, s.p1y), xmul(s.p0y, s.p1x));
-    const float iw = xdiv(1.f, xadd(xadd(s.a0, s.a1), s.a2));
-    s.u = __saturatef(xmul(s.a0, iw));
-    s.v = __saturatef(xmul(s.a1, iw));
+    s.p0x = msub_<EXACT>(s.c0[0], s.fx, s.c0[3]); s.p0y = msub_<EXACT>(s.c0[1], s.fy, s.c0[3]);
+    s.p1x = msub_<EXACT>(s.c1[0], s.fx, s.c1[3]); s.p1y = msub_<EXACT>(s.c1[1], s.fy, s.c1[3]);
+    s.p2x = msub_<EXACT>(s.c2[0], s.fx, s.c2[3]); s.p2y = msub_<EXACT>(s.c2[1], s.fy, s.c2[3]);
+    s.a0 = sub_<EXACT>(mul_<EXACT>(s.p1x, s.p2y), mul_<EXACT>(s.p1y, s.p2x));
+    s.a1 = sub_<EXACT>(mul_<EXACT>(s.p2x, s.p0y), mul_<EXACT>(s.p2y, s.p0x));
+    s.a2 = sub_<EXACT>(mul_<EXACT>(s.p0x, s.p1y), mul_<EXACT>(s.p0y, s.p1x));
+    const float at = add_<EXACT>(add_<EXACT>(s.a0, s.a1), s.a2);
+    const float iw = EXACT ? xdiv(1.f, at) : __frcp_rn(at);
+    s.u = __saturatef(mul_<EXACT>(s.a0, iw));
+    s.v = __saturatef(mul_<EXACT>(s.a1, iw));
 }
 
 __device__ __forceinline__ float shade_zw(const Shade& s) {
@@ -62,11 +82,11 @@ __device__ __forceinline__ void raster_grad_accum(const SceneDev& S, const Shade
     gy[0] = gbb * (s.p1x - s.p2x) + gb1 * s.p2x;
     gy[1] = gbb * (s.p2x - s.p0x) - gb0 * s.p2x;
     gy[2] = gbb * (s.p0x - s.p1x) + gb0 * s.p1x - gb1 * s.p0x;
-    const int vi[3] = {s.i0, s.i1, s.i2};
+    const float4 vs[3] = {s.v0, s.v1, s.v2};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         gw[k] = -s.fx * gx[k] - s.fy * gy[k];
-        const float x = S.pos[3 * vi[k]], y = S.pos[3 * vi[k] + 1], z = S.pos[3 * vi[k] + 2];
+        const float x = vs[k].x, y = vs[k].y, z = vs[k].z;
         acc[0] += gx[k] * x; acc[1] += gx[k] * y; acc[2] += gx[k] * z; acc[3] += gx[k];
         acc[4] += gy[k] * x; acc[5] += gy[k] * y; acc[6] += gy[k] * z; acc[7] += gy[k];
         acc[8] += gw[k] * x; acc[9] += gw[k] * y; acc[10] += gw[k] * z; acc[11] += gw[k];
@@ -217,6 +237,9 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
 
     const int total = *total_tiles;
     const int tid = threadIdx.x;
+    // pixel centre -> NDC: fx = xs*px + xo (nvdiffrast's xs = 2/W, xo = 1/W - 1), hoisted out of the pixel loop
+    const float ndc_xs = xdiv(2.f, (float)S.W), ndc_xo = xsub(xdiv(1.f, (float)S.W), 1.f);
+    const float ndc_ys = xdiv(2.f, (float)S.H), ndc_yo = xsub(xdiv(1.f, (float)S.H), 1.f);
     const int lx = tid % TILE_W, ly0 = tid / TILE_W;  // this thread's pixels: (lx, ly0 + 8k), k = 0..3
 
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
@@ -411,17 +434,17 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
             float gu = 0.f, gv = 0.f;  // dL/d(u,v)
             if (id >= 0) {
                 Shade sh;
-                shade_setup(S, s_mvp, id, x, y, sh);
-                const float b0 = sh.u, b1 = sh.v, b2 = xsub(xsub(1.f, sh.u), sh.v);
-                const float* P0 = S.pos + 3 * sh.i0;
-                const float* P1 = S.pos + 3 * sh.i1;
-                const float* P2 = S.pos + 3 * sh.i2;
-                const float p0[3] = {P0[0], P0[1], P0[2]}, p1[3] = {P1[0], P1[1], P1[2]}, p2[3] = {P2[0], P2[1], P2[2]};
+                constexpr bool EX = (MODE == MODE_RENDER);
+                // barycentrics stay on the exactly-rounded path in every mode: sliver triangles amplify a 1-ulp change of
+                // the clip coordinates into 1e-3 of (u,v), which the 1e-4 gradient budget cannot absorb
+                shade_setup<true>(S, s_mvp, id, x, y, ndc_xs, ndc_xo, ndc_ys, ndc_yo, sh);
+                const float b0 = sh.u, b1 = sh.v, b2 = sub_<EX>(sub_<EX>(1.f, sh.u), sh.v);
+                const float p0[3] = {sh.v0.x, sh.v0.y, sh.v0.z}, p1[3] = {sh.v1.x, sh.v1.y, sh.v1.z}, p2[3] = {sh.v2.x, sh.v2.y, sh.v2.z};
                 // forward values use separately rounded ops in the oracle's order (bit-equal outputs)
                 float g[3];
 #pragma unroll
-                for (int k = 0; k < 3; k++) g[k] = xadd(xadd(xmul(b0, p0[k]), xmul(b1, p1[k])), xmul(b2, p2[k]));
-                depth = -xadd(xadd(xadd(xmul(s_m2[0], g[0]), xmul(s_m2[1], g[1])), xmul(s_m2[2], g[2])), s_m2[3]);
+                for (int k = 0; k < 3; k++) g[k] = add_<EX>(add_<EX>(mul_<EX>(b0, p0[k]), mul_<EX>(b1, p1[k])), mul_<EX>(b2, p2[k]));
+                depth = -add_<EX>(add_<EX>(add_<EX>(mul_<EX>(s_m2[0], g[0]), mul_<EX>(s_m2[1], g[1])), mul_<EX>(s_m2[2], g[2])), s_m2[3]);
 
                 float gd = 0.f;  // dL/d depth
                 if (MODE == MODE_LOSS && cfg.use_depth) {
@@ -441,15 +464,13 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                 }
                 const bool want_rgb_grad = (MODE == MODE_LOSS && cfg.use_rgb) || (MODE == MODE_EXT && ext.d_rgb);
                 if (S.tex) {
-                    const float2 t0 = *reinterpret_cast<const float2*>(S.uv + 2 * sh.i0);
-                    const float2 t1 = *reinterpret_cast<const float2*>(S.uv + 2 * sh.i1);
-                    const float2 t2 = *reinterpret_cast<const float2*>(S.uv + 2 * sh.i2);
-                    float tu = xadd(xadd(xmul(b0, t0.x), xmul(b1, t1.x)), xmul(b2, t2.x));
-                    float tv = xadd(xadd(xmul(b0, t0.y), xmul(b1, t1.y)), xmul(b2, t2.y));
-                    tu = xsub(tu, floorf(tu)); tv = xsub(tv, floorf(tv));
-                    tu = xsub(xmul(tu, (float)S.tex_w), 0.5f); tv = xsub(xmul(tv, (float)S.tex_h), 0.5f);
+                    const float2 t0 = make_float2(sh.v0.w, sh.vv.x), t1 = make_float2(sh.v1.w, sh.vv.y), t2 = make_float2(sh.v2.w, sh.vv.z);
+                    float tu = add_<EX>(add_<EX>(mul_<EX>(b0, t0.x), mul_<EX>(b1, t1.x)), mul_<EX>(b2, t2.x));
+                    float tv = add_<EX>(add_<EX>(mul_<EX>(b0, t0.y), mul_<EX>(b1, t1.y)), mul_<EX>(b2, t2.y));
+                    tu = sub_<EX>(tu, floorf(tu)); tv = sub_<EX>(tv, floorf(tv));
+                    tu = sub_<EX>(mul_<EX>(tu, (float)S.tex_w), 0.5f); tv = sub_<EX>(mul_<EX>(tv, (float)S.tex_h), 0.5f);
                     int iu0 = (int)floorf(tu), iv0 = (int)floorf(tv);
-                    const float fu = xsub(tu, (float)iu0), fv = xsub(tv, (float)iv0);
+                    const float fu = sub_<EX>(tu, (float)iu0), fv = sub_<EX>(tv, (float)iv0);
                     int iu1 = iu0 + 1, iv1 = iv0 + 1;
                     if (iu0 < 0) iu0 += S.tex_w;
                     if (iv0 < 0) iv0 += S.tex_h;
@@ -463,8 +484,8 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
                         const float v00 = a00[c], v10 = a10[c], v01 = a01[c], v11 = a11[c];
-                        const float top = xadd(v00, xmul(xsub(v10, v00), fu)), bot = xadd(v01, xmul(xsub(v11, v01), fu));
-                        rgb[c] = xadd(top, xmul(xsub(bot, top), fv));
+                        const float top = add_<EX>(v00, mul_<EX>(sub_<EX>(v10, v00), fu)), bot = add_<EX>(v01, mul_<EX>(sub_<EX>(v11, v01), fu));
+                        rgb[c] = add_<EX>(top, mul_<EX>(sub_<EX>(bot, top), fv));
                         if (want_rgb_grad) {
                             float dy;
                             if (MODE == MODE_LOSS) {
@@ -484,11 +505,13 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                         gu += gtu * (t0.x - t2.x) + gtv * (t0.y - t2.y);
                         gv += gtu * (t1.x - t2.x) + gtv * (t1.y - t2.y);
                     }
-                } else if (S.vcol) {
+                } else if (S.tricol) {
+                    const float4 q0 = S.tricol[3 * (size_t)id], q1 = S.tricol[3 * (size_t)id + 1], q2 = S.tricol[3 * (size_t)id + 2];
+                    const float kc0[3] = {q0.x, q0.y, q0.z}, kc1[3] = {q1.x, q1.y, q1.z}, kc2[3] = {q2.x, q2.y, q2.z};
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
-                        const float k0 = S.vcol[3 * sh.i0 + c], k1 = S.vcol[3 * sh.i1 + c], k2 = S.vcol[3 * sh.i2 + c];
-                        rgb[c] = xadd(xadd(xmul(b0, k0), xmul(b1, k1)), xmul(b2, k2));
+                        const float k0 = kc0[c], k1 = kc1[c], k2 = kc2[c];
+                        rgb[c] = add_<EX>(add_<EX>(mul_<EX>(b0, k0), mul_<EX>(b1, k1)), mul_<EX>(b2, k2));
                         if (want_rgb_grad) {
                             float dy;
                             if (MODE == MODE_LOSS) {

@@ -115,11 +115,11 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
     int X[3], Y[3];
     int lxmin = 0, lxmax = -1, lymin = 0, lymax = -1;
     if (t < S.T) {
-        const int i0 = S.tri[3 * t], i1 = S.tri[3 * t + 1], i2 = S.tri[3 * t + 2];
+        const float4 v0 = S.tripos[4 * (size_t)t], v1 = S.tripos[4 * (size_t)t + 1], v2 = S.tripos[4 * (size_t)t + 2];
         float c0[4], c1[4], c2[4];
-        xfm_exact(s_mvp, S.pos[3 * i0], S.pos[3 * i0 + 1], S.pos[3 * i0 + 2], c0);
-        xfm_exact(s_mvp, S.pos[3 * i1], S.pos[3 * i1 + 1], S.pos[3 * i1 + 2], c1);
-        xfm_exact(s_mvp, S.pos[3 * i2], S.pos[3 * i2 + 1], S.pos[3 * i2 + 2], c2);
+        xfm_exact(s_mvp, v0.x, v0.y, v0.z, c0);
+        xfm_exact(s_mvp, v1.x, v1.y, v1.z, c1);
+        xfm_exact(s_mvp, v2.x, v2.y, v2.z, c2);
         const float hw = xmul((float)S.W, 0.5f), hh = xmul((float)S.H, 0.5f);
         const float sx0 = xadd(xmul(xdiv(c0[0], c0[3]), hw), hw), sy0 = xadd(xmul(xdiv(c0[1], c0[3]), hh), hh);
         const float sx1 = xadd(xmul(xdiv(c1[0], c1[3]), hw), hw), sy1 = xadd(xmul(xdiv(c1[1], c1[3]), hh), hh);
