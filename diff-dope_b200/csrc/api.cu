@@ -193,7 +193,7 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     CK(cudaMalloc(&s->seg_bbox, sizeof(int) * 4));
     int init_bbox[4] = {1 << 30, 1 << 30, -1, -1};
     CK(cudaMemcpy(s->seg_bbox, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&s->total_tiles, sizeof(int)));
+    CK(cudaMalloc(&s->total_tiles, sizeof(int) * 2));  // [0] tile count, [1] pixel kernel work counter
     CK(cudaMalloc(&s->arrive, sizeof(unsigned int)));
     CK(cudaMemset(s->arrive, 0, sizeof(unsigned int)));
 

@@ -242,7 +242,19 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
     const float ndc_ys = xdiv(2.f, (float)S.H), ndc_yo = xsub(xdiv(1.f, (float)S.H), 1.f);
     const int lx = tid % TILE_W, ly0 = tid / TILE_W;  // this thread's pixels: (lx, ly0 + 8k), k = 0..3
 
+#if DYN_TILES
+    // work items are handed out by an atomic counter: tiles differ a lot in cost (silhouette tiles,
+    // fully covered tiles, target-only tiles), static striding left ~10 % of the SMs idle at the end
+    int* work_counter = const_cast<int*>(total_tiles) + 1;  // reset to 0 by whichever kernel wrote total_tiles
+    __shared__ int s_item;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total) break;
+#else
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
+#endif
         // locate the hypothesis owning this work item (one load per thread instead of a serial search)
         for (int bb = tid; bb < B; bb += TILE_THREADS) {
             const int base = hyp[bb].tile_base;

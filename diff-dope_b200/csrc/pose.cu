@@ -135,7 +135,10 @@ __global__ void __launch_bounds__(256) pose_kernel(SceneDev S, const float* __re
         if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total_tiles = s_carry;
+    if (threadIdx.x == 0) {
+        total_tiles[0] = s_carry;
+        total_tiles[1] = 0;  // pixel kernel's work counter
+    }
 }
 
 void launch_pose(const SceneDev& S, const float* quat, const float* trans, const float* mtx_in, const float* lr_mult,
@@ -334,7 +337,8 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, HypState
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        *total_tiles = s_carry;
+        total_tiles[0] = s_carry;
+        total_tiles[1] = 0;  // pixel kernel's work counter
         *arrive = 0u;
     }
 }
