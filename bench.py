@@ -248,7 +248,7 @@ def run_ours(args):
     # ---- timed: K iterations, one C-ABI call each, L2 flushed between them ----------------------
     qd, td = fresh_pose()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    loss_tab = torch.empty(K, B, 3, device=dev)
+    loss_tab = torch.empty(K, B, nat.NUM_LOSSES, device=dev)
     pose_tab = torch.empty(K, B, 7, device=dev)
     barrier()
     launches = 0

@@ -1,5 +1,6 @@
 // C ABI of libddope_b200 (include/ddope_b200.h): scene objects, work buffers, kernel sequencing.
 // No torch, no host threads, one stream per call.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -28,7 +29,14 @@ struct ddope_scene {
     int* tri = nullptr;
     int* opp = nullptr;
     float* uv = nullptr;
-    float* tex = nullptr;
+    float4* tex4 = nullptr;   // texel chain (level 0, then the mip levels once the mipmap filter was requested)
+    float* gt_edge = nullptr; // [H,W] Sobel magnitude of the target (edge loss)
+    size_t gt_edge_cap = 0;
+    bool gt_edge_dirty = true;
+    ddope_optim_cfg optim = {DDOPE_OPT_SGD, 0.9f, 0.999f, 1e-8f, 0};
+    float* adam_state = nullptr;  // [B,14]
+    int adam_cap = 0;
+    int hyp_cur = 0;          // which half of `hyp` the current iteration reads
     float* vcol = nullptr;
     float4* tripos = nullptr;
     float4* tricol = nullptr;
@@ -52,6 +60,7 @@ struct ddope_scene {
     std::vector<cudaEvent_t> prof_events;  // (start, stop) per launch
     std::vector<int> prof_class;           // kernel class of each pair
     unsigned int* arrive = nullptr;        // CTA arrival counter of iter_kernel's last-block scan
+    std::vector<float> sched_host;         // staging of the per-iteration scalars (must outlive the async copy)
 };
 
 extern "C" int ddope_abi_version(void) { return DDOPE_ABI_VERSION; }
@@ -158,9 +167,14 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     if (textured) {
         CK(cudaMalloc(&s->uv, sizeof(float) * 2 * V));
         CK(cudaMemcpy(s->uv, uv, sizeof(float) * 2 * V, cudaMemcpyHostToDevice));
-        size_t nb = sizeof(float) * 3 * (size_t)tex_h * tex_w;
-        CK(cudaMalloc(&s->tex, nb));
-        CK(cudaMemcpy(s->tex, tex, nb, cudaMemcpyHostToDevice));
+        const size_t ntex = (size_t)tex_h * tex_w;
+        float* tex3 = nullptr;
+        CK(cudaMalloc(&tex3, sizeof(float) * 3 * ntex));
+        CK(cudaMemcpy(tex3, tex, sizeof(float) * 3 * ntex, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&s->tex4, sizeof(float4) * ntex));
+        launch_tex_pack(tex3, ntex, s->tex4, 0);
+        CK(cudaDeviceSynchronize());
+        CK(cudaFree(tex3));
     } else {
         CK(cudaMalloc(&s->vcol, sizeof(float) * 3 * V));
         CK(cudaMemcpy(s->vcol, vcol, sizeof(float) * 3 * V, cudaMemcpyHostToDevice));
@@ -198,8 +212,11 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     CK(cudaMemset(s->arrive, 0, sizeof(unsigned int)));
 
     SceneDev& d = s->dev;
-    d.pos = s->pos; d.tri = s->tri; d.opp = s->opp; d.uv = s->uv; d.tex = s->tex; d.vcol = s->vcol; d.tripos = s->tripos; d.tricol = s->tricol;
+    d.pos = s->pos; d.tri = s->tri; d.opp = s->opp; d.uv = s->uv; d.tex4 = s->tex4; d.vcol = s->vcol; d.tripos = s->tripos; d.tricol = s->tricol;
     d.V = V; d.T = T; d.tex_h = textured ? tex_h : 0; d.tex_w = textured ? tex_w : 0;
+    d.tex_levels = textured ? 1 : 0; d.tex_filter = DDOPE_TEX_LINEAR;
+    for (int l = 0; l < MAX_MIP; l++) d.tex_off[l] = 0;
+    d.gt_edge = nullptr;
     d.seg_bbox = s->seg_bbox;
     for (int k = 0; k < 3; k++) { d.bbmin[k] = 1e30f; d.bbmax[k] = -1e30f; }
     for (int v = 0; v < V; v++)
@@ -217,7 +234,7 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
 
 extern "C" int ddope_scene_destroy(ddope_scene* s) {
     if (!s) return 0;
-    cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex); cudaFree(s->vcol); cudaFree(s->tripos); cudaFree(s->tricol);
+    cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex4); cudaFree(s->vcol); cudaFree(s->gt_edge); cudaFree(s->adam_state); cudaFree(s->tripos); cudaFree(s->tricol);
     cudaFree(s->seg_bbox); cudaFree(s->total_tiles); cudaFree(s->hyp); cudaFree(s->zbuf); cudaFree(s->partials);
     cudaFree(s->lr_sched); cudaFree(s->xfm_scratch); cudaFree(s->arrive);
     delete s;
@@ -226,6 +243,7 @@ extern "C" int ddope_scene_destroy(ddope_scene* s) {
 
 static void set_window(ddope_scene* s, int y0, int x0, int h, int w) {
     SceneDev& d = s->dev;
+    s->gt_edge_dirty = true;
     d.wy0 = y0; d.wx0 = x0; d.wh = h; d.ww = w;
     int zx0 = x0 - 1 < 0 ? 0 : x0 - 1, zy0 = y0 - 1 < 0 ? 0 : y0 - 1;
     int zx1 = x0 + w + 1 > d.W ? d.W : x0 + w + 1, zy1 = y0 + h + 1 > d.H ? d.H : y0 + h + 1;
@@ -261,6 +279,7 @@ extern "C" int ddope_scene_set_target(ddope_scene* s, const float* rgb, const fl
     if (seg && !(seg_c == 1 || seg_c == 3)) return fail("ddope_scene_set_target: seg_c must be 1 or 3");
     SceneDev& d = s->dev;
     d.gt_rgb = rgb; d.gt_depth = depth; d.gt_seg = seg;
+    s->gt_edge_dirty = true;
     d.seg_pix_stride = seg ? seg_c : 0;
     d.seg_ch_stride = (seg && seg_c == 3) ? 1 : 0;
     if (seg) {
@@ -270,20 +289,67 @@ extern "C" int ddope_scene_set_target(ddope_scene* s, const float* rgb, const fl
     return 0;
 }
 
+extern "C" int ddope_scene_set_texture_filter(ddope_scene* s, int mode, int max_levels) {
+    if (!s) return fail("ddope_scene_set_texture_filter: null scene");
+    if (mode != DDOPE_TEX_LINEAR && mode != DDOPE_TEX_MIPMAP) return fail("ddope_scene_set_texture_filter: unknown filter mode");
+    SceneDev& d = s->dev;
+    if (!d.tex4) return 0;  // vertex-coloured mesh: nothing to filter
+    if (mode == DDOPE_TEX_MIPMAP) {
+        int want = 1;
+        for (int w = d.tex_w, h = d.tex_h; (w > 1 || h > 1) && want < MAX_MIP; w = w > 1 ? w >> 1 : 1, h = h > 1 ? h >> 1 : 1) want++;
+        if (max_levels > 0 && max_levels < want) want = max_levels;
+        if (want != d.tex_levels) {  // (re)build the chain: level 0 is kept, the others are 2x2 box filters of the previous one
+            size_t total = 0;
+            unsigned int off[MAX_MIP];
+            int lw[MAX_MIP], lh[MAX_MIP];
+            for (int l = 0, w = d.tex_w, h = d.tex_h; l < want; l++, w = w > 1 ? w >> 1 : 1, h = h > 1 ? h >> 1 : 1) {
+                off[l] = (unsigned int)total; lw[l] = w; lh[l] = h;
+                total += (size_t)w * h;
+            }
+            float4* chain = nullptr;
+            CK(cudaMalloc(&chain, sizeof(float4) * total));
+            CK(cudaMemcpy(chain, s->tex4, sizeof(float4) * (size_t)d.tex_w * d.tex_h, cudaMemcpyDeviceToDevice));
+            for (int l = 1; l < want; l++) launch_tex_mip(chain + off[l - 1], lw[l - 1], lh[l - 1], chain + off[l], lw[l], lh[l], 0);
+            CK(cudaDeviceSynchronize());
+            CK(cudaFree(s->tex4));
+            s->tex4 = chain;
+            d.tex4 = chain;
+            d.tex_levels = want;
+            for (int l = 0; l < want; l++) d.tex_off[l] = off[l];
+        }
+    }
+    d.tex_filter = mode;
+    return 0;
+}
+
+extern "C" int ddope_scene_set_optimizer(ddope_scene* s, const ddope_optim_cfg* cfg) {
+    if (!s || !cfg) return fail("ddope_scene_set_optimizer: null pointer");
+    if (cfg->kind != DDOPE_OPT_SGD && cfg->kind != DDOPE_OPT_ADAM) return fail("ddope_scene_set_optimizer: unknown optimizer kind");
+    if (cfg->kind == DDOPE_OPT_ADAM) {
+        if (!(cfg->beta1 >= 0.f && cfg->beta1 < 1.f) || !(cfg->beta2 >= 0.f && cfg->beta2 < 1.f) || !(cfg->eps >= 0.f) || cfg->step0 < 0)
+            return fail("ddope_scene_set_optimizer: need 0 <= beta1, beta2 < 1, eps >= 0, step0 >= 0");
+    }
+    s->optim = *cfg;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // hot path
 
-static int ensure_buffers(ddope_scene* s, int B, bool need_partials) {
+// Work buffers. The z-buffer invariant: every key is EMPTY between API calls (each path restores the region it
+// rasterised into), so it is initialised once here, on the caller's stream.
+static int ensure_buffers(ddope_scene* s, int B, bool need_partials, cudaStream_t st) {
     const SceneDev& d = s->dev;
     if (B > s->hyp_cap) {
         if (s->hyp) CK(cudaFree(s->hyp));
-        CK(cudaMalloc(&s->hyp, sizeof(HypState) * (size_t)B));
+        CK(cudaMalloc(&s->hyp, sizeof(HypState) * 2 * (size_t)B));  // two halves: iterations alternate between them
         s->hyp_cap = B;
     }
     size_t zneed = (size_t)B * d.zh * d.zw;
     if (zneed > s->zbuf_cap) {
         if (s->zbuf) CK(cudaFree(s->zbuf));
         CK(cudaMalloc(&s->zbuf, sizeof(unsigned long long) * zneed));
+        CK(cudaMemsetAsync(s->zbuf, 0xFF, sizeof(unsigned long long) * zneed, st));
         s->zbuf_cap = zneed;
     }
     if (need_partials) {
@@ -308,6 +374,7 @@ static LossCfgDev to_dev(const ddope_loss_cfg* c) {
     LossCfgDev o;
     o.use_rgb = c->use_rgb != 0; o.use_depth = c->use_depth != 0; o.use_mask = c->use_mask != 0;
     o.w_rgb = c->weight_rgb; o.w_depth = c->weight_depth; o.w_mask = c->weight_mask;
+    o.use_edge = c->use_edge != 0; o.w_edge = c->weight_edge;
     return o;
 }
 
@@ -315,10 +382,31 @@ static int check_loss_inputs(const ddope_scene* s, const ddope_loss_cfg* cfg, co
     const SceneDev& d = s->dev;
     if (!s->have_camera) return fail(std::string(who) + ": set the camera first");
     if (!cfg) return fail(std::string(who) + ": null loss config");
-    if (!(cfg->use_rgb || cfg->use_depth || cfg->use_mask)) return fail(std::string(who) + ": no loss enabled");
+    if (!(cfg->use_rgb || cfg->use_depth || cfg->use_mask || cfg->use_edge)) return fail(std::string(who) + ": no loss enabled");
+    if (cfg->use_edge && !d.gt_rgb) return fail(std::string(who) + ": edge loss needs the rgb target");
     if (!d.gt_seg) return fail(std::string(who) + ": every reference loss needs the segmentation target");
     if (cfg->use_rgb && !d.gt_rgb) return fail(std::string(who) + ": rgb loss needs the rgb target");
     if (cfg->use_depth && !d.gt_depth) return fail(std::string(who) + ": depth loss needs the depth target");
+    return 0;
+}
+
+// Edge loss: the target's Sobel magnitude over the current window, recomputed when target or window changed.
+static int prepare_edge(ddope_scene* s, const ddope_loss_cfg* cfg, cudaStream_t st) {
+    if (!cfg->use_edge) return 0;
+    SceneDev& d = s->dev;
+    const size_t need = (size_t)d.H * d.W;
+    if (need > s->gt_edge_cap) {
+        if (s->gt_edge) CK(cudaFree(s->gt_edge));
+        CK(cudaMalloc(&s->gt_edge, sizeof(float) * need));
+        s->gt_edge_cap = need;
+        s->gt_edge_dirty = true;
+    }
+    d.gt_edge = s->gt_edge;
+    if (s->gt_edge_dirty) {
+        launch_gt_edge(d, s->gt_edge, st);
+        CK(cudaGetLastError());
+        s->gt_edge_dirty = false;
+    }
     return 0;
 }
 
@@ -328,13 +416,13 @@ static int render_common(ddope_scene* s, const float* quat, const float* trans, 
     if (B <= 0 || B > 65535) return fail(std::string(who) + ": B must be in [1, 65535]");
     if (!s->have_camera) return fail(std::string(who) + ": set the camera first");
     cudaStream_t st = (cudaStream_t)stream;
-    if (int r = ensure_buffers(s, B, false)) return r;
-    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f};
+    if (int r = ensure_buffers(s, B, false, st)) return r;
+    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
     launch_pose(s->dev, quat, trans, mtx_in, nullptr, B, B, cfg, 0, s->hyp, s->total_tiles, st);
-    launch_clear(s->dev, s->hyp, B, s->zbuf, st);
     launch_raster(s->dev, s->hyp, B, s->zbuf, st);
     RenderOut out = {rgb, depth, mask, rast};
     launch_pixel_render(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), s->zbuf, out, s->num_sms, st);
+    launch_clear(s->dev, s->hyp, B, s->zbuf, st);  // restore the z-buffer invariant
     s->launches = 4;
     if (mtx) {
         launch_copy_mtx(s->hyp, B, mtx, st);
@@ -360,15 +448,14 @@ extern "C" int ddope_render_bwd(ddope_scene* s, const float* mtx_in, int B, cons
     if (B <= 0 || B > 65535) return fail("ddope_render_bwd: B must be in [1, 65535]");
     if (!s->have_camera) return fail("ddope_render_bwd: set the camera first");
     cudaStream_t st = (cudaStream_t)stream;
-    if (int r = ensure_buffers(s, B, true)) return r;
-    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f};
+    if (int r = ensure_buffers(s, B, true, st)) return r;
+    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
     launch_pose(s->dev, nullptr, nullptr, mtx_in, nullptr, B, B, cfg, 0, s->hyp, s->total_tiles, st);
-    launch_clear(s->dev, s->hyp, B, s->zbuf, st);
     launch_raster(s->dev, s->hyp, B, s->zbuf, st);
     ExtGrad ext = {d_rgb, d_depth, d_mask};
     launch_pixel_ext(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), s->zbuf, ext, s->partials, s->num_sms, st);
-    launch_step(s->dev, s->hyp, s->partials, B, cfg, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                nullptr, d_mtx, st);
+    launch_step(s->dev, s->hyp, s->partials, B, cfg, d_mtx, st);
+    launch_clear(s->dev, s->hyp, B, s->zbuf, st);  // restore the z-buffer invariant
     s->launches = 5;
     CK(cudaGetLastError());
     return 0;
@@ -398,32 +485,46 @@ struct ProfMark {
     }
 };
 
-// [pose + z clear + tile prefix] of the first iteration
+static OptimDev optim_dev(const ddope_scene* s, int n_iters) {
+    OptimDev o;
+    o.kind = s->optim.kind; o.beta1 = s->optim.beta1; o.beta2 = s->optim.beta2; o.eps = s->optim.eps;
+    o.state = s->adam_state;
+    o.step_size = s->lr_sched ? s->lr_sched + n_iters : nullptr;
+    o.bc2_sqrt = s->lr_sched ? s->lr_sched + 2 * (size_t)n_iters : nullptr;
+    return o;
+}
+
+// [pose + tile prefix] of the first iteration
 static void enqueue_prologue(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
-                             LossCfgDev cfg, cudaStream_t st) {
+                             LossCfgDev cfg, OptimDev opt, cudaStream_t st) {
     ProfMark m(s, st, K_ITER);
-    launch_iter(s->dev, s->hyp, s->partials, B, B_global, cfg, quat, trans, lr_mult, s->lr_sched, 0, 0, 0, 1, nullptr, nullptr,
-                nullptr, nullptr, s->zbuf, s->total_tiles, s->arrive, st);
+    s->hyp_cur = 0;
+    launch_iter(s->dev, s->hyp, s->hyp, s->partials, B, B_global, cfg, opt, quat, trans, lr_mult, s->lr_sched, 0, 0, 0, 1, nullptr,
+                nullptr, nullptr, nullptr, s->zbuf, s->total_tiles, s->arrive, st);
     s->launches += 1;
 }
 
-// raster + pixel of iteration `it`, then one launch that finishes it and (if more follow) sets up the next
+// raster + pixel of iteration `it`, then one launch that finishes it (step, z-buffer restore) and, if more
+// follow, sets up the next one
 static void enqueue_iteration(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
-                              LossCfgDev cfg, int it, int do_update, int more, float* loss_table, float* grad,
+                              LossCfgDev cfg, OptimDev opt, int it, int do_update, int more, float* loss_table, float* grad,
                               float* pose_hist, float* loss_hist, cudaStream_t st) {
+    HypState* cur = s->hyp + (size_t)s->hyp_cur * s->hyp_cap;
+    HypState* nxt = s->hyp + (size_t)(s->hyp_cur ^ 1) * s->hyp_cap;
     {
         ProfMark m(s, st, K_RASTER);
-        launch_raster(s->dev, s->hyp, B, s->zbuf, st);
+        launch_raster(s->dev, cur, B, s->zbuf, st);
     }
     {
         ProfMark m(s, st, K_PIXEL);
-        launch_pixel_loss(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), cfg, s->zbuf, s->partials, s->num_sms, st);
+        launch_pixel_loss(s->dev, cur, s->total_tiles, B, max_tiles(s, B), cfg, s->zbuf, s->partials, s->num_sms, st);
     }
     {
         ProfMark m(s, st, K_ITER);
-        launch_iter(s->dev, s->hyp, s->partials, B, B_global, cfg, quat, trans, lr_mult, s->lr_sched, it, 1, do_update, more,
+        launch_iter(s->dev, cur, nxt, s->partials, B, B_global, cfg, opt, quat, trans, lr_mult, s->lr_sched, it, 1, do_update, more,
                     loss_table, grad, pose_hist, loss_hist, s->zbuf, s->total_tiles, s->arrive, st);
     }
+    s->hyp_cur ^= 1;
     s->launches += 3;
 }
 
@@ -434,10 +535,12 @@ extern "C" int ddope_loss_grad(ddope_scene* s, const float* quat, const float* t
     if (B <= 0 || B > 65535 || B_global < B) return fail("ddope_loss_grad: need 1 <= B <= 65535 and B_global >= B");
     if (int r = check_loss_inputs(s, cfg, "ddope_loss_grad")) return r;
     cudaStream_t st = (cudaStream_t)stream;
-    if (int r = ensure_buffers(s, B, true)) return r;
+    if (int r = ensure_buffers(s, B, true, st)) return r;
+    if (int r = prepare_edge(s, cfg, st)) return r;
     s->launches = 0;
-    enqueue_prologue(s, const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B, B_global, to_dev(cfg), st);
-    enqueue_iteration(s, const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B, B_global, to_dev(cfg), 0, 0, 0,
+    OptimDev opt = {0, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr};
+    enqueue_prologue(s, const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B, B_global, to_dev(cfg), opt, st);
+    enqueue_iteration(s, const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B, B_global, to_dev(cfg), opt, 0, 0, 0,
                       loss_table, grad, nullptr, nullptr, st);
     CK(cudaGetLastError());
     return 0;
@@ -451,18 +554,41 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     if (n_iters <= 0) return fail("ddope_optimize: n_iters must be positive");
     if (int r = check_loss_inputs(s, cfg, "ddope_optimize")) return r;
     cudaStream_t st = (cudaStream_t)stream;
-    if (int r = ensure_buffers(s, B, true)) return r;
+    if (int r = ensure_buffers(s, B, true, st)) return r;
+    if (int r = prepare_edge(s, cfg, st)) return r;
     if (n_iters > s->lr_cap) {
         if (s->lr_sched) CK(cudaFree(s->lr_sched));
-        CK(cudaMalloc(&s->lr_sched, sizeof(float) * n_iters));
+        CK(cudaMalloc(&s->lr_sched, sizeof(float) * 3 * (size_t)n_iters));
         s->lr_cap = n_iters;
     }
-    CK(cudaMemcpyAsync(s->lr_sched, lr_sched, sizeof(float) * n_iters, cudaMemcpyHostToDevice, st));
+    // per-iteration scalars, computed in double like torch's Python side: lr_t | lr_t / (1 - beta1^t) | sqrt(1 - beta2^t)
+    s->sched_host.resize(3 * (size_t)n_iters);
+    for (int it = 0; it < n_iters; it++) {
+        const double t = (double)s->optim.step0 + it + 1;
+        const double bc1 = 1.0 - std::pow((double)s->optim.beta1, t), bc2 = 1.0 - std::pow((double)s->optim.beta2, t);
+        s->sched_host[it] = lr_sched[it];
+        s->sched_host[n_iters + it] = (float)((double)lr_sched[it] / bc1);
+        s->sched_host[2 * (size_t)n_iters + it] = (float)std::sqrt(bc2);
+    }
+    // sized for lr_cap so the three sections stay at offsets 0, n_iters, 2 n_iters of this call
+    CK(cudaMemcpyAsync(s->lr_sched, s->sched_host.data(), sizeof(float) * 3 * (size_t)n_iters, cudaMemcpyHostToDevice, st));
+    if (s->optim.kind == DDOPE_OPT_ADAM) {
+        if (B > s->adam_cap) {
+            if (s->optim.step0 > 0 && s->adam_state) return fail("ddope_optimize: Adam continuation (step0 > 0) with a larger batch than the stored moments");
+            if (s->adam_state) CK(cudaFree(s->adam_state));
+            CK(cudaMalloc(&s->adam_state, sizeof(float) * 14 * (size_t)B));
+            s->adam_cap = B;
+            CK(cudaMemsetAsync(s->adam_state, 0, sizeof(float) * 14 * (size_t)B, st));
+        } else if (s->optim.step0 == 0) {
+            CK(cudaMemsetAsync(s->adam_state, 0, sizeof(float) * 14 * (size_t)B, st));
+        }
+    }
     LossCfgDev c = to_dev(cfg);
+    OptimDev opt = optim_dev(s, n_iters);
     s->launches = 0;
-    enqueue_prologue(s, quat, trans, lr_mult, B, B_global, c, st);
+    enqueue_prologue(s, quat, trans, lr_mult, B, B_global, c, opt, st);
     for (int it = 0; it < n_iters; it++)
-        enqueue_iteration(s, quat, trans, lr_mult, B, B_global, c, it, 1, it + 1 < n_iters, nullptr, nullptr, pose_hist,
+        enqueue_iteration(s, quat, trans, lr_mult, B, B_global, c, opt, it, 1, it + 1 < n_iters, nullptr, nullptr, pose_hist,
                           loss_hist, st);
     CK(cudaGetLastError());
     return 0;

@@ -8,10 +8,12 @@ namespace ddope {
 constexpr int TILE_W = 32;
 constexpr int TILE_H = 32;        // one work item of the pixel pass: 32x32 px, 4 px per thread
 constexpr int TILE_THREADS = 256;
-constexpr int NACC = 20;  // 12 dMVP(rows x,y,w) + 4 dM(row z) + 3 loss sums + 1 pad
+constexpr int NACC = 20;  // 12 dMVP(rows x,y,w) + 4 dM(row z) + 4 loss sums (rgb, depth, mask, edge)
 constexpr unsigned long long EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
 constexpr int SUBPIX = 256;
 constexpr float COORD_LIMIT = 1048576.f;  // 2^20 px
+constexpr int MAX_MIP = 15;               // 16384^2 down to 1x1
+constexpr int NLOSS = 4;                  // rgb, depth, mask, edge (include/ddope_b200.h DDOPE_NUM_LOSSES)
 
 // ---------------------------------------------------------------------------------------------
 // Separately-rounded IEEE float32 ops. Everything that feeds a discrete decision (snapping,
@@ -28,7 +30,7 @@ struct SceneDev {
     const int* tri;      // [T,3]
     const int* opp;      // [T,3] opposite vertex across edge i, or -1
     const float* uv;     // [V,2] or null
-    const float* tex;    // [tex_h,tex_w,3] or null
+    const float4* tex4;  // texels as (r,g,b,-), mip levels 0..tex_levels-1 back to back (level l at tex_off[l]), or null
     const float* vcol;   // [V,3] or null
     const float4* tripos;  // [T,4]: per-triangle (x,y,z,u) of its three vertices + (v0,v1,v2,0): one 64 B record,
                            // so a pixel reaches its vertex data with one dependent load level instead of two
@@ -36,8 +38,11 @@ struct SceneDev {
     const float* gt_rgb;    // [H,W,3] or null
     const float* gt_depth;  // [H,W] or null
     const float* gt_seg;    // [H,W,seg_c] or null
+    const float* gt_edge;   // [H,W] Sobel magnitude of the target's grey image, zero-padded at the loss window (edge loss) or null
     const int* seg_bbox;    // device int[4]: xmin,ymin,xmax,ymax of seg != 0 (inclusive); xmin > xmax if none
     int V, T, tex_h, tex_w;
+    int tex_levels, tex_filter;      // levels present in tex4; 0 = bilinear on level 0, 1 = trilinear over the chain
+    unsigned int tex_off[MAX_MIP];   // texel offset of each level in tex4
     int seg_pix_stride, seg_ch_stride;
     int H, W;                // frame
     int wy0, wx0, wh, ww;    // loss window
@@ -54,12 +59,24 @@ struct __align__(16) HypState {
     float qnorm;
     float k_rgb, k_depth, k_mask;  // d loss / d pixel value scale: w_k * lr_b / (B_global * P * C)
     int rx0, ry0, rx1, ry1;        // loss ROI in frame pixels, [rx0,rx1) x [ry0,ry1)
-    int tiles_x, tiles_y, tile_base, pad0;
+    int tiles_x, tiles_y, tile_base;
+    float k_edge;
 };
 
 struct LossCfgDev {
     int use_rgb, use_depth, use_mask;
     float w_rgb, w_depth, w_mask;
+    int use_edge;
+    float w_edge;
+};
+
+// Parameter update of ddope_optimize: kind 0 = SGD (reference), 1 = Adam (extension).
+struct OptimDev {
+    int kind;
+    float beta1, beta2, eps;
+    float* state;            // [B,14]: first and second moment of the 7 parameters
+    const float* step_size;  // [n_iters]: lr_t / (1 - beta1^t)
+    const float* bc2_sqrt;   // [n_iters]: sqrt(1 - beta2^t)
 };
 
 __device__ __forceinline__ void xfm_exact(const float* __restrict__ m, float x, float y, float z, float* c) {

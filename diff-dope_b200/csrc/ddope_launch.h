@@ -9,15 +9,14 @@ namespace ddope {
 // mtx_in != null: take M = mtx_in[b] instead of building it from quat/trans.
 void launch_pose(const SceneDev& S, const float* quat, const float* trans, const float* mtx_in, const float* lr_mult,
                  int B, int B_global, LossCfgDev cfg, int roi_mode, HypState* hyp, int* total_tiles, cudaStream_t st);
-// Reduce tile partials per hypothesis, chain to d(quat,trans), optionally apply the SGD step.
-void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg,
-                 float* quat, float* trans, const float* lr_sched, int it, int do_update, float* loss_table,
-                 float* grad_out, float* pose_hist, float* loss_hist, float* dmtx_out, cudaStream_t st);
-// Fused iteration boundary: [step of iteration it] + [pose, z clear, tile prefix of the next iteration].
-void launch_iter(const SceneDev& S, HypState* hyp, const float* partials, int B, int B_global, LossCfgDev cfg, float* quat,
-                 float* trans, const float* lr_mult, const float* lr_sched, int it, int do_step, int do_update, int do_pose,
-                 float* loss_table, float* grad_out, float* pose_hist, float* loss_hist, unsigned long long* zbuf,
-                 int* total_tiles, unsigned int* arrive, cudaStream_t st);
+// Reduce tile partials per hypothesis and chain to dL/dM (ddope_render_bwd).
+void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg, float* dmtx_out,
+                 cudaStream_t st);
+// Fused iteration boundary: [step of iteration it + z-buffer restore] + [pose, tile prefix of the next iteration].
+void launch_iter(const SceneDev& S, const HypState* hyp_old, HypState* hyp_new, const float* partials, int B, int B_global,
+                 LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, const float* lr_sched, int it,
+                 int do_step, int do_update, int do_pose, float* loss_table, float* grad_out, float* pose_hist,
+                 float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, cudaStream_t st);
 void launch_seg_bbox(const float* seg, int H, int W, int seg_c, int* bbox4, cudaStream_t st);
 void launch_copy_mtx(const HypState* hyp, int B, float* mtx, cudaStream_t st);
 
@@ -43,6 +42,10 @@ void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_
                        LossCfgDev cfg, const unsigned long long* zbuf, float* partials, int num_sms, cudaStream_t st);
 void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                          const unsigned long long* zbuf, RenderOut out, int num_sms, cudaStream_t st);
+
+void launch_gt_edge(const SceneDev& S, float* out, cudaStream_t st);
+void launch_tex_pack(const float* tex3, size_t n, float4* out, cudaStream_t st);
+void launch_tex_mip(const float4* src, int sw, int sh, float4* dst, int dw, int dh, cudaStream_t st);
 
 // xfm.cu
 void launch_xfm_fwd(const float* points, int Bp, int N, const float* matrix, int B, int is_points, float* out,

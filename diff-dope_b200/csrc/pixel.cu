@@ -67,6 +67,109 @@ __device__ __forceinline__ float shade_zw(const Shade& s) {
     return xdiv(z, w);
 }
 
+// One bilinear, wrap-mode lookup on one level of the texel chain (nvdiffrast TextureFwdKernelLinear's
+// indexing). GRAD: also d rgb_c / d(u,v) in uv units (TextureGradKernelLinear's position part).
+template <bool EX, bool GRAD>
+__device__ __forceinline__ void tex_bilinear(const float4* __restrict__ lvl, int tw, int th, float u, float v, float* rgb,
+                                             float* du, float* dv) {
+    float tu = sub_<EX>(u, floorf(u)), tv = sub_<EX>(v, floorf(v));
+    tu = sub_<EX>(mul_<EX>(tu, (float)tw), 0.5f); tv = sub_<EX>(mul_<EX>(tv, (float)th), 0.5f);
+    int iu0 = (int)floorf(tu), iv0 = (int)floorf(tv);
+    const float fu = sub_<EX>(tu, (float)iu0), fv = sub_<EX>(tv, (float)iv0);
+    int iu1 = iu0 + 1, iv1 = iv0 + 1;
+    if (iu0 < 0) iu0 += tw;
+    if (iv0 < 0) iv0 += th;
+    if (iu1 >= tw) iu1 -= tw;
+    if (iv1 >= th) iv1 -= th;
+    const float4 t00 = lvl[(size_t)iv0 * tw + iu0], t10 = lvl[(size_t)iv0 * tw + iu1];
+    const float4 t01 = lvl[(size_t)iv1 * tw + iu0], t11 = lvl[(size_t)iv1 * tw + iu1];
+    const float a00[3] = {t00.x, t00.y, t00.z}, a10[3] = {t10.x, t10.y, t10.z};
+    const float a01[3] = {t01.x, t01.y, t01.z}, a11[3] = {t11.x, t11.y, t11.z};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float v00 = a00[c], v10 = a10[c], v01 = a01[c], v11 = a11[c];
+        const float top = add_<EX>(v00, mul_<EX>(sub_<EX>(v10, v00), fu)), bot = add_<EX>(v01, mul_<EX>(sub_<EX>(v11, v01), fu));
+        rgb[c] = add_<EX>(top, mul_<EX>(sub_<EX>(bot, top), fv));
+        if (GRAD) {
+            const float ad = (v11 + v00) - (v10 + v01);
+            du[c] = ((v10 - v00) + fv * ad) * (float)tw;
+            dv[c] = ((v01 - v00) + fu * ad) * (float)th;
+        }
+    }
+}
+
+// Level of detail of the "linear-mipmap-linear" extension: log2 of the major axis (in level-0 texels) of the
+// pixel footprint in texture space, from the analytic screen derivatives of the barycentrics.
+__device__ __forceinline__ float tex_lod(const SceneDev& S, const Shade& s, float xs, float ys) {
+    const float w0 = s.c0[3], w1 = s.c1[3], w2 = s.c2[3];
+    const float a0x = s.p1y * w2 - w1 * s.p2y, a0y = w1 * s.p2x - s.p1x * w2;
+    const float a1x = s.p2y * w0 - w2 * s.p0y, a1y = w2 * s.p0x - s.p2x * w0;
+    const float a2x = s.p0y * w1 - w0 * s.p1y, a2y = w0 * s.p1x - s.p0x * w1;
+    const float at = (s.a0 + s.a1) + s.a2;
+    const float iw = 1.f / at;
+    const float b0 = s.a0 * iw, b1 = s.a1 * iw;
+    const float atx = (a0x + a1x) + a2x, aty = (a0y + a1y) + a2y;
+    const float b0x = (a0x - b0 * atx) * iw * xs, b0y = (a0y - b0 * aty) * iw * ys;  // per pixel
+    const float b1x = (a1x - b1 * atx) * iw * xs, b1y = (a1y - b1 * aty) * iw * ys;
+    const float du0 = s.v0.w - s.v2.w, du1 = s.v1.w - s.v2.w, dv0 = s.vv.x - s.vv.z, dv1 = s.vv.y - s.vv.z;
+    const float dudx = (b0x * du0 + b1x * du1) * (float)S.tex_w, dvdx = (b0x * dv0 + b1x * dv1) * (float)S.tex_h;
+    const float dudy = (b0y * du0 + b1y * du1) * (float)S.tex_w, dvdy = (b0y * dv0 + b1y * dv1) * (float)S.tex_h;
+    const float A = dudx * dudx + dvdx * dvdx, Bq = dudy * dudy + dvdy * dvdy, C = dudx * dudy + dvdx * dvdy;
+    const float l2b = 0.5f * (A + Bq), l2n = 0.25f * (A - Bq) * (A - Bq) + C * C;
+    const float major2 = l2b + sqrtf(l2n);
+    const float lod = 0.5f * log2f(fmaxf(major2, 1e-30f));
+    return fminf(fmaxf(lod, 0.f), (float)(S.tex_levels - 1));
+}
+
+// Colour of a covered pixel and (GRAD) its derivative w.r.t. the barycentrics (b0, b1), b2 = 1 - b0 - b1:
+// dr.interpolate(uv) + dr.texture (diffdope/diffdope.py:218-226) or dr.interpolate(vtx_color) (:230).
+template <bool EX, bool GRAD, bool MIP>
+__device__ __forceinline__ void shade_color(const SceneDev& S, const Shade& sh, int id, float b0, float b1, float b2, float xs,
+                                            float ys, float* rgb, float* g0, float* g1) {
+    if (S.tex4) {
+        const float2 t0 = make_float2(sh.v0.w, sh.vv.x), t1 = make_float2(sh.v1.w, sh.vv.y), t2 = make_float2(sh.v2.w, sh.vv.z);
+        const float tu = add_<EX>(add_<EX>(mul_<EX>(b0, t0.x), mul_<EX>(b1, t1.x)), mul_<EX>(b2, t2.x));
+        const float tv = add_<EX>(add_<EX>(mul_<EX>(b0, t0.y), mul_<EX>(b1, t1.y)), mul_<EX>(b2, t2.y));
+        float du[3], dv[3];
+        if (!MIP) {
+            tex_bilinear<EX, GRAD>(S.tex4, S.tex_w, S.tex_h, tu, tv, rgb, du, dv);
+        } else {
+            const float lod = tex_lod(S, sh, xs, ys);
+            const int l0 = min((int)lod, S.tex_levels - 1);
+            const float f = lod - (float)l0;
+            tex_bilinear<false, GRAD>(S.tex4 + S.tex_off[l0], max(S.tex_w >> l0, 1), max(S.tex_h >> l0, 1), tu, tv, rgb, du, dv);
+            if (f > 0.f && l0 + 1 < S.tex_levels) {
+                float rgb1[3], du1[3], dv1[3];
+                const int l1 = l0 + 1;
+                tex_bilinear<false, GRAD>(S.tex4 + S.tex_off[l1], max(S.tex_w >> l1, 1), max(S.tex_h >> l1, 1), tu, tv, rgb1, du1, dv1);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    rgb[c] += f * (rgb1[c] - rgb[c]);
+                    if (GRAD) { du[c] += f * (du1[c] - du[c]); dv[c] += f * (dv1[c] - dv[c]); }
+                }
+            }
+        }
+        if (GRAD) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                g0[c] = du[c] * (t0.x - t2.x) + dv[c] * (t0.y - t2.y);
+                g1[c] = du[c] * (t1.x - t2.x) + dv[c] * (t1.y - t2.y);
+            }
+        }
+    } else if (S.tricol) {
+        const float4 q0 = S.tricol[3 * (size_t)id], q1 = S.tricol[3 * (size_t)id + 1], q2 = S.tricol[3 * (size_t)id + 2];
+        const float kc0[3] = {q0.x, q0.y, q0.z}, kc1[3] = {q1.x, q1.y, q1.z}, kc2[3] = {q2.x, q2.y, q2.z};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            rgb[c] = add_<EX>(add_<EX>(mul_<EX>(b0, kc0[c]), mul_<EX>(b1, kc1[c])), mul_<EX>(b2, kc2[c]));
+            if (GRAD) { g0[c] = kc0[c] - kc2[c]; g1[c] = kc1[c] - kc2[c]; }
+        }
+    } else {
+        rgb[0] = rgb[1] = rgb[2] = 0.f;
+        if (GRAD) { g0[0] = g0[1] = g0[2] = g1[0] = g1[1] = g1[2] = 0.f; }
+    }
+}
+
 // d(u,v) -> d clip (x,y,w) of the three vertices -> accumulate dL/dMVP rows x,y,w
 // (nvdiffrast RasterizeGradKernel followed by xfm_bwd_mtx, diffdope/c_src/mesh.cu:165-214).
 __device__ __forceinline__ void raster_grad_accum(const SceneDev& S, const Shade& s, float gu, float gv, float* acc) {
@@ -218,7 +321,10 @@ constexpr int MODE_EXT = 2;     // backward of externally supplied image gradien
 constexpr int NPAIR = IDS_W * IDS_H;  // pair slots per direction, indexed by the pair's first pixel
 constexpr int DI_NONE = 3;            // no pair here / analysis found no usable edge
 
-template <int MODE>
+constexpr int GRAY_W = TILE_W + 4;  // grey image of the render: tile + 2 px halo (edge loss)
+constexpr int DG_W = TILE_W + 2;    // dL/d(Gx,Gy): tile + 1 px halo
+
+template <int MODE, bool EDGE, bool MIP>
 __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(SceneDev S, const HypState* __restrict__ hyp,
                                                              const int* __restrict__ total_tiles, int B,
                                                              LossCfgDev cfg,
@@ -234,6 +340,8 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
     __shared__ float s_red[TILE_THREADS / 32][NACC];
     __shared__ unsigned long long s_cov[IDS_H], s_inf[IDS_H];
     __shared__ int s_b, s_nq;
+    __shared__ float s_gray[EDGE ? GRAY_W * GRAY_W : 1];
+    __shared__ float s_dgx[EDGE ? DG_W * DG_W : 1], s_dgy[EDGE ? DG_W * DG_W : 1];
 
     const int total = *total_tiles;
     const int tid = threadIdx.x;
@@ -269,7 +377,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
         const int local = item - h.tile_base;
         const int tx = local % h.tiles_x, ty = local / h.tiles_x;
         const int ox = rx0 + tx * TILE_W, oy = ry0 + ty * TILE_H;  // tile origin, frame pixels
-        const float k_rgb = h.k_rgb, k_depth = h.k_depth, k_mask = h.k_mask;
+        const float k_rgb = h.k_rgb, k_depth = h.k_depth, k_mask = h.k_mask, k_edge = h.k_edge;
         // valid z-buffer region of this hypothesis
         const int vx0 = max(rx0 - 1, S.zx0), vx1 = min(rx1 + 1, S.zx0 + S.zw);
         const int vy0 = max(ry0 - 1, S.zy0), vy1 = min(ry1 + 1, S.zy0 + S.zh);
@@ -422,6 +530,53 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
 #pragma unroll
         for (int k = 0; k < NACC; k++) acc[k] = 0.f;
 
+        if (EDGE) {
+            // E1. grey image of the render over tile + 2 px halo (0 for background and outside the loss window:
+            //     the Sobel stencil is zero-padded at the window)
+            for (int i = tid; i < GRAY_W * GRAY_W; i += TILE_THREADS) {
+                const int ix = i % GRAY_W, iy = i / GRAY_W;
+                const int x = ox - 2 + ix, y = oy - 2 + iy;
+                const int id = s_ids[iy * IDS_W + ix];
+                float gray = 0.f;
+                if (id >= 0 && x >= S.wx0 && x < S.wx0 + S.ww && y >= S.wy0 && y < S.wy0 + S.wh) {
+                    Shade sh;
+                    shade_setup<true>(S, s_mvp, id, x, y, ndc_xs, ndc_xo, ndc_ys, ndc_yo, sh);
+                    float rgb[3];
+                    shade_color<false, false, MIP>(S, sh, id, sh.u, sh.v, (1.f - sh.u) - sh.v, ndc_xs, ndc_ys, rgb, nullptr, nullptr);
+                    gray = ((rgb[0] + rgb[1]) + rgb[2]) * (1.f / 3.f);
+                }
+                s_gray[i] = gray;
+            }
+            __syncthreads();
+            // E2. Sobel magnitude of the render, the edge loss against the precomputed target edges and
+            //     dL/d(Gx, Gy) over tile + 1 px halo
+            for (int i = tid; i < DG_W * DG_W; i += TILE_THREADS) {
+                const int ix = i % DG_W, iy = i / DG_W;
+                const int x = ox - 1 + ix, y = oy - 1 + iy;
+                float dgx = 0.f, dgy = 0.f;
+                if (x >= S.wx0 && x < S.wx0 + S.ww && y >= S.wy0 && y < S.wy0 + S.wh) {
+                    const size_t gp = (size_t)y * S.W + x;
+                    const float sg = S.gt_seg[gp * S.seg_pix_stride];
+                    if (sg != 0.f) {
+                        const float* g = s_gray + (iy + 1) * GRAY_W + (ix + 1);  // centre
+                        const float tl = g[GRAY_W - 1], tc = g[GRAY_W], tr = g[GRAY_W + 1];
+                        const float ml = g[-1], mr = g[1];
+                        const float bl = g[-GRAY_W - 1], bc = g[-GRAY_W], br = g[-GRAY_W + 1];
+                        const float gx = ((tr - tl) + 2.f * (mr - ml)) + (br - bl);
+                        const float gy = ((tl - bl) + 2.f * (tc - bc)) + (tr - br);
+                        const float e = sqrtf(gx * gx + gy * gy + 1e-12f);
+                        const float diff = (e - S.gt_edge[gp]) * sg;
+                        const bool own = ix >= 1 && ix <= TILE_W && iy >= 1 && iy <= TILE_H && x < rx1 && y < ry1;
+                        if (own) acc[19] += fabsf(diff);
+                        const float de = k_edge * sgn(diff) * sg / e;
+                        dgx = de * gx; dgy = de * gy;
+                    }
+                }
+                s_dgx[i] = dgx; s_dgy[i] = dgy;
+            }
+            __syncthreads();
+        }
+
         // 5. shading, losses and their backward, 4 pixels per thread
         for (int rep = 0; rep < TILE_H / 8; rep++) {
             const int ly = ly0 + 8 * rep;
@@ -474,68 +629,36 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                         gv += dg * (p1[k] - p2[k]);
                     }
                 }
-                const bool want_rgb_grad = (MODE == MODE_LOSS && cfg.use_rgb) || (MODE == MODE_EXT && ext.d_rgb);
-                if (S.tex) {
-                    const float2 t0 = make_float2(sh.v0.w, sh.vv.x), t1 = make_float2(sh.v1.w, sh.vv.y), t2 = make_float2(sh.v2.w, sh.vv.z);
-                    float tu = add_<EX>(add_<EX>(mul_<EX>(b0, t0.x), mul_<EX>(b1, t1.x)), mul_<EX>(b2, t2.x));
-                    float tv = add_<EX>(add_<EX>(mul_<EX>(b0, t0.y), mul_<EX>(b1, t1.y)), mul_<EX>(b2, t2.y));
-                    tu = sub_<EX>(tu, floorf(tu)); tv = sub_<EX>(tv, floorf(tv));
-                    tu = sub_<EX>(mul_<EX>(tu, (float)S.tex_w), 0.5f); tv = sub_<EX>(mul_<EX>(tv, (float)S.tex_h), 0.5f);
-                    int iu0 = (int)floorf(tu), iv0 = (int)floorf(tv);
-                    const float fu = sub_<EX>(tu, (float)iu0), fv = sub_<EX>(tv, (float)iv0);
-                    int iu1 = iu0 + 1, iv1 = iv0 + 1;
-                    if (iu0 < 0) iu0 += S.tex_w;
-                    if (iv0 < 0) iv0 += S.tex_h;
-                    if (iu1 >= S.tex_w) iu1 -= S.tex_w;
-                    if (iv1 >= S.tex_h) iv1 -= S.tex_h;
-                    const float* a00 = S.tex + ((size_t)iv0 * S.tex_w + iu0) * 3;
-                    const float* a10 = S.tex + ((size_t)iv0 * S.tex_w + iu1) * 3;
-                    const float* a01 = S.tex + ((size_t)iv1 * S.tex_w + iu0) * 3;
-                    const float* a11 = S.tex + ((size_t)iv1 * S.tex_w + iu1) * 3;
-                    float gtu = 0.f, gtv = 0.f;
+                const bool want_rgb_grad = (MODE == MODE_LOSS && (cfg.use_rgb || EDGE)) || (MODE == MODE_EXT && ext.d_rgb);
+                if (MODE == MODE_RENDER) {
+                    shade_color<EX, false, MIP>(S, sh, id, b0, b1, b2, ndc_xs, ndc_ys, rgb, nullptr, nullptr);
+                } else if (want_rgb_grad) {
+                    float g0[3], g1[3];
+                    shade_color<EX, true, MIP>(S, sh, id, b0, b1, b2, ndc_xs, ndc_ys, rgb, g0, g1);
+                    float dgray3 = 0.f;  // dL/d rgb_c of the edge loss: dL/d grey / 3
+                    if (EDGE) {
+                        // transpose of the Sobel stencils: grey(q) enters G(p) for the 8 neighbours p of q
+                        const float* dx = s_dgx + (ly + 1) * DG_W + (lx + 1);
+                        const float* dy = s_dgy + (ly + 1) * DG_W + (lx + 1);
+                        const float sx = ((dx[-DG_W - 1] - dx[-DG_W + 1]) + 2.f * (dx[-1] - dx[1])) + (dx[DG_W - 1] - dx[DG_W + 1]);
+                        const float sy = ((dy[-DG_W - 1] - dy[DG_W - 1]) + 2.f * (dy[-DG_W] - dy[DG_W])) + (dy[-DG_W + 1] - dy[DG_W + 1]);
+                        dgray3 = (sx + sy) * (1.f / 3.f);
+                    }
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
-                        const float v00 = a00[c], v10 = a10[c], v01 = a01[c], v11 = a11[c];
-                        const float top = add_<EX>(v00, mul_<EX>(sub_<EX>(v10, v00), fu)), bot = add_<EX>(v01, mul_<EX>(sub_<EX>(v11, v01), fu));
-                        rgb[c] = add_<EX>(top, mul_<EX>(sub_<EX>(bot, top), fv));
-                        if (want_rgb_grad) {
-                            float dy;
-                            if (MODE == MODE_LOSS) {
+                        float dy;
+                        if (MODE == MODE_LOSS) {
+                            dy = dgray3;
+                            if (cfg.use_rgb) {
                                 const float diff = (rgb[c] - gt_rgb[c]) * seg[c];
                                 acc[16] += fabsf(diff);
-                                dy = k_rgb * sgn(diff) * seg[c];
-                            } else {
-                                dy = ext.d_rgb[wp * 3 + c];
+                                dy += k_rgb * sgn(diff) * seg[c];
                             }
-                            const float ad = (v11 + v00) - (v10 + v01);
-                            gtu += dy * ((v10 - v00) + fv * ad);
-                            gtv += dy * ((v01 - v00) + fu * ad);
+                        } else {
+                            dy = ext.d_rgb[wp * 3 + c];
                         }
-                    }
-                    if (want_rgb_grad) {
-                        gtu *= (float)S.tex_w; gtv *= (float)S.tex_h;
-                        gu += gtu * (t0.x - t2.x) + gtv * (t0.y - t2.y);
-                        gv += gtu * (t1.x - t2.x) + gtv * (t1.y - t2.y);
-                    }
-                } else if (S.tricol) {
-                    const float4 q0 = S.tricol[3 * (size_t)id], q1 = S.tricol[3 * (size_t)id + 1], q2 = S.tricol[3 * (size_t)id + 2];
-                    const float kc0[3] = {q0.x, q0.y, q0.z}, kc1[3] = {q1.x, q1.y, q1.z}, kc2[3] = {q2.x, q2.y, q2.z};
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const float k0 = kc0[c], k1 = kc1[c], k2 = kc2[c];
-                        rgb[c] = add_<EX>(add_<EX>(mul_<EX>(b0, k0), mul_<EX>(b1, k1)), mul_<EX>(b2, k2));
-                        if (want_rgb_grad) {
-                            float dy;
-                            if (MODE == MODE_LOSS) {
-                                const float diff = (rgb[c] - gt_rgb[c]) * seg[c];
-                                acc[16] += fabsf(diff);
-                                dy = k_rgb * sgn(diff) * seg[c];
-                            } else {
-                                dy = ext.d_rgb[wp * 3 + c];
-                            }
-                            gu += dy * (k0 - k2);
-                            gv += dy * (k1 - k2);
-                        }
+                        gu += dy * g0[c];
+                        gv += dy * g1[c];
                     }
                 }
                 if (MODE != MODE_RENDER && (gu != 0.f || gv != 0.f)) raster_grad_accum(S, sh, gu, gv, acc);
@@ -613,7 +736,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
         if (MODE != MODE_RENDER) {
             // 7. CTA reduction of the accumulators, one partial row per tile (fixed order: deterministic)
 #pragma unroll
-            for (int k = 0; k < NACC - 1; k++) {
+            for (int k = 0; k < NACC; k++) {
                 float v = acc[k];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -622,9 +745,8 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
             __syncthreads();
             if (tid < NACC) {
                 float v = 0.f;
-                if (tid < NACC - 1)
 #pragma unroll
-                    for (int w = 0; w < TILE_THREADS / 32; w++) v += s_red[w][tid];
+                for (int w = 0; w < TILE_THREADS / 32; w++) v += s_red[w][tid];
                 partials[(size_t)item * NACC + tid] = v;
             }
         }
@@ -638,28 +760,91 @@ static int pixel_grid(int max_tiles, int num_sms) {
     return g < 1 ? 1 : g;
 }
 
+template <int MODE, bool EDGE>
+static void launch_pixel(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles, LossCfgDev cfg,
+                         const unsigned long long* zbuf, float* partials, RenderOut out, ExtGrad ext, int num_sms, cudaStream_t st) {
+    const int grid = pixel_grid(max_tiles, num_sms);
+    if (S.tex4 && S.tex_filter == 1)
+        pixel_kernel<MODE, EDGE, true><<<grid, TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext);
+    else
+        pixel_kernel<MODE, EDGE, false><<<grid, TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext);
+}
+
 void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                        LossCfgDev cfg, const unsigned long long* zbuf, float* partials, int num_sms, cudaStream_t st) {
     RenderOut none = {nullptr, nullptr, nullptr, nullptr};
     ExtGrad noext = {nullptr, nullptr, nullptr};
-    pixel_kernel<MODE_LOSS><<<pixel_grid(max_tiles, num_sms), TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf,
-                                                                                    partials, none, noext);
+    if (cfg.use_edge)
+        launch_pixel<MODE_LOSS, true>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, noext, num_sms, st);
+    else
+        launch_pixel<MODE_LOSS, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, noext, num_sms, st);
 }
 
 void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                          const unsigned long long* zbuf, RenderOut out, int num_sms, cudaStream_t st) {
-    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f};
+    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
     ExtGrad noext = {nullptr, nullptr, nullptr};
-    pixel_kernel<MODE_RENDER><<<pixel_grid(max_tiles, num_sms), TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf,
-                                                                                      nullptr, out, noext);
+    launch_pixel<MODE_RENDER, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, nullptr, out, noext, num_sms, st);
 }
 
 void launch_pixel_ext(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                       const unsigned long long* zbuf, ExtGrad ext, float* partials, int num_sms, cudaStream_t st) {
-    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f};
+    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
     RenderOut none = {nullptr, nullptr, nullptr, nullptr};
-    pixel_kernel<MODE_EXT><<<pixel_grid(max_tiles, num_sms), TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf,
-                                                                                   partials, none, ext);
+    launch_pixel<MODE_EXT, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, ext, num_sms, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// once-per-target / once-per-scene helpers of the extensions
+
+// Sobel magnitude of the target's grey image over the loss window (zero outside it), frame-indexed.
+__global__ void gt_edge_kernel(const float* __restrict__ rgb, int W, int wy0, int wx0, int wh, int ww, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wh * ww) return;
+    const int x = wx0 + i % ww, y = wy0 + i / ww;
+    float g[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int xx = x + k - 1, yy = y + j - 1;
+            float v = 0.f;
+            if (xx >= wx0 && xx < wx0 + ww && yy >= wy0 && yy < wy0 + wh) {
+                const float* p = rgb + ((size_t)yy * W + xx) * 3;
+                v = ((p[0] + p[1]) + p[2]) * (1.f / 3.f);
+            }
+            g[j][k] = v;
+        }
+    const float gx = ((g[2][2] - g[2][0]) + 2.f * (g[1][2] - g[1][0])) + (g[0][2] - g[0][0]);
+    const float gy = ((g[2][0] - g[0][0]) + 2.f * (g[2][1] - g[0][1])) + (g[2][2] - g[0][2]);
+    out[(size_t)y * W + x] = sqrtf(gx * gx + gy * gy + 1e-12f);
+}
+
+void launch_gt_edge(const SceneDev& S, float* out, cudaStream_t st) {
+    const int n = S.wh * S.ww;
+    gt_edge_kernel<<<(n + 255) / 256, 256, 0, st>>>(S.gt_rgb, S.W, S.wy0, S.wx0, S.wh, S.ww, out);
+}
+
+// [h,w,3] float texels -> (r,g,b,0) float4 texels (level 0 of the chain)
+__global__ void tex_pack_kernel(const float* __restrict__ tex3, size_t n, float4* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4(tex3[3 * i], tex3[3 * i + 1], tex3[3 * i + 2], 0.f);
+}
+void launch_tex_pack(const float* tex3, size_t n, float4* out, cudaStream_t st) {
+    tex_pack_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(tex3, n, out);
+}
+
+// one mip level: 2x2 box filter (a dimension of 1 stays 1 and averages two texels along the other axis)
+__global__ void tex_mip_kernel(const float4* __restrict__ src, int sw, int sh, float4* __restrict__ dst, int dw, int dh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dw * dh) return;
+    const int x = i % dw, y = i / dw;
+    const int x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
+    const float4 a = src[(size_t)y0 * sw + x0], b = src[(size_t)y0 * sw + x1], c = src[(size_t)y1 * sw + x0], d = src[(size_t)y1 * sw + x1];
+    dst[i] = make_float4(((a.x + b.x) + (c.x + d.x)) * 0.25f, ((a.y + b.y) + (c.y + d.y)) * 0.25f, ((a.z + b.z) + (c.z + d.z)) * 0.25f, 0.f);
+}
+void launch_tex_mip(const float4* src, int sw, int sh, float4* dst, int dw, int dh, cudaStream_t st) {
+    tex_mip_kernel<<<(dw * dh + 255) / 256, 256, 0, st>>>(src, sw, sh, dst, dw, dh);
 }
 
 }  // namespace ddope

@@ -87,12 +87,12 @@ __device__ void hyp_from_pose(const SceneDev& S, const float* qb, const float* t
     h.rx0 = x0; h.ry0 = y0; h.rx1 = x1; h.ry1 = y1;
     h.tiles_x = (x1 - x0 + TILE_W - 1) / TILE_W;
     h.tiles_y = (y1 - y0 + TILE_H - 1) / TILE_H;
-                h.pad0 = 0;
     double P = (double)S.wh * (double)S.ww;
     double lr = (double)lr_b;
     h.k_rgb = (float)((double)cfg.w_rgb * lr / ((double)B_global * P * 3.0));
     h.k_depth = (float)((double)cfg.w_depth * lr / ((double)B_global * P));
     h.k_mask = (float)((double)cfg.w_mask * lr / ((double)B_global * P * 3.0));
+    h.k_edge = (float)((double)cfg.w_edge * lr / ((double)B_global * P));
     h.tile_base = 0;
 }
 
@@ -148,11 +148,13 @@ void launch_pose(const SceneDev& S, const float* quat, const float* trans, const
 
 // ---------------------------------------------------------------------------------------------
 
-// Thread-level tail of an iteration for hypothesis b: tile sums a[0..18] -> dL/dM -> dL/d(q,t) ->
-// logged losses, history rows and (optionally) the SGD update.
+// Thread-level tail of an iteration for hypothesis b: tile sums a[0..19] -> dL/dM -> dL/d(q,t) ->
+// logged losses, history rows and (optionally) the parameter update. `theta` holds the 7 raw parameters
+// (qx,qy,qz,qw,x,y,z) the iteration rendered with and receives the updated ones.
 __device__ void step_from_sums(const SceneDev& S, const HypState& h, const float* a, int b, int B, LossCfgDev cfg,
-                               float* __restrict__ quat, float* __restrict__ trans, const float* __restrict__ lr_sched,
-                               int it, int do_update, float* __restrict__ loss_table, float* __restrict__ grad_out,
+                               OptimDev opt, float* theta, float* __restrict__ quat, float* __restrict__ trans,
+                               const float* __restrict__ lr_sched, int it, int do_update,
+                               float* __restrict__ loss_table, float* __restrict__ grad_out,
                                float* __restrict__ pose_hist, float* __restrict__ loss_hist,
                                float* __restrict__ dmtx_out) {
     // dL/dM = P^T dL/dMVP (+ the direct depth term on row 2); rows x,y,w of dMVP are a[0..11]
@@ -188,31 +190,46 @@ __device__ void step_from_sums(const SceneDev& S, const HypState& h, const float
     g[4] = dM[0][3]; g[5] = dM[1][3]; g[6] = dM[2][3];
 
     const float P_px = (float)S.wh * (float)S.ww;
-    float l_rgb = cfg.use_rgb ? cfg.w_rgb * (a[16] / (P_px * 3.f)) : 0.f;
-    float l_dep = cfg.use_depth ? cfg.w_depth * (a[17] / P_px) : 0.f;
-    float l_msk = cfg.use_mask ? cfg.w_mask * (a[18] / (P_px * 3.f)) : 0.f;
-    if (loss_table) {
-        loss_table[3 * b + 0] = l_rgb; loss_table[3 * b + 1] = l_dep; loss_table[3 * b + 2] = l_msk;
-    }
+    float l[NLOSS];
+    l[0] = cfg.use_rgb ? cfg.w_rgb * (a[16] / (P_px * 3.f)) : 0.f;
+    l[1] = cfg.use_depth ? cfg.w_depth * (a[17] / P_px) : 0.f;
+    l[2] = cfg.use_mask ? cfg.w_mask * (a[18] / (P_px * 3.f)) : 0.f;
+    l[3] = cfg.use_edge ? cfg.w_edge * (a[19] / P_px) : 0.f;
+    if (loss_table)
+        for (int k = 0; k < NLOSS; k++) loss_table[NLOSS * b + k] = l[k];
     if (loss_hist) {
-        float* lh = loss_hist + ((size_t)it * B + b) * 3;
-        lh[0] = l_rgb; lh[1] = l_dep; lh[2] = l_msk;
+        float* lh = loss_hist + ((size_t)it * B + b) * NLOSS;
+        for (int k = 0; k < NLOSS; k++) lh[k] = l[k];
     }
     if (grad_out)
         for (int k = 0; k < 7; k++) grad_out[7 * b + k] = g[k];
     if (pose_hist) {
         float* ph = pose_hist + ((size_t)it * B + b) * 7;
-        for (int k = 0; k < 4; k++) ph[k] = quat[4 * b + k];
-        for (int k = 0; k < 3; k++) ph[4 + k] = trans[3 * b + k];
+        for (int k = 0; k < 7; k++) ph[k] = theta[k];
     }
     if (do_update) {
-        const float lr = lr_sched[it];
-        for (int k = 0; k < 4; k++) quat[4 * b + k] -= lr * g[k];
-        for (int k = 0; k < 3; k++) trans[3 * b + k] -= lr * g[4 + k];
+        if (opt.kind == 1) {  // torch.optim.Adam (_single_tensor_adam): lerp, addcmul, sqrt / bc2_sqrt + eps, addcdiv
+            float* m = opt.state + 14 * (size_t)b;
+            float* v = m + 7;
+            const float ss = opt.step_size[it], bc2s = opt.bc2_sqrt[it];
+            for (int k = 0; k < 7; k++) {
+                const float mk = m[k] + (g[k] - m[k]) * (1.f - opt.beta1);
+                const float vk = v[k] * opt.beta2 + (1.f - opt.beta2) * (g[k] * g[k]);
+                m[k] = mk; v[k] = vk;
+                const float denom = sqrtf(vk) / bc2s + opt.eps;
+                theta[k] -= ss * (mk / denom);
+            }
+        } else {
+            const float lr = lr_sched[it];
+            for (int k = 0; k < 7; k++) theta[k] -= lr * g[k];
+        }
+        for (int k = 0; k < 4; k++) quat[4 * b + k] = theta[k];
+        for (int k = 0; k < 3; k++) trans[3 * b + k] = theta[4 + k];
     }
 }
 
-// Deterministic reduction of the per-tile partial rows of hypothesis b into s_out[NACC] (thread 0 valid).
+// Deterministic reduction of the per-tile partial rows of hypothesis h into s_out[NACC] (valid for every
+// thread after the trailing barrier). Fixed summation order: bit-reproducible.
 __device__ void reduce_tile_partials(const HypState& h, const float* __restrict__ partials, float* s_out) {
     const int n_items = h.tiles_x * h.tiles_y;
     const float* base = partials + (size_t)h.tile_base * NACC;
@@ -229,80 +246,109 @@ __device__ void reduce_tile_partials(const HypState& h, const float* __restrict_
     }
     __shared__ float s_acc[16][NACC];
     const int nw = blockDim.x >> 5;
+    // warps that hold no tile contribute exact zeros: skip their shuffles (warp-uniform)
+    const bool warp_has = (int)(threadIdx.x & ~31u) < n_items;
+    if (warp_has) {
 #pragma unroll
-    for (int k = 0; k < NACC; k++) {
-        float v = acc[k];
+        for (int k = 0; k < NACC; k++) {
+            float v = acc[k];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        acc[k] = v;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            acc[k] = v;
+        }
     }
     if ((threadIdx.x & 31) == 0)
         for (int k = 0; k < NACC; k++) s_acc[threadIdx.x >> 5][k] = acc[k];
     __syncthreads();
-    if (threadIdx.x == 0)
-        for (int k = 0; k < NACC; k++) {
-            float v = 0.f;
-            for (int w = 0; w < nw; w++) v += s_acc[w][k];  // fixed order
-            s_out[k] = v;
-        }
+    if (threadIdx.x < NACC) {
+        float v = 0.f;
+        for (int w = 0; w < nw; w++) v += s_acc[w][threadIdx.x];  // fixed order
+        s_out[threadIdx.x] = v;
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(128) step_kernel(SceneDev S, const HypState* __restrict__ hyp,
                                                    const float* __restrict__ partials, int B, LossCfgDev cfg,
-                                                   float* __restrict__ quat, float* __restrict__ trans,
-                                                   const float* __restrict__ lr_sched, int it, int do_update,
-                                                   float* __restrict__ loss_table, float* __restrict__ grad_out,
-                                                   float* __restrict__ pose_hist, float* __restrict__ loss_hist,
                                                    float* __restrict__ dmtx_out) {
     __shared__ float s_sum[NACC];
     const int b = blockIdx.x;
     reduce_tile_partials(hyp[b], partials, s_sum);
-    if (threadIdx.x == 0)
-        step_from_sums(S, hyp[b], s_sum, b, B, cfg, quat, trans, lr_sched, it, do_update, loss_table, grad_out, pose_hist,
-                       loss_hist, dmtx_out);
+    if (threadIdx.x == 0) {
+        OptimDev none = {0, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr};
+        step_from_sums(S, hyp[b], s_sum, b, B, cfg, none, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                       nullptr, dmtx_out);
+    }
 }
 
 constexpr int ITER_THREADS = 512;
+constexpr int CLEAR_CTAS = 3;  // CTAs per hypothesis that restore the z-buffer while CTA 0 does the serial math
 
-// One launch per iteration boundary: finish iteration `it` (reduce, gradient chain, SGD step) and
-// set up the next one (pose -> matrices -> ROI, z-buffer clear over the new ROI, tile prefix by the last
-// CTA to arrive). Replaces step_kernel + pose_kernel + clear_kernel (3 launches) inside ddope_optimize.
-__global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, HypState* __restrict__ hyp,
+// One launch per iteration boundary, grid (1 + CLEAR_CTAS, B).
+//   CTA (0,b): finish iteration `it` of hypothesis b (deterministic tile reduction, gradient chain, SGD / Adam
+//              step) and set up the next one (pose -> matrices -> ROI -> hyp_new[b]); the last of these CTAs to
+//              arrive computes the tile prefix over all hypotheses.
+//   CTA (k,b), k >= 1: restore the z-buffer to EMPTY over the ROI the finished iteration used (hyp_old[b]), rows
+//              k-1, k-1+CLEAR_CTAS, ... -- independent of the step, so it overlaps CTA 0's serial math.
+// Replaces step_kernel + pose_kernel + clear_kernel (3 launches) inside ddope_optimize. The z-buffer
+// invariant is "all EMPTY between iterations"; hyp_old / hyp_new alternate so nothing is read after it is rewritten.
+__global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const HypState* __restrict__ hyp_old,
+                                                   HypState* __restrict__ hyp_new,
                                                    const float* __restrict__ partials, int B, int B_global,
-                                                   LossCfgDev cfg, float* __restrict__ quat, float* __restrict__ trans,
-                                                   const float* __restrict__ lr_mult, const float* __restrict__ lr_sched,
-                                                   int it, int do_step, int do_update, int do_pose,
-                                                   float* __restrict__ loss_table, float* __restrict__ grad_out,
+                                                   LossCfgDev cfg, OptimDev opt, float* __restrict__ quat,
+                                                   float* __restrict__ trans, const float* __restrict__ lr_mult,
+                                                   const float* __restrict__ lr_sched, int it, int do_step, int do_update,
+                                                   int do_pose, float* __restrict__ loss_table, float* __restrict__ grad_out,
                                                    float* __restrict__ pose_hist, float* __restrict__ loss_hist,
                                                    unsigned long long* __restrict__ zbuf, int* __restrict__ total_tiles,
                                                    unsigned int* __restrict__ arrive) {
+    const int b = blockIdx.y;
+    if (blockIdx.x > 0) {
+        if (!do_step) return;  // nothing was rasterised yet
+        const HypState& h = hyp_old[b];
+        const int rx0 = h.rx0, ry0 = h.ry0, rx1 = h.rx1, ry1 = h.ry1;
+        if (rx1 <= rx0) return;
+        const int x0 = max(rx0 - 1, S.zx0), x1 = min(rx1 + 1, S.zx0 + S.zw);
+        const int y0 = max(ry0 - 1, S.zy0), y1 = min(ry1 + 1, S.zy0 + S.zh);
+        unsigned long long* zb = zbuf + (size_t)b * S.zh * S.zw;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        const int stride = nwarps * CLEAR_CTAS;
+        // one warp per row; 16-byte stores where the row allows it
+        for (int y = y0 + (int)(blockIdx.x - 1) * nwarps + warp; y < y1; y += stride) {
+            unsigned long long* row = zb + (size_t)(y - S.zy0) * S.zw - S.zx0;
+            int xa = x0, xb = x1;
+            if (((size_t)(row + xa) & 15) != 0 && xa < xb) { if (lane == 0) row[xa] = EMPTY_KEY; xa++; }
+            if (((xb - xa) & 1) != 0) { if (lane == 0) row[xb - 1] = EMPTY_KEY; xb--; }
+            ulonglong2* r2 = reinterpret_cast<ulonglong2*>(row + xa);
+            const int n2 = (xb - xa) >> 1;
+            for (int i = lane; i < n2; i += 32) r2[i] = make_ulonglong2(EMPTY_KEY, EMPTY_KEY);
+        }
+        return;
+    }
+
     __shared__ float s_sum[NACC];
-    __shared__ int s_roi[4];
+    __shared__ float s_theta[8];
+    __shared__ __align__(16) HypState s_h;
     __shared__ bool s_last;
-    const int b = blockIdx.x;
+    if (threadIdx.x < 4) s_theta[threadIdx.x] = quat[4 * b + threadIdx.x];
+    else if (threadIdx.x < 7) s_theta[threadIdx.x] = trans[3 * b + threadIdx.x - 4];
     if (do_step) {
-        reduce_tile_partials(hyp[b], partials, s_sum);
+        constexpr int HW = sizeof(HypState) / 4;
+        if (threadIdx.x >= 32 && threadIdx.x < 32 + HW)
+            reinterpret_cast<unsigned int*>(&s_h)[threadIdx.x - 32] = reinterpret_cast<const unsigned int*>(&hyp_old[b])[threadIdx.x - 32];
+        __syncthreads();
+        reduce_tile_partials(s_h, partials, s_sum);
         if (threadIdx.x == 0)
-            step_from_sums(S, hyp[b], s_sum, b, B, cfg, quat, trans, lr_sched, it, do_update, loss_table, grad_out, pose_hist,
-                           loss_hist, nullptr);
+            step_from_sums(S, s_h, s_sum, b, B, cfg, opt, s_theta, quat, trans, lr_sched, it, do_update, loss_table, grad_out,
+                           pose_hist, loss_hist, nullptr);
+    } else {
+        __syncthreads();
     }
     if (!do_pose) return;
     if (threadIdx.x == 0) {
         HypState h;
-        hyp_from_pose(S, quat + 4 * b, trans + 3 * b, nullptr, lr_mult ? lr_mult[b] : 1.f, B_global, cfg, 1, h);
-        hyp[b] = h;
-        s_roi[0] = h.rx0; s_roi[1] = h.ry0; s_roi[2] = h.rx1; s_roi[3] = h.ry1;
-    }
-    __syncthreads();
-    if (s_roi[2] > s_roi[0]) {  // clear the z-buffer over the new ROI (+1 px ring)
-        const int x0 = max(s_roi[0] - 1, S.zx0), x1 = min(s_roi[2] + 1, S.zx0 + S.zw);
-        const int y0 = max(s_roi[1] - 1, S.zy0), y1 = min(s_roi[3] + 1, S.zy0 + S.zh);
-        unsigned long long* zb = zbuf + (size_t)b * S.zh * S.zw;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-        for (int y = y0 + warp; y < y1; y += nwarps) {  // one warp per row: 256 B coalesced stores, no division
-            unsigned long long* row = zb + (size_t)(y - S.zy0) * S.zw - S.zx0;
-            for (int x = x0 + lane; x < x1; x += 32) row[x] = EMPTY_KEY;
-        }
+        hyp_from_pose(S, s_theta, s_theta + 4, nullptr, lr_mult ? lr_mult[b] : 1.f, B_global, cfg, 1, h);
+        hyp_new[b] = h;
     }
     // tile prefix over all hypotheses, by whichever CTA arrives last
     __threadfence();
@@ -319,7 +365,7 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, HypState
     for (int b0 = 0; b0 < B; b0 += blockDim.x) {
         const int bb = b0 + threadIdx.x;
         int ntiles = 0;
-        if (bb < B) ntiles = __ldcg(&hyp[bb].tiles_x) * __ldcg(&hyp[bb].tiles_y);
+        if (bb < B) ntiles = __ldcg(&hyp_new[bb].tiles_x) * __ldcg(&hyp_new[bb].tiles_y);
         int v = ntiles;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -331,7 +377,7 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, HypState
         int woff = 0;
         for (int w = 0; w < warp; w++) woff += s_warp[w];
         const int carry = s_carry;
-        if (bb < B) hyp[bb].tile_base = carry + woff + v - ntiles;
+        if (bb < B) hyp_new[bb].tile_base = carry + woff + v - ntiles;
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + v;
         __syncthreads();
@@ -343,19 +389,18 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, HypState
     }
 }
 
-void launch_iter(const SceneDev& S, HypState* hyp, const float* partials, int B, int B_global, LossCfgDev cfg, float* quat,
-                 float* trans, const float* lr_mult, const float* lr_sched, int it, int do_step, int do_update, int do_pose,
-                 float* loss_table, float* grad_out, float* pose_hist, float* loss_hist, unsigned long long* zbuf,
-                 int* total_tiles, unsigned int* arrive, cudaStream_t st) {
-    iter_kernel<<<B, ITER_THREADS, 0, st>>>(S, hyp, partials, B, B_global, cfg, quat, trans, lr_mult, lr_sched, it, do_step, do_update,
-                                   do_pose, loss_table, grad_out, pose_hist, loss_hist, zbuf, total_tiles, arrive);
+void launch_iter(const SceneDev& S, const HypState* hyp_old, HypState* hyp_new, const float* partials, int B, int B_global,
+                 LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, const float* lr_sched, int it,
+                 int do_step, int do_update, int do_pose, float* loss_table, float* grad_out, float* pose_hist,
+                 float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, cudaStream_t st) {
+    iter_kernel<<<dim3(do_step ? 1 + CLEAR_CTAS : 1, B), ITER_THREADS, 0, st>>>(
+        S, hyp_old, hyp_new, partials, B, B_global, cfg, opt, quat, trans, lr_mult, lr_sched, it, do_step, do_update, do_pose,
+        loss_table, grad_out, pose_hist, loss_hist, zbuf, total_tiles, arrive);
 }
 
-void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg,
-                 float* quat, float* trans, const float* lr_sched, int it, int do_update, float* loss_table,
-                 float* grad_out, float* pose_hist, float* loss_hist, float* dmtx_out, cudaStream_t st) {
-    step_kernel<<<B, 128, 0, st>>>(S, hyp, partials, B, cfg, quat, trans, lr_sched, it, do_update, loss_table,
-                                   grad_out, pose_hist, loss_hist, dmtx_out);
+void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg, float* dmtx_out,
+                 cudaStream_t st) {
+    step_kernel<<<B, 128, 0, st>>>(S, hyp, partials, B, cfg, dmtx_out);
 }
 
 // ---------------------------------------------------------------------------------------------

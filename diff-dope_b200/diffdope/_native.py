@@ -13,8 +13,10 @@ import torch
 _LIB = None
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libddope_b200.so")
 
-NUM_LOSSES = 3
-LOSS_KEYS = ("rgb", "depth", "mask_selection")  # reference add_loss_value keys, diffdope.py:559,577,605
+NUM_LOSSES = 4
+LOSS_KEYS = ("rgb", "depth", "mask_selection", "edge")  # reference add_loss_value keys, diffdope.py:559,577,605; "edge" is an extension
+OPT_SGD, OPT_ADAM = 0, 1
+TEX_LINEAR, TEX_MIPMAP = 0, 1
 
 
 class LossCfg(ctypes.Structure):
@@ -25,6 +27,18 @@ class LossCfg(ctypes.Structure):
         ("weight_rgb", ctypes.c_float),
         ("weight_depth", ctypes.c_float),
         ("weight_mask", ctypes.c_float),
+        ("use_edge", ctypes.c_int32),
+        ("weight_edge", ctypes.c_float),
+    ]
+
+
+class OptimCfg(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("beta1", ctypes.c_float),
+        ("beta2", ctypes.c_float),
+        ("eps", ctypes.c_float),
+        ("step0", ctypes.c_int32),
     ]
 
 
@@ -57,6 +71,8 @@ def lib():
     L.ddope_scene_set_camera.argtypes = [vp, vp, ci, ci]
     L.ddope_scene_set_target.argtypes = [vp, vp, vp, vp, ci, vp]
     L.ddope_scene_set_window.argtypes = [vp, ci, ci, ci, ci]
+    L.ddope_scene_set_texture_filter.argtypes = [vp, ci, ci]
+    L.ddope_scene_set_optimizer.argtypes = [vp, ctypes.POINTER(OptimCfg)]
     L.ddope_render.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
     L.ddope_render_mtx.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
     L.ddope_render_bwd.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
@@ -68,10 +84,10 @@ def lib():
         "ddope_xfm_fwd", "ddope_xfm_bwd", "ddope_xfm_bwd_mtx", "ddope_xfm_bwd_full", "ddope_scene_create",
         "ddope_scene_destroy", "ddope_scene_set_camera", "ddope_scene_set_target", "ddope_scene_set_window",
         "ddope_render", "ddope_render_mtx", "ddope_render_bwd", "ddope_loss_grad", "ddope_optimize",
-        "ddope_profile_begin", "ddope_profile_end",
+        "ddope_profile_begin", "ddope_profile_end", "ddope_scene_set_texture_filter", "ddope_scene_set_optimizer",
     ):
         getattr(L, name).restype = ci
-    if L.ddope_abi_version() != 1:
+    if L.ddope_abi_version() != 2:
         raise RuntimeError("libddope_b200.so ABI version mismatch")
     _LIB = L
     return L
@@ -110,8 +126,9 @@ def _hptr(a):
     return ctypes.c_void_p(0 if a is None else a.ctypes.data)
 
 
-def make_loss_cfg(use_rgb, use_depth, use_mask, w_rgb=1.0, w_depth=1.0, w_mask=1.0):
-    return LossCfg(int(bool(use_rgb)), int(bool(use_depth)), int(bool(use_mask)), float(w_rgb), float(w_depth), float(w_mask))
+def make_loss_cfg(use_rgb, use_depth, use_mask, w_rgb=1.0, w_depth=1.0, w_mask=1.0, use_edge=False, w_edge=1.0):
+    return LossCfg(int(bool(use_rgb)), int(bool(use_depth)), int(bool(use_mask)), float(w_rgb), float(w_depth), float(w_mask),
+                   int(bool(use_edge)), float(w_edge))
 
 
 class NativeScene:
@@ -158,6 +175,21 @@ class NativeScene:
     def set_window(self, y0, x0, h, w):
         _check(lib().ddope_scene_set_window(self._h, int(y0), int(x0), int(h), int(w)))
         self.window = (int(y0), int(x0), int(h), int(w))
+
+    def set_texture_filter(self, mode="linear", max_levels=0):
+        """'linear' (reference, default) or 'linear-mipmap-linear' (extension)."""
+        modes = {"linear": TEX_LINEAR, "linear-mipmap-linear": TEX_MIPMAP, TEX_LINEAR: TEX_LINEAR, TEX_MIPMAP: TEX_MIPMAP}
+        if mode not in modes:
+            raise RuntimeError("ddope_b200: unknown texture filter %r" % (mode,))
+        _check(lib().ddope_scene_set_texture_filter(self._h, modes[mode], int(max_levels)))
+
+    def set_optimizer(self, kind="sgd", beta1=0.9, beta2=0.999, eps=1e-8, step0=0):
+        """'sgd' (reference, default) or 'adam' (extension; torch.optim.Adam's algebra)."""
+        kinds = {"sgd": OPT_SGD, "adam": OPT_ADAM}
+        if str(kind).lower() not in kinds:
+            raise RuntimeError("ddope_b200: unknown optimizer %r" % (kind,))
+        cfg = OptimCfg(kinds[str(kind).lower()], float(beta1), float(beta2), float(eps), int(step0))
+        _check(lib().ddope_scene_set_optimizer(self._h, ctypes.byref(cfg)))
 
     def set_target(self, rgb=None, depth=None, seg=None):
         """rgb [H,W,3], depth [H,W], seg [H,W,3] or [H,W] or [H,W,1]; cuda float32, borrowed."""

@@ -275,7 +275,39 @@ def l1_mask(ddope):
     return dist_batch_lr(diff, ddope.learning_rates).mean() * ddope.cfg.losses.weight_mask
 
 
-_FUSED_LOSSES = {l1_rgb_with_mask: "rgb", l1_depth_with_mask: "depth", l1_mask: "mask"}
+_SOBEL_X = [[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]]
+_SOBEL_Y = [[-1.0, -2.0, -1.0], [0.0, 0.0, 0.0], [1.0, 2.0, 1.0]]
+
+
+def sobel_magnitude(img):
+    """[B,H,W,3] -> [B,H,W]: grey = channel mean, 3x3 Sobel with zero padding, sqrt(Gx^2 + Gy^2 + 1e-12)."""
+    g = img.mean(dim=-1).unsqueeze(1)
+    k = torch.tensor([_SOBEL_X, _SOBEL_Y], dtype=g.dtype, device=g.device).unsqueeze(1)
+    d = torch.nn.functional.conv2d(g, k, padding=1)
+    return torch.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2 + 1e-12)
+
+
+def l1_edge(ddope):
+    """Sobel-edge loss. EXTENSION: the reference has no edge loss (its readme lists it as a TODO,
+    readme.md:29); BASELINE.json's north_star asks for one. Definition: SURVEY.md Appendix B."""
+    er = sobel_magnitude(ddope.renders["rgb"])
+    eg = sobel_magnitude(ddope.gt_tensors["rgb"])
+    diff = torch.abs((er - eg) * ddope.gt_tensors["segmentation"][..., 0])
+    w = _cfg_get(ddope.cfg.losses, "weight_edge", 1.0)
+    ddope.add_loss_value("edge", torch.mean(diff.detach(), (1, 2)) * w)
+    return dist_batch_lr(diff, ddope.learning_rates, [1, 2]).mean() * w
+
+
+def _cfg_get(node, key, default=None):
+    """Optional config key (the reference's yaml does not have the extension keys)."""
+    try:
+        v = node.get(key, default)
+    except Exception:
+        v = getattr(node, key, default)
+    return default if v is None else v
+
+
+_FUSED_LOSSES = {l1_rgb_with_mask: "rgb", l1_depth_with_mask: "depth", l1_mask: "mask", l1_edge: "edge"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -642,6 +674,8 @@ class DiffDope:
             self.loss_functions.append(l1_depth_with_mask)
         if self.cfg.losses.l1_mask:
             self.loss_functions.append(l1_mask)
+        if _cfg_get(self.cfg.losses, "l1_edge", False):  # extension, default off
+            self.loss_functions.append(l1_edge)
         self.renders = None
         self.window = None  # optional (y0, x0, h, w) loss window; None = full frame like the reference
         log.info(f"batchsize is {self.batchsize}")
@@ -664,7 +698,7 @@ class DiffDope:
         self.object3d.set_batchsize(batchsize)
         self.camera.set_batchsize(batchsize)
         self._refresh_gt()
-        self.optimizer = torch.optim.SGD(self.object3d.parameters(), lr=self.cfg.hyperparameters.learning_rate_base)
+        self.optimizer = self._make_optimizer()
         lo, hi = self.cfg.hyperparameters.learning_rates_bound[0], self.cfg.hyperparameters.learning_rates_bound[1]
         self.learning_rates = torch.tensor([random.uniform(lo, hi) for _ in range(batchsize)]).float().cuda()
 
@@ -672,6 +706,28 @@ class DiffDope:
         self.object3d.cuda()
         self.scene.cuda()
         self.camera.cuda()
+
+    def _optimizer_kind(self):
+        kind = str(_cfg_get(self.cfg.hyperparameters, "optimizer", "sgd")).lower()
+        if kind not in ("sgd", "adam"):
+            raise ValueError("hyperparameters.optimizer must be 'sgd' (reference) or 'adam' (extension), got %r" % kind)
+        return kind
+
+    def _adam_args(self):
+        hp = self.cfg.hyperparameters
+        return dict(beta1=float(_cfg_get(hp, "adam_beta1", 0.9)), beta2=float(_cfg_get(hp, "adam_beta2", 0.999)), eps=float(_cfg_get(hp, "adam_eps", 1e-8)))
+
+    def _make_optimizer(self):
+        """torch.optim.SGD as the reference builds it (`diffdope.py:1363,1642`), or Adam (extension)."""
+        lr = self.cfg.hyperparameters.learning_rate_base
+        if self._optimizer_kind() == "adam":
+            a = self._adam_args()
+            return torch.optim.Adam(self.object3d.parameters(), lr=lr, betas=(a["beta1"], a["beta2"]), eps=a["eps"])
+        return torch.optim.SGD(self.object3d.parameters(), lr=lr)
+
+    def _texture_filter(self):
+        node = _cfg_get(self.cfg, "render", None)
+        return "linear" if node is None else str(_cfg_get(node, "texture_filter", "linear"))
 
     def add_loss_value(self, key, values, values_weighted=None):
         v = values.detach().cpu().unsqueeze(0)
@@ -705,6 +761,7 @@ class DiffDope:
             if bool(torch.equal(seg[..., 0], seg[..., 1])) and bool(torch.equal(seg[..., 0], seg[..., 2])):
                 seg = seg[..., 0].contiguous()  # 4 B/px instead of 12
         sc.set_target(rgb, depth, seg)
+        sc.set_texture_filter(self._texture_filter())
         if self.window is not None:
             sc.set_window(*self.window)
         return sc
@@ -714,7 +771,7 @@ class DiffDope:
         (`diffdope/diffdope.py:1634-1714`)."""
         self.losses_values = {}
         self.optimization_results = []
-        self.optimizer = torch.optim.SGD(self.object3d.parameters(), lr=self.cfg.hyperparameters.learning_rate_base)
+        self.optimizer = self._make_optimizer()
         self._refresh_gt()
         if all(f in _FUSED_LOSSES for f in self.loss_functions) and len(self.loss_functions) > 0:
             return self._run_fused()
@@ -725,8 +782,10 @@ class DiffDope:
 
         L = self.cfg.losses
         kinds = [_FUSED_LOSSES[f] for f in self.loss_functions]
-        cfg = _native.make_loss_cfg("rgb" in kinds, "depth" in kinds, "mask" in kinds, L.weight_rgb, L.weight_depth, L.weight_mask)
+        cfg = _native.make_loss_cfg("rgb" in kinds, "depth" in kinds, "mask" in kinds, L.weight_rgb, L.weight_depth, L.weight_mask,
+                                    "edge" in kinds, _cfg_get(L, "weight_edge", 1.0))
         sc = self._prepare_native()
+        sc.set_optimizer(self._optimizer_kind(), **self._adam_args())
         sched = self._lr_schedule()
         q, t = self.object3d.pose_tensors()
         B = q.shape[0]
@@ -741,8 +800,8 @@ class DiffDope:
         self._native_scene = sc
         ph = pose_hist.cpu()
         lh = loss_hist.cpu()
-        cols = {"rgb": 0, "depth": 1, "mask": 2}
-        keys = {"rgb": "rgb", "depth": "depth", "mask": "mask_selection"}
+        cols = {"rgb": 0, "depth": 1, "mask": 2, "edge": 3}
+        keys = {"rgb": "rgb", "depth": "depth", "mask": "mask_selection", "edge": "edge"}
         for k in kinds:
             self.losses_values[keys[k]] = lh[:, :, cols[k]].contiguous()
         qn = ph[..., :4] / torch.norm(ph[..., :4], dim=-1, keepdim=True)

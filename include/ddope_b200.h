@@ -30,12 +30,16 @@
 extern "C" {
 #endif
 
-#define DDOPE_ABI_VERSION 1
+#define DDOPE_ABI_VERSION 2
 
 typedef struct ddope_scene ddope_scene; /* opaque: one mesh + camera + target + work buffers */
 
 /* Which losses run, and their weights: `cfg.losses.*` of configs/diffdope.yaml as read by
- * l1_rgb_with_mask / l1_depth_with_mask / l1_mask (diffdope/diffdope.py:547-613). */
+ * l1_rgb_with_mask / l1_depth_with_mask / l1_mask (diffdope/diffdope.py:547-613).
+ * use_edge / weight_edge: the Sobel-edge loss, an EXTENSION with no reference counterpart (the
+ * reference's readme lists edges as a TODO, readme.md:29; definition in SURVEY.md Appendix B):
+ * grey = mean(rgb); 3x3 Sobel Gx, Gy with zero padding at the loss window; E = sqrt(Gx^2+Gy^2+1e-12);
+ * L_edge = weight_edge * mean_b(lr_b * mean_px(|E(render) - E(target rgb)| * seg)). Default off. */
 typedef struct ddope_loss_cfg {
     int32_t use_rgb;
     int32_t use_depth;
@@ -43,7 +47,33 @@ typedef struct ddope_loss_cfg {
     float weight_rgb;
     float weight_depth;
     float weight_mask;
+    int32_t use_edge;
+    float weight_edge;
 } ddope_loss_cfg;
+
+/* The parameter update of ddope_optimize. kind 0 = the reference's torch.optim.SGD without momentum
+ * (diffdope/diffdope.py:1363,1642,1714; the default). kind 1 = Adam with torch.optim.Adam's algebra
+ * (bias-corrected, eps outside the square root), an EXTENSION (BASELINE.json north_star; no
+ * reference counterpart). step0 = Adam steps already taken by earlier ddope_optimize calls on this
+ * scene (0 resets the moment buffers; > 0 continues them). */
+#define DDOPE_OPT_SGD 0
+#define DDOPE_OPT_ADAM 1
+typedef struct ddope_optim_cfg {
+    int32_t kind;
+    float beta1;
+    float beta2;
+    float eps;
+    int32_t step0;
+} ddope_optim_cfg;
+
+/* Texture filter of the colour lookup. 0 = dr.texture(filter_mode="linear") as the reference calls
+ * it (diffdope/diffdope.py:221-226; the default). 1 = "linear-mipmap-linear", an EXTENSION: 2x2
+ * box-filtered mip chain built once per scene, level of detail from the analytic screen-space
+ * derivatives of uv (isotropic, log2 of the longer footprint axis in texels), trilinear blend of
+ * two bilinear wrap lookups. The gradient flows to uv through both lookups; the level of detail
+ * itself is treated as a constant. */
+#define DDOPE_TEX_LINEAR 0
+#define DDOPE_TEX_MIPMAP 1
 
 /* Columns of the per-hypothesis loss table written by ddope_loss_grad / ddope_optimize:
  * the values the reference logs through add_loss_value under the keys "rgb", "depth",
@@ -51,7 +81,8 @@ typedef struct ddope_loss_cfg {
 #define DDOPE_LOSS_RGB 0
 #define DDOPE_LOSS_DEPTH 1
 #define DDOPE_LOSS_MASK 2
-#define DDOPE_NUM_LOSSES 3
+#define DDOPE_LOSS_EDGE 3 /* extension, key "edge" */
+#define DDOPE_NUM_LOSSES 4
 
 int ddope_abi_version(void);
 const char* ddope_last_error(void);
@@ -111,6 +142,10 @@ int ddope_scene_set_target(ddope_scene* s, const float* rgb_dev, const float* de
  * ground truth" (the reference always uses the full frame; default after set_camera). */
 int ddope_scene_set_window(ddope_scene* s, int y0, int x0, int h, int w);
 
+/* Extensions (defaults = reference behaviour). max_levels <= 0: the full chain down to 1x1. */
+int ddope_scene_set_texture_filter(ddope_scene* s, int mode, int max_levels);
+int ddope_scene_set_optimizer(ddope_scene* s, const ddope_optim_cfg* cfg);
+
 /* ------------------------------------------------------------------------------------------
  * (3) the hot path
  * ---------------------------------------------------------------------------------------- */
@@ -140,16 +175,17 @@ int ddope_render_bwd(ddope_scene* s, const float* mtx_dev, int B, const float* d
 /* One forward + loss + backward without a parameter update: the gradient autograd
  * produces at diffdope.py:1713 for loss = sum_k w_k * mean_b(lr_b * mean_px |.|)
  * (diffdope.py:534-613). B_global is the divisor of mean_b (the whole job's hypothesis
- * count when B is one rank's shard). loss_table [B,3], grad [B,7] = d/d(qx,qy,qz,qw,x,y,z). */
+ * count when B is one rank's shard). loss_table [B,DDOPE_NUM_LOSSES], grad [B,7] = d/d(qx,qy,qz,qw,x,y,z). */
 int ddope_loss_grad(ddope_scene* s, const float* quat_dev, const float* trans_dev,
                     const float* lr_mult_dev, int B, int B_global, const ddope_loss_cfg* cfg,
                     float* loss_table_dev, float* grad_dev, void* stream);
 
 /* DiffDope.run_optimization's loop (diffdope.py:1656-1714): n_iters iterations of
- * forward, loss, backward, SGD step theta -= lr_sched[it] * grad, in place on quat/trans.
+ * forward, loss, backward, parameter update (SGD: theta -= lr_sched[it] * grad; or Adam, see
+ * ddope_scene_set_optimizer), in place on quat/trans.
  * lr_sched_host [n_iters] (diffdope.py:1657-1664, computed by the caller in double).
  * pose_hist [n_iters,B,7] = parameters each iteration rendered with (or NULL);
- * loss_hist [n_iters,B,3] = logged loss values per iteration (or NULL). */
+ * loss_hist [n_iters,B,DDOPE_NUM_LOSSES] = logged loss values per iteration (or NULL). */
 int ddope_optimize(ddope_scene* s, float* quat_dev, float* trans_dev, const float* lr_mult_dev,
                    int B, int B_global, const float* lr_sched_host, int n_iters,
                    const ddope_loss_cfg* cfg, float* pose_hist_dev, float* loss_hist_dev,

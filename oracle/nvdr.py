@@ -437,6 +437,112 @@ def texture_linear_grad_uv(tex, uv, d_out):
 
 
 # ----------------------------------------------------------------------------
+# texture, "linear-mipmap-linear" -- EXTENSION with no reference counterpart (the reference calls
+# dr.texture with filter_mode="linear" only, `diffdope/diffdope.py:221-226`; BASELINE.json's
+# north_star asks for a mipmapped sample). Definition:
+#   * chain: level l+1 = 2x2 box filter of level l (a dimension of 1 stays 1), down to 1x1;
+#   * level of detail per pixel: 0.5*log2 of the squared major axis (in level-0 texels) of the pixel
+#     footprint in texture space, from the analytic screen derivatives of the interpolated uv
+#     (the ellipse formula nvdiffrast's mip lookup uses), clamped to [0, levels-1];
+#   * colour: linear blend of two bilinear wrap lookups at floor(lod) and floor(lod)+1;
+#   * gradient: to uv through both lookups; the level of detail is a constant.
+
+
+def build_mip_chain(tex, max_levels=0):
+    """List of float32 levels [h,w,C], level 0 = tex."""
+    lv = [np.asarray(tex, dtype=F)]
+    while (lv[-1].shape[0] > 1 or lv[-1].shape[1] > 1) and (max_levels <= 0 or len(lv) < max_levels) and len(lv) < 15:
+        t = lv[-1]
+        h, w = t.shape[:2]
+        dh, dw = max(h >> 1, 1), max(w >> 1, 1)
+        y0 = np.minimum(2 * np.arange(dh), h - 1)
+        y1 = np.minimum(2 * np.arange(dh) + 1, h - 1)
+        x0 = np.minimum(2 * np.arange(dw), w - 1)
+        x1 = np.minimum(2 * np.arange(dw) + 1, w - 1)
+        a, b = t[y0][:, x0], t[y0][:, x1]
+        c, d = t[y1][:, x0], t[y1][:, x1]
+        lv.append((((a + b) + (c + d)) * F(0.25)).astype(F))
+    return lv
+
+
+def texture_lod(clip, tri, uv_attr, rast, tex_hw, n_levels):
+    """Per-pixel level of detail [B,H,W] (0 at background). float64 inside: the value is
+    continuous in its inputs, so no decision depends on its last bits."""
+    B, H, W, _ = rast.shape
+    Ht, Wt = tex_hw
+    lod = np.zeros((B, H, W), dtype=F)
+    tid = rast[..., 3].astype(np.int64) - 1
+    b, py, px = np.nonzero(tid >= 0)
+    if b.size == 0:
+        return lod
+    t = tid[b, py, px]
+    c = np.asarray(clip, dtype=np.float64)
+    c0, c1, c2 = c[b, tri[t, 0]], c[b, tri[t, 1]], c[b, tri[t, 2]]
+    fx, fy = pixel_ndc(px, py, W, H)
+    fx, fy = fx.astype(np.float64), fy.astype(np.float64)
+    a0, a1, a2, (p0x, p0y, p1x, p1y, p2x, p2y) = shader_terms(c0, c1, c2, fx, fy)
+    w0, w1, w2 = c0[:, 3], c1[:, 3], c2[:, 3]
+    a0x, a0y = p1y * w2 - w1 * p2y, w1 * p2x - p1x * w2
+    a1x, a1y = p2y * w0 - w2 * p0y, w2 * p0x - p2x * w0
+    a2x, a2y = p0y * w1 - w0 * p1y, w0 * p1x - p0x * w1
+    at = a0 + a1 + a2
+    b0, b1 = a0 / at, a1 / at
+    atx, aty = a0x + a1x + a2x, a0y + a1y + a2y
+    xs, ys = 2.0 / W, 2.0 / H
+    b0x, b0y = (a0x - b0 * atx) / at * xs, (a0y - b0 * aty) / at * ys
+    b1x, b1y = (a1x - b1 * atx) / at * xs, (a1y - b1 * aty) / at * ys
+    uv = np.asarray(uv_attr, dtype=np.float64)
+    t0, t1, t2 = uv[tri[t, 0]], uv[tri[t, 1]], uv[tri[t, 2]]
+    du0, du1 = t0[:, 0] - t2[:, 0], t1[:, 0] - t2[:, 0]
+    dv0, dv1 = t0[:, 1] - t2[:, 1], t1[:, 1] - t2[:, 1]
+    dudx, dvdx = (b0x * du0 + b1x * du1) * Wt, (b0x * dv0 + b1x * dv1) * Ht
+    dudy, dvdy = (b0y * du0 + b1y * du1) * Wt, (b0y * dv0 + b1y * dv1) * Ht
+    A, Bq, C = dudx * dudx + dvdx * dvdx, dudy * dudy + dvdy * dvdy, dudx * dudy + dvdx * dvdy
+    major2 = 0.5 * (A + Bq) + np.sqrt(0.25 * (A - Bq) ** 2 + C * C)
+    l = 0.5 * np.log2(np.maximum(major2, 1e-30))
+    lod[b, py, px] = np.clip(l, 0.0, float(n_levels - 1)).astype(F)
+    return lod
+
+
+def _mip_levels_of(lod, n_levels):
+    l0 = np.minimum(lod.astype(np.int64), n_levels - 1)
+    f = (lod - l0.astype(F)).astype(F)
+    use1 = (f > 0) & (l0 + 1 < n_levels)
+    return l0, f, use1
+
+
+def texture_mipmap(levels, uv, lod):
+    """Trilinear lookup: levels from build_mip_chain, uv [B,H,W,2], lod [B,H,W]."""
+    n = len(levels)
+    l0, f, use1 = _mip_levels_of(lod, n)
+    out = np.zeros(uv.shape[:-1] + (levels[0].shape[2],), dtype=F)
+    for l in range(n):
+        m0 = l0 == l
+        if m0.any():
+            out[m0] = texture_linear(levels[l], uv[m0])
+        m1 = use1 & (l0 + 1 == l)
+        if m1.any():
+            c1 = texture_linear(levels[l], uv[m1])
+            out[m1] = out[m1] + f[m1][:, None] * (c1 - out[m1])
+    return out
+
+
+def texture_mipmap_grad_uv(levels, uv, lod, d_out):
+    n = len(levels)
+    l0, f, use1 = _mip_levels_of(lod, n)
+    g = np.zeros(uv.shape, dtype=F)
+    for l in range(n):
+        m0 = l0 == l
+        if m0.any():
+            g[m0] = texture_linear_grad_uv(levels[l], uv[m0], d_out[m0])
+        m1 = use1 & (l0 + 1 == l)
+        if m1.any():
+            g1 = texture_linear_grad_uv(levels[l], uv[m1], d_out[m1])
+            g[m1] = g[m1] + f[m1][:, None] * (g1 - g[m1])
+    return g
+
+
+# ----------------------------------------------------------------------------
 # antialias
 
 

@@ -103,6 +103,21 @@ class _TextureLinear(torch.autograd.Function):
         return None, torch.from_numpy(nvdr.texture_linear_grad_uv(tex.numpy(), uv.detach().numpy(), d_out.numpy()))
 
 
+class _TextureMipmap(torch.autograd.Function):
+    """EXTENSION (no reference counterpart): trilinear mip lookup, level of detail constant in the backward."""
+
+    @staticmethod
+    def forward(ctx, uv, lod, levels):
+        ctx.levels = levels
+        ctx.save_for_backward(uv, lod)
+        return torch.from_numpy(nvdr.texture_mipmap(levels, uv.detach().numpy(), lod.numpy()))
+
+    @staticmethod
+    def backward(ctx, d_out):
+        uv, lod = ctx.saved_tensors
+        return torch.from_numpy(nvdr.texture_mipmap_grad_uv(ctx.levels, uv.detach().numpy(), lod.numpy(), d_out.numpy())), None, None
+
+
 class _Antialias(torch.autograd.Function):
     @staticmethod
     def forward(ctx, color, rast, pos_clip, tri, opp):
@@ -161,6 +176,13 @@ class Mesh:
         self.tex = None if tex is None else np.ascontiguousarray(tex, dtype=F)
         self.vtx_color = None if vtx_color is None else np.ascontiguousarray(vtx_color, dtype=F)
         self.opp = nvdr.build_edge_opposites(self.tri)
+        self.texture_filter = "linear"  # or "linear-mipmap-linear" (extension)
+        self._mips = None
+
+    def mip_levels(self):
+        if self._mips is None:
+            self._mips = nvdr.build_mip_chain(self.tex)
+        return self._mips
 
     @property
     def textured(self):
@@ -197,11 +219,28 @@ def render(mesh, proj, quat_raw, trans, H, W):
 
     if mesh.textured:
         texc = _Interpolate.apply(torch.from_numpy(mesh.uv), rast, mesh.tri)
-        color = _TextureLinear.apply(torch.from_numpy(mesh.tex), texc)
+        if mesh.texture_filter == "linear-mipmap-linear":
+            levels = mesh.mip_levels()
+            lod = nvdr.texture_lod(pos_clip.detach().numpy(), mesh.tri, mesh.uv, rast.detach().numpy(), mesh.tex.shape[:2], len(levels))
+            color = _TextureMipmap.apply(texc, torch.from_numpy(lod), levels)
+        else:
+            color = _TextureLinear.apply(torch.from_numpy(mesh.tex), texc)
     else:
         color = _Interpolate.apply(torch.from_numpy(mesh.vtx_color), rast, mesh.tri)
     color = color * torch.clamp(rast[..., -1:], 0, 1)
     return {"rgb": color, "depth": depth, "mask": mask, "rast_out": rast, "mtx": mtx}
+
+
+_SOBEL = torch.tensor([[[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]], [[-1.0, -2.0, -1.0], [0.0, 0.0, 0.0], [1.0, 2.0, 1.0]]])
+
+
+def sobel_magnitude(img):
+    """EXTENSION: [B,h,w,3] -> [B,h,w]; grey = channel mean, 3x3 Sobel with zero
+    padding (cross-correlation, row index increasing with the array's first image axis),
+    sqrt(Gx^2 + Gy^2 + 1e-12)."""
+    g = img.mean(dim=-1).unsqueeze(1)
+    d = torch.nn.functional.conv2d(g, _SOBEL.unsqueeze(1), padding=1)
+    return torch.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2 + 1e-12)
 
 
 def window_slice(t, window):
@@ -233,6 +272,13 @@ def losses(renders, gt, lr_mult, cfg_losses, window=None):
         d = torch.abs(window_slice(renders["mask"], window) - seg)
         logged["mask_selection"] = torch.mean(torch.abs(d.detach()), (1, 2, 3)) * w
         total = total + (torch.mean(d, (1, 2, 3)) * lr_mult).mean() * w
+    if cfg_losses.get("l1_edge"):  # extension, no reference counterpart
+        w = cfg_losses.get("weight_edge", 1.0)
+        er = sobel_magnitude(window_slice(renders["rgb"], window))
+        eg = sobel_magnitude(window_slice(gt["rgb"][None], window))
+        d = torch.abs((er - eg) * seg[..., 0])
+        logged["edge"] = torch.mean(d.detach(), (1, 2)) * w
+        total = total + (torch.mean(d, (1, 2)) * lr_mult).mean() * w
     return total, logged
 
 
@@ -267,7 +313,11 @@ def run_optimization(mesh, proj, quat0, trans0, gt, lr_mult, cfg_losses, hyper, 
     nb = int(hyper["nb_iterations"])
     params = [torch.nn.Parameter(torch.tensor(np.asarray(quat0, dtype=F)[:, i].copy())) for i in range(4)]
     params += [torch.nn.Parameter(torch.tensor(np.asarray(trans0, dtype=F)[:, i].copy())) for i in range(3)]
-    opt = torch.optim.SGD(params, lr=hyper.get("learning_rate_base", 1))
+    if hyper.get("optimizer", "sgd") == "adam":  # extension: torch.optim.Adam on the same graph
+        opt = torch.optim.Adam(params, lr=hyper.get("learning_rate_base", 1), betas=(hyper.get("adam_beta1", 0.9), hyper.get("adam_beta2", 0.999)),
+                               eps=hyper.get("adam_eps", 1e-8))
+    else:
+        opt = torch.optim.SGD(params, lr=hyper.get("learning_rate_base", 1))
     lr = torch.as_tensor(np.asarray(lr_mult, dtype=F))
     poses, mtxs, hist = [], [], {}
     for it in range(nb + 1):

@@ -1,0 +1,12 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, bench (both arms), ncu launch list + full capture of the two hot kernels.
+TAG=${1:-r01b}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/${TAG}_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
+timeout 600 python bench.py --steps 200 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
+ITERS=12 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python scripts/dev_kernels.py > gpurun_out/${TAG}_launches.log 2>&1
+ITERS=6 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'raster_kernel|pixel_kernel' -s 24 -c 2 -f -o gpurun_out/${TAG}_full python scripts/dev_kernels.py > gpurun_out/${TAG}_full.log 2>&1
+tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_bench.json; cat gpurun_out/${TAG}_bench_ref.json

@@ -1,0 +1,151 @@
+"""GPU parity of the north_star extensions that have no reference counterpart:
+Sobel-edge loss, linear-mipmap-linear texture filter, Adam pose step. Each is checked through the C ABI
+against its own oracle (oracle/refpath.py, oracle/nvdr.py); defaults stay the reference's behaviour."""
+import numpy as np
+import pytest
+import torch
+
+import scene_util as su
+from test_gpu_parity import ALL, Example, _angle_deg, _cfg, _loss_table
+
+pytestmark = pytest.mark.gpu
+
+EDGE_ONLY = dict(l1_edge=True, weight_edge=1.0)
+FULL = dict(ALL, l1_edge=True, weight_edge=0.5)
+
+
+@pytest.fixture(scope="module")
+def ex_q():
+    return Example(0.5)
+
+
+def _oracle(ex, qs, ts, lr, losses, mip=False, window=None, b_global=None):
+    from oracle import refpath
+
+    mesh = ex.oracle_mesh()
+    if mip:
+        mesh.texture_filter = "linear-mipmap-linear"
+    return refpath.forward_backward(mesh, ex.P, qs, ts, ex.gt_t(), lr, losses, ex.H, ex.W, window=window, b_global=b_global)
+
+
+@pytest.mark.parametrize("losses", [EDGE_ONLY, FULL])
+def test_edge_loss_and_gradient_match_oracle(ex_q, losses):
+    ex = ex_q
+    B = 3
+    qs, ts = su.perturbed_poses(ex.q, ex.t, B)
+    lr = su.lr_multipliers(B)
+    ex.sc.set_texture_filter("linear")
+    loss, grad = ex.sc.loss_grad(torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda(), torch.from_numpy(lr).cuda(), _cfg(ex.n, losses))
+    logged, gq, gtr, _ = _oracle(ex, qs, ts, lr, losses)
+    assert logged["edge"].numpy().min() > 1e-5, "the edge loss must be live"
+    assert np.allclose(loss.cpu().numpy(), _loss_table(logged, B), rtol=1e-4, atol=1e-10)
+    go, gg = np.concatenate([gq, gtr], 1), grad.cpu().numpy()
+    assert np.abs(go).max() > 0
+    assert np.abs(go - gg).max() <= 1e-4 * np.abs(go).max()
+
+
+def test_edge_loss_window_zero_padding_and_shard(ex_q):
+    """The Sobel stencil is zero-padded at the loss window (not at the frame), for render and target alike;
+    a 2-of-5 shard carries the global divisor."""
+    ex = ex_q
+    B = 2
+    qs, ts = su.perturbed_poses(ex.q, ex.t, B)
+    lr = su.lr_multipliers(B)
+    seg = ex.gt["segmentation"]
+    ys, xs = np.nonzero(seg[..., 0] > 0)
+    # a window that cuts through the object: its border lies on covered pixels
+    cy, cx = int((ys.min() + ys.max()) // 2), int((xs.min() + xs.max()) // 2)
+    win = (cy - 20, cx - 90, 70, 100)
+    try:
+        ex.sc.set_window(*win)
+        loss, grad = ex.sc.loss_grad(torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda(), torch.from_numpy(lr).cuda(), _cfg(ex.n, FULL), b_global=5)
+        logged, gq, gtr, _ = _oracle(ex, qs, ts, lr, FULL, window=win, b_global=5)
+        assert np.allclose(loss.cpu().numpy(), _loss_table(logged, B), rtol=1e-4, atol=1e-10)
+        go, gg = np.concatenate([gq, gtr], 1), grad.cpu().numpy()
+        assert np.abs(go - gg).max() <= 1e-4 * np.abs(go).max()
+    finally:
+        ex.sc.set_window(0, 0, ex.H, ex.W)
+
+
+def test_mipmap_render_loss_gradient_match_oracle(ex_q):
+    from oracle import refpath
+
+    ex = ex_q
+    B = 3
+    qs, ts = su.perturbed_poses(ex.q, ex.t, B)
+    lr = su.lr_multipliers(B)
+    try:
+        ex.sc.set_texture_filter("linear-mipmap-linear")
+        out = ex.sc.render(torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda())
+        mesh = ex.oracle_mesh()
+        mesh.texture_filter = "linear-mipmap-linear"
+        r = refpath.render(mesh, ex.P, torch.from_numpy(qs), torch.from_numpy(ts), ex.H, ex.W)
+        rgb_o, rgb_g = r["rgb"].numpy(), out["rgb"].cpu().numpy()
+        assert np.array_equal(r["rast_out"].numpy()[..., 3], out["rast"].cpu().numpy()[..., 3])
+        assert np.abs(rgb_o - rgb_g).max() <= 1e-4, "trilinear colour within 1e-4 (float32 level of detail vs float64 in the oracle)"
+        # the filter must actually do something on this heavily minified texture
+        lin = refpath.render(ex.oracle_mesh(), ex.P, torch.from_numpy(qs), torch.from_numpy(ts), ex.H, ex.W)["rgb"].numpy()
+        assert np.abs(lin - rgb_o).max() > 0.05
+        for losses in (ALL, FULL):
+            loss, grad = ex.sc.loss_grad(torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda(), torch.from_numpy(lr).cuda(), _cfg(ex.n, losses))
+            logged, gq, gtr, _ = _oracle(ex, qs, ts, lr, losses, mip=True)
+            assert np.allclose(loss.cpu().numpy(), _loss_table(logged, B), rtol=1e-4, atol=1e-10)
+            go, gg = np.concatenate([gq, gtr], 1), grad.cpu().numpy()
+            assert np.abs(go - gg).max() <= 2e-4 * np.abs(go).max()
+    finally:
+        ex.sc.set_texture_filter("linear")
+    # back on the reference filter the render is bit-exact again
+    out = ex.sc.render(torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda(), want=("rgb",))
+    assert np.array_equal(lin, out["rgb"].cpu().numpy())
+
+
+def test_adam_trajectory_matches_torch_adam(ex_q):
+    """ddope_optimize with DDOPE_OPT_ADAM against torch.optim.Adam on the oracle graph, 8 iterations."""
+    from oracle import refpath
+
+    ex = ex_q
+    B, iters = 2, 8
+    qs, ts = np.tile(ex.q, (B, 1)), np.tile(ex.t, (B, 1))
+    lr = np.array([0.5, 2.0], dtype=np.float32)
+    hyper = dict(nb_iterations=iters - 1, base_lr=0.002, lr_decay=0.5, learning_rate_base=1, optimizer="adam", adam_beta1=0.9, adam_beta2=0.99, adam_eps=1e-8)
+    o = refpath.run_optimization(ex.oracle_mesh(), ex.P, qs, ts, ex.gt_t(), lr, ALL, hyper, ex.H, ex.W)
+    sched = [refpath.lr_schedule(it, iters - 1, hyper["base_lr"], hyper["lr_decay"]) for it in range(iters)]
+    try:
+        ex.sc.set_optimizer("adam", beta1=0.9, beta2=0.99, eps=1e-8)
+        qd, td = torch.from_numpy(qs).cuda().contiguous(), torch.from_numpy(ts).cuda().contiguous()
+        ph, lh = ex.sc.optimize(qd, td, torch.from_numpy(lr).cuda(), sched, _cfg(ex.n, ALL))
+        # the first Adam step moves every parameter by exactly lr_0 (bias-corrected m/sqrt(v) = sign g)
+        step0 = np.abs(ph[1].cpu().numpy() - ph[0].cpu().numpy())
+        assert np.allclose(step0, sched[0], rtol=2e-3)
+        fin = np.concatenate([qd.cpu().numpy(), td.cpu().numpy()], 1)
+        assert _angle_deg(fin[:, :4], o["final"][:, :4]).max() < 0.1
+        assert np.abs(fin[:, 4:] - o["final"][:, 4:]).max() < 1e-3
+        assert np.abs(ph.cpu().numpy()[:3] - o["poses"][:3]).max() < 2e-5
+        # continuing from stored moments (step0 = 4) reproduces the one-call trajectory bit for bit
+        qd2, td2 = torch.from_numpy(qs).cuda().contiguous(), torch.from_numpy(ts).cuda().contiguous()
+        ex.sc.set_optimizer("adam", beta1=0.9, beta2=0.99, eps=1e-8, step0=0)
+        ex.sc.optimize(qd2, td2, torch.from_numpy(lr).cuda(), sched[:4], _cfg(ex.n, ALL))
+        ex.sc.set_optimizer("adam", beta1=0.9, beta2=0.99, eps=1e-8, step0=4)
+        ex.sc.optimize(qd2, td2, torch.from_numpy(lr).cuda(), sched[4:], _cfg(ex.n, ALL))
+        assert torch.equal(qd2, qd) and torch.equal(td2, td)
+    finally:
+        ex.sc.set_optimizer("sgd")
+
+
+def test_extension_errors(ex_q):
+    ex = ex_q
+    with pytest.raises(RuntimeError):
+        ex.sc.set_texture_filter("cubic")
+    with pytest.raises(RuntimeError):
+        ex.sc.set_optimizer("lbfgs")
+    with pytest.raises(RuntimeError):
+        ex.sc.set_optimizer("adam", beta1=1.5)
+    # edge loss needs the rgb target
+    n = ex.n
+    sc = n.NativeScene(ex.arr["pos"], ex.arr["tri"], ex.arr["uv"], ex.arr["tex"])
+    sc.set_camera(ex.P, ex.H, ex.W)
+    sc.set_target(None, ex.g["depth"], ex.g["segmentation"])
+    q = torch.from_numpy(ex.q[None]).cuda()
+    t = torch.from_numpy(ex.t[None]).cuda()
+    with pytest.raises(RuntimeError, match="edge loss needs the rgb target"):
+        sc.loss_grad(q, t, torch.ones(1).cuda(), _cfg(n, EDGE_ONLY))

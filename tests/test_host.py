@@ -33,11 +33,11 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(LIB)
     names = _declared_symbols()
-    assert len(names) >= 18
+    assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), "libddope_b200.so does not export %s" % n
     lib.ddope_abi_version.restype = ctypes.c_int
-    assert lib.ddope_abi_version() == 1
+    assert lib.ddope_abi_version() == 2
 
 
 def test_library_is_sm100a_with_lineinfo():

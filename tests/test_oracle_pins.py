@@ -299,3 +299,98 @@ def test_window_equals_slice_of_full_frame(golden):
     y0, x0, h, w = win
     manual = torch.abs(r["mask"][:, y0:y0 + h, x0:x0 + w] - gt["segmentation"][None, y0:y0 + h, x0:x0 + w]).mean((1, 2, 3))
     assert torch.allclose(logged["mask_selection"], manual)
+
+
+# ----------------------------------------------------------------------------------------------
+# extensions (no reference counterpart): pinned against closed forms
+
+
+def test_ext_sobel_closed_forms():
+    """Linear ramps have constant Sobel response 8*slope in the interior; the window border is zero-padded."""
+    H, W = 12, 16
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    img = torch.tensor(np.stack([0.5 * xx + 0.25 * yy] * 3, -1)[None])
+    e = refpath.sobel_magnitude(img)[0].numpy()
+    assert np.allclose(e[1:-1, 1:-1], np.hypot(8 * 0.5, 8 * 0.25), rtol=1e-6)
+    assert e[0, 0] != pytest.approx(np.hypot(4.0, 2.0))  # border sees the zero padding
+    flat = refpath.sobel_magnitude(torch.full((1, H, W, 3), 0.7))[0].numpy()
+    assert np.allclose(flat[1:-1, 1:-1], 1e-6, atol=1e-8)  # sqrt(1e-12)
+    # grey is the channel mean
+    rgb = torch.rand(1, H, W, 3)
+    assert torch.allclose(refpath.sobel_magnitude(rgb), refpath.sobel_magnitude(rgb.mean(-1, keepdim=True).expand(-1, -1, -1, 3)), atol=1e-6)
+
+
+def test_ext_mip_chain_and_lod_closed_form():
+    tex = np.random.default_rng(0).random((64, 32, 3)).astype(np.float32)
+    lv = nvdr.build_mip_chain(tex)
+    assert [l.shape[:2] for l in lv] == [(64, 32), (32, 16), (16, 8), (8, 4), (4, 2), (2, 1), (1, 1)]
+    for l in lv:
+        assert np.allclose(l.mean((0, 1)), tex.mean((0, 1)), atol=1e-6)  # box filtering preserves the mean
+    assert np.allclose(lv[1][3, 5], tex[6:8, 10:12].mean((0, 1)), atol=1e-7)
+    assert len(nvdr.build_mip_chain(tex, max_levels=3)) == 3
+    # fronto-parallel unit quad at depth d, uv = (x+0.5, y+0.5): footprint = tex_size / pixels-across
+    fx = 100.0
+    H = W = 64
+    P = refpath.projection_matrix(fx, fx, 32.0, 32.0, W, H)
+    d = 4.0
+    pos = np.array([[-0.5, -0.5, 0], [0.5, -0.5, 0], [0.5, 0.5, 0], [-0.5, 0.5, 0]], dtype=np.float32)
+    tri = np.array([[0, 1, 2], [0, 2, 3]])
+    uv = (pos[:, :2] + 0.5).astype(np.float32)
+    M = np.eye(4, dtype=np.float32)[None].copy()
+    M[0, 2, 3] = -d
+    clip = nvdr.canonical_xfm_points(pos[None], nvdr.canonical_mvp(P, M))
+    rast = nvdr.rasterize(clip, tri, H, W)
+    assert (rast[..., 3] > 0).sum() > 400
+    for tw in (256, 1024):
+        lod = nvdr.texture_lod(clip, tri, uv, rast, (tw, tw), 11)
+        want = np.log2(tw / (fx / d))  # texels per pixel: tw texels over fx/d pixels
+        cov = rast[..., 3] > 0
+        assert np.allclose(lod[cov], want, atol=1e-3)
+        assert (lod[~cov] == 0).all()
+    # trilinear lookup of a constant-per-level chain returns the level blend
+    levels = [np.full((8 >> l, 8 >> l, 3), float(l), np.float32) for l in range(4)]
+    uvq = np.random.default_rng(1).random((1, 4, 4, 2)).astype(np.float32)
+    lodq = np.array([0.0, 0.25, 1.5, 3.0, 2.999, 0.5, 1.0, 2.0] * 2, np.float32).reshape(1, 4, 4)
+    out = nvdr.texture_mipmap(levels, uvq, lodq)
+    assert np.allclose(out[..., 0], lodq, atol=1e-6)
+
+
+def test_ext_mipmap_uv_gradient_matches_finite_differences():
+    rng = np.random.default_rng(2)
+    levels = nvdr.build_mip_chain(rng.random((32, 32, 3)).astype(np.float32))
+    uv = rng.random((1, 6, 6, 2)).astype(np.float32) * 3 - 1  # wraps
+    lod = (rng.random((1, 6, 6)) * 3.5).astype(np.float32)
+    dy = rng.normal(size=(1, 6, 6, 3)).astype(np.float32)
+    g = nvdr.texture_mipmap_grad_uv(levels, uv, lod, dy)
+    h = 1e-3
+    for k in range(2):
+        up, um = uv.copy(), uv.copy()
+        up[..., k] += h
+        um[..., k] -= h
+        fd = ((nvdr.texture_mipmap(levels, up, lod) - nvdr.texture_mipmap(levels, um, lod)) * dy).sum(-1) / (2 * h)
+        # bilinear is piecewise linear in uv: exclude samples whose +-h interval crosses a texel boundary
+        ok = np.ones(fd.shape, bool)
+        for l in range(len(levels)):
+            s = levels[l].shape[1 - k]
+            a = np.floor((up[..., k] - np.floor(up[..., k])) * s - 0.5)
+            b = np.floor((um[..., k] - np.floor(um[..., k])) * s - 0.5)
+            ok &= a == b
+        assert ok.sum() > 10
+        assert np.allclose(g[..., k][ok], fd[ok], rtol=2e-2, atol=2e-2)
+
+
+def test_ext_adam_oracle_first_step_is_lr():
+    v, f, col = _cube()
+    mesh = refpath.Mesh(v, f, vtx_color=col)
+    H, W = 48, 64
+    P = refpath.projection_matrix(80.0, 80.0, 32.0, 24.0, W, H)
+    rng = np.random.default_rng(5)
+    gt = dict(rgb=torch.tensor(rng.random((H, W, 3)).astype(np.float32)), depth=torch.tensor((3 + rng.random((H, W))).astype(np.float32)),
+              segmentation=torch.ones(H, W, 3))
+    q0 = np.array([[0.3, 0.2, 0.1, 0.9]], dtype=np.float32)
+    t0 = np.array([[0.1, -0.05, -4.0]], dtype=np.float32)
+    losses = dict(l1_rgb_with_mask=True, l1_depth_with_mask=True, l1_mask=True)
+    hyper = dict(nb_iterations=1, base_lr=0.01, lr_decay=0.5, learning_rate_base=1, optimizer="adam")
+    o = refpath.run_optimization(mesh, P, q0, t0, gt, np.ones(1, np.float32), losses, hyper, H, W)
+    lr0 = refpath.lr_schedule(0, 1, 0.01, 0.5)
+    assert np.allclose(np.abs(o["poses"][1] - o["poses"][0]), lr0, rtol=1e-3)
