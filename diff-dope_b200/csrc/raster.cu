@@ -29,10 +29,6 @@ void launch_clear(const SceneDev& S, const HypState* hyp, int B, unsigned long l
 constexpr int RASTER_THREADS = 256;
 constexpr int SMALL_EXTENT = 64 * SUBPIX;  // bbox extent up to which int32 edge functions cannot overflow
 constexpr int REC_WORDS = 25;
-#ifndef OWN_CAP_N
-#define OWN_CAP_N 0
-#endif
-constexpr int OWN_CAP = OWN_CAP_N;  // candidates a lane walks on its own before the warp shares the work
 
 // Per-triangle record in shared memory (25 words: odd stride, so lanes reading different records
 // hit different banks). Small triangles: incremental int32 edge functions relative to the bbox
@@ -89,7 +85,6 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
     __shared__ int s_rec[RASTER_THREADS * REC_WORDS];
     __shared__ int s_off[RASTER_THREADS];
     __shared__ int s_nlarge;
-    __shared__ unsigned int s_queue[(RASTER_THREADS / 32) * 64];
     if (threadIdx.x < 16) s_mvp[threadIdx.x] = hyp[b].mvp[threadIdx.x];
     if (threadIdx.x == 0) {
         const HypState& h = hyp[b];
@@ -152,7 +147,8 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
                         edge_setup32(X[0], Y[0], X[1], Y[1], ox, oy, my->k0, my->a0, my->b0);
                         edge_setup32(X[1], Y[1], X[2], Y[2], ox, oy, my->k1, my->a1, my->b1);
                         edge_setup32(X[2], Y[2], X[0], Y[0], ox, oy, my->k2, my->a2, my->b2);
-                        my->pxmin = pxmin; my->pymin = pymin; my->bw = pxmax - pxmin + 1;
+                        my->pxmin = pxmin; my->pymin = pymin;
+                        my->bw = (pxmax - pxmin + 1) | ((pymax - pymin + 1) << 8);  // both <= 66 (SMALL_EXTENT)
                         npx = (pxmax - pxmin + 1) * (pymax - pymin + 1);
                         nrows = pymax - pymin + 1;
                     } else {
@@ -165,96 +161,55 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
     }
 
     // ---- small triangles --------------------------------------------------------------------------
-    // Stage 1 finds the candidates whose pixel centre is inside (integer edge functions) and pushes
-    // them into a per-warp queue; stage 2 runs whenever 32 are queued: float z/w + atomicMin with all
-    // lanes busy (only ~1 candidate in 4 is inside its triangle).
-    unsigned int* wq = s_queue + (threadIdx.x >> 5) * 64;
-    int nqueued = 0;
-    auto push_and_drain = [&](bool inside, unsigned int entry) {
-        const unsigned int m = __ballot_sync(0xffffffffu, inside);
-        if (inside) wq[nqueued + __popc(m & ((1u << lane) - 1))] = entry;
-        nqueued += __popc(m);
-        if (nqueued >= 32) {  // warp-uniform
-            __syncwarp();
-            const unsigned int e = wq[lane];
-            const unsigned int keep = wq[32 + lane];
-            __syncwarp();
-            const TriRec* r = reinterpret_cast<const TriRec*>(s_rec + (wbase + (e >> 16)) * REC_WORDS);
-            depth_test_write(S, r->c0, r->c1, r->c2, r->tri, r->pxmin + (int)(e & 0xFF), r->pymin + (int)((e >> 8) & 0xFF), zb,
-                             xs, xo, ys, yo);
-            nqueued -= 32;
-            if (lane < nqueued) wq[lane] = keep;
-        }
-    };
-
-    // (a) bounding boxes of up to OWN_CAP pixel centres (almost all of a dense mesh): each lane walks
-    //     its own triangle with incremental edge functions -- no search, three adds per candidate
-    {
-        const int own = (npx <= OWN_CAP) ? npx : 0;
-        int maxown = own;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxown = max(maxown, __shfl_xor_sync(0xffffffffu, maxown, o));
-        int e0 = 0, e1 = 0, e2 = 0, r0 = 0, r1 = 0, r2 = 0, bw = 1, col = 0, row = 0;
-        if (own > 0) {
-            r0 = e0 = my->k0; r1 = e1 = my->k1; r2 = e2 = my->k2;
-            bw = my->bw;
-        }
-        const int a0 = own > 0 ? my->a0 : 0, a1 = own > 0 ? my->a1 : 0, a2 = own > 0 ? my->a2 : 0;
-        const int b0 = own > 0 ? my->b0 : 0, b1 = own > 0 ? my->b1 : 0, b2 = own > 0 ? my->b2 : 0;
-        for (int it = 0; it < maxown; it++) {
-            const bool inside = (it < own) && ((e0 | e1 | e2) >= 0);
-            push_and_drain(inside, ((unsigned int)lane << 16) | ((unsigned int)row << 8) | (unsigned int)col);
-            col++;
-            e0 += a0; e1 += a1; e2 += a2;
-            if (col == bw) {
-                col = 0; row++;
-                r0 += b0; r1 += b1; r2 += b2;
-                e0 = r0; e1 = r1; e2 = r2;
-            }
-        }
-    }
-
-    // (b) flatten the warp's (triangle, row) items: each lane takes one row of some triangle, solves
-    //     the three edge inequalities for the column span (float estimate, exact integer fix-up: the
-    //     inside set of a row is an interval), and pushes only the pixels that are inside. Work is
-    //     proportional to rows + covered samples, not to bounding-box area (5x fewer items at 1080p).
-    const int nbig = (npx > OWN_CAP) ? nrows : 0;
-    int incl = nbig;
+    // Two levels of flattening, so lanes stay busy whatever the triangle shapes are (the mesh mixes ~1 px^2
+    // triangles with 200 x 1 px strips):
+    //  (1) the warp's (triangle, scanline) items: a scanline is a row, or a column when the bounding box is
+    //      taller than wide (fewer items). Each lane takes one item and solves the three edge inequalities for
+    //      the covered span (float estimate + exact integer fix-up: the inside set of a scanline is an interval);
+    //  (2) the covered pixels of those 32 spans: prefix sum over the span lengths, then 32 pixels per step, each
+    //      lane finding its span by a 5-step shuffle search. Every pixel handed out is inside its triangle, so
+    //      all lanes run the float z/w + atomicMin.
+    // Work is proportional to scanlines + covered samples, not to bounding-box area.
+    const int nitems = (npx > 0) ? min(nrows, my->bw & 0xFF) : 0;
+    int incl = nitems;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int n = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += n;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    s_off[threadIdx.x] = incl - nbig;
+    s_off[threadIdx.x] = incl - nitems;
     __syncwarp();
     for (int base = 0; base < total; base += 32) {
         const int j = base + lane;
-        int lo = 0, row = 0, L = 0, count = 0;
+        int lo = 0, item = 0, L = 0, count = 0, tr = 0;
         if (j < total) {
             // owner = last lane whose exclusive offset is <= j
 #pragma unroll
             for (int step = 16; step > 0; step >>= 1)
                 if (s_off[wbase + lo + step] <= j) lo += step;
             const TriRec* r = reinterpret_cast<const TriRec*>(s_rec + (wbase + lo) * REC_WORDS);
-            row = j - s_off[wbase + lo];
-            const int bw = r->bw;
-            int U = bw - 1;
-            const int ek[3] = {r->k0 + r->b0 * row, r->k1 + r->b1 * row, r->k2 + r->b2 * row};
-            const int ak[3] = {r->a0, r->a1, r->a2};
-            const float fbw = (float)bw;
+            item = j - s_off[wbase + lo];
+            const int bw = r->bw & 0xFF, bh = (r->bw >> 8) & 0xFF;
+            tr = bw < bh;                       // scan columns instead of rows
+            const int along = tr ? bh : bw;     // pixels along a scanline
+            int U = along - 1;
+            const int ek[3] = {r->k0 + (tr ? r->a0 : r->b0) * item, r->k1 + (tr ? r->a1 : r->b1) * item,
+                               r->k2 + (tr ? r->a2 : r->b2) * item};
+            const int ak[3] = {tr ? r->b0 : r->a0, tr ? r->b1 : r->a1, tr ? r->b2 : r->a2};
+            const float fal = (float)along;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                // columns with e + a*c >= 0: c >= ceil(-e/a) if a > 0, c <= floor(-e/a) if a < 0. The float
+                // positions with e + a*c >= 0: c >= ceil(-e/a) if a > 0, c <= floor(-e/a) if a < 0. The float
                 // root is within 1e-5 of the true one wherever it matters (|root| <= 65), so one exact
                 // integer correction step in each direction settles it; no loops, no divergence.
                 const int e = ek[k], a = ak[k];
                 const float root = __fdividef(-(float)e, (float)a);  // +-inf / NaN when a == 0: clamped below, unused
-                int cl = (int)fminf(fmaxf(ceilf(root), 0.f), fbw);
-                int cu = (int)fminf(fmaxf(floorf(root), -1.f), fbw - 1.f);
+                int cl = (int)fminf(fmaxf(ceilf(root), 0.f), fal);
+                int cu = (int)fminf(fmaxf(floorf(root), -1.f), fal - 1.f);
                 if (cl > 0 && e + a * (cl - 1) >= 0) cl--;
-                else if (cl < bw && e + a * cl < 0) cl++;
-                if (cu < bw - 1 && e + a * (cu + 1) >= 0) cu++;
+                else if (cl < along && e + a * cl < 0) cl++;
+                if (cu < along - 1 && e + a * (cu + 1) >= 0) cu++;
                 else if (cu >= 0 && e + a * cu < 0) cu--;
                 if (a > 0) L = max(L, cl);
                 if (a < 0) U = min(U, cu);
@@ -262,18 +217,34 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
             }
             count = max(0, U - L + 1);
         }
-        int maxc = count;
+        // (2) hand the covered pixels of these 32 spans out evenly
+        int pin = count;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
-        for (int k = 0; k < maxc; k++)
-            push_and_drain(k < count, ((unsigned int)lo << 16) | ((unsigned int)row << 8) | (unsigned int)(L + k));
-    }
-    __syncwarp();
-    if (lane < nqueued) {
-        const unsigned int e = wq[lane];
-        const TriRec* r = reinterpret_cast<const TriRec*>(s_rec + (wbase + (e >> 16)) * REC_WORDS);
-        depth_test_write(S, r->c0, r->c1, r->c2, r->tri, r->pxmin + (int)(e & 0xFF), r->pymin + (int)((e >> 8) & 0xFF), zb, xs,
-                         xo, ys, yo);
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, pin, o);
+            if (lane >= o) pin += n;
+        }
+        const int totpx = __shfl_sync(0xffffffffu, pin, 31);
+        const int pex = pin - count;
+        const unsigned int pack = (unsigned int)lo | ((unsigned int)item << 8) | ((unsigned int)L << 16) | ((unsigned int)tr << 24);
+        for (int pb = 0; pb < totpx; pb += 32) {
+            const int p = pb + lane;
+            int ol = 0;  // first lane whose inclusive count exceeds p
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, pin, ol + step - 1);
+                if (v <= p) ol += step;
+            }
+            const unsigned int opk = __shfl_sync(0xffffffffu, pack, ol);
+            const int oex = __shfl_sync(0xffffffffu, pex, ol);
+            if (p < totpx) {
+                const TriRec* r = reinterpret_cast<const TriRec*>(s_rec + (wbase + (int)(opk & 31u)) * REC_WORDS);
+                const int it2 = (int)((opk >> 8) & 0xFFu), al = (int)((opk >> 16) & 0xFFu) + (p - oex);
+                const bool t2 = (opk >> 24) != 0u;
+                depth_test_write(S, r->c0, r->c1, r->c2, r->tri, r->pxmin + (t2 ? it2 : al), r->pymin + (t2 ? al : it2), zb, xs, xo,
+                                 ys, yo);
+            }
+        }
     }
 
     // ---- large triangles: the whole CTA walks each bounding box (64-bit edge functions) ---------

@@ -7,7 +7,8 @@ _compat.ensure()
 from .diffdope import *  # noqa: F401,F403,E402
 from .diffdope import (Camera, DiffDope, Image, Mesh, Object3D, Scene, dist_batch_lr, find_crop, interpolate,  # noqa: F401
                        l1_depth_with_mask, l1_mask, l1_rgb_with_mask, make_grid, make_grid_image, make_grid_overlay_batch,
-                       matrix_batch_44_from_position_quat, opencv_2_opengl, render_texture_batch)
+                       matrix_batch_44_from_position_quat, opencv_2_opengl, render_texture_batch,
+                       l1_edge, run_optimization_batched, sobel_magnitude)  # the last three are extensions
 from .ops import xfm_points, xfm_vectors  # noqa: F401
 
 __all__ = ["xfm_points", "xfm_vectors"]

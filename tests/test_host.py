@@ -143,7 +143,7 @@ def test_compat_shims_and_config():
 
     cfg = OmegaConf.load(os.path.join(ROOT, "configs", "diffdope.yaml"))
     assert cfg.camera.fx == 1390.53 and cfg.hyperparameters.nb_iterations == 60 and cfg.losses.l1_mask is True
-    assert set(cfg.keys()) == {"camera", "scene", "object3d", "losses", "hyperparameters", "render_images"}
+    assert set(cfg.keys()) == {"camera", "scene", "object3d", "losses", "hyperparameters", "render_images", "render"}  # "render" holds an extension key
     assert dict(**cfg.camera)["im_height"] == 1080
     assert len(cfg.object3d.rotation) == 9 and cfg.hyperparameters.learning_rates_bound[1] == 100
     assert hasattr(hydra, "main") and hasattr(hydra.core.hydra_config, "HydraConfig")
