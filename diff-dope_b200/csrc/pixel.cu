@@ -314,6 +314,57 @@ __device__ void aa_grad_accum(const SceneDev& S, const float* mvp, int tri, int 
 
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
+// Sum each of the NACC accumulators over the warp by recursive halving: at every step a lane keeps one half of
+// its values and trades the other half with its partner, so 20 values cost 10+5+3+2+1 = 21 shuffles instead of
+// 20 x 5. Lane l ends up with the warp total of accumulator `idx` (valid == true) or with padding. Fixed order:
+// bit-reproducible.
+__device__ __forceinline__ float warp_reduce_nacc(const float* v, int lane, int& idx, bool& valid) {
+    static_assert(NACC == 20, "halving schedule below is written for 20 values");
+    const unsigned int full = 0xffffffffu;
+    bool up = (lane & 16) != 0;
+    float a10[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const float send = up ? v[i] : v[10 + i], keep = up ? v[10 + i] : v[i];
+        a10[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+    int base = up ? 10 : 0;
+    up = (lane & 8) != 0;
+    float a5[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const float send = up ? a10[i] : a10[5 + i], keep = up ? a10[5 + i] : a10[i];
+        a5[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+    base += up ? 5 : 0;
+    up = (lane & 4) != 0;  // 5 -> [0,3) | [3,5) + one pad
+    float a3[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float hi = (i < 2) ? a5[3 + i] : 0.f;
+        const float send = up ? a5[i] : hi, keep = up ? hi : a5[i];
+        a3[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    base += up ? 3 : 0;
+    int nv = up ? 2 : 3;
+    up = (lane & 2) != 0;  // 3 -> [0,2) | [2,3) + one pad
+    float a2[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const float hi = (i < 1) ? a3[2] : 0.f;
+        const float send = up ? a3[i] : hi, keep = up ? hi : a3[i];
+        a2[i] = keep + __shfl_xor_sync(full, send, 2);
+    }
+    base += up ? 2 : 0;
+    nv = up ? (nv > 2 ? 1 : 0) : 2;
+    up = (lane & 1) != 0;
+    const float send = up ? a2[0] : a2[1], keep = up ? a2[1] : a2[0];
+    const float r = keep + __shfl_xor_sync(full, send, 1);
+    idx = base + (up ? 1 : 0);
+    valid = up ? (nv > 1) : (nv > 0);
+    return r;
+}
+
 constexpr int MODE_RENDER = 0;  // write rgb / depth / mask / rast images (ddope_render*)
 constexpr int MODE_LOSS = 1;    // fused reference losses + backward (ddope_loss_grad / ddope_optimize)
 constexpr int MODE_EXT = 2;     // backward of externally supplied image gradients (ddope_render_bwd)
@@ -332,7 +383,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                                                              float* __restrict__ partials, RenderOut out, ExtGrad ext) {
     __shared__ int s_ids[NPAIR];
     __shared__ float s_alpha[2][NPAIR];
-    __shared__ unsigned char s_di[2][NPAIR];
+    __shared__ __align__(4) unsigned char s_di[2][NPAIR];
     __shared__ unsigned short s_queue[2 * NPAIR];
     __shared__ float s_maa[MAA_W * MAA_H];
     __shared__ float s_mvp[16];
@@ -417,13 +468,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                 const unsigned int f0 = __ballot_sync(0xffffffffu, idr[k][0] != ID_OUTSIDE);
                 const unsigned int f1 = __ballot_sync(0xffffffffu, idr[k][1] != ID_OUTSIDE);
                 s_ids[iy * IDS_W + lane] = idr[k][0];
-                s_di[0][iy * IDS_W + lane] = DI_NONE;
-                s_di[1][iy * IDS_W + lane] = DI_NONE;
-                if (lane < IDS_W - 32) {
-                    s_ids[iy * IDS_W + 32 + lane] = idr[k][1];
-                    s_di[0][iy * IDS_W + 32 + lane] = DI_NONE;
-                    s_di[1][iy * IDS_W + 32 + lane] = DI_NONE;
-                }
+                if (lane < IDS_W - 32) s_ids[iy * IDS_W + 32 + lane] = idr[k][1];
                 if (lane == 0) {
                     s_cov[iy] = ((unsigned long long)c1 << 32) | c0;
                     s_inf[iy] = ((unsigned long long)f1 << 32) | f0;
@@ -477,8 +522,12 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
             if (tid == 31) s_nq = incl;
         }
         __syncthreads();
-        const int nq = s_nq;
+        const int nq = s_nq;  // 0 for interior and background tiles: their mask is the plain coverage
 
+        if (nq > 0) {
+        static_assert((2 * NPAIR) % 4 == 0, "s_di is cleared as 32-bit words");
+        for (int i = tid; i < 2 * NPAIR / 4; i += TILE_THREADS) reinterpret_cast<unsigned int*>(&s_di[0][0])[i] = 0x01010101u * DI_NONE;
+        __syncthreads();
         // 3. analyse every queued pair once, one pair per thread
         for (int q = tid; q < nq; q += TILE_THREADS) {
             const int e = s_queue[q];
@@ -525,10 +574,12 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
             s_maa[i] = m;
         }
         __syncthreads();
+        }  // nq > 0
 
         float acc[NACC];
 #pragma unroll
         for (int k = 0; k < NACC; k++) acc[k] = 0.f;
+        bool gtouch = false;  // this thread added to a gradient accumulator (acc[0..15])
 
         if (EDGE) {
             // E1. grey image of the render over tile + 2 px halo (0 for background and outside the loss window:
@@ -583,7 +634,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
             const int x = ox + lx, y = oy + ly;
             if (!(x < rx1 && y < ry1)) continue;
             const int id = s_ids[(ly + 2) * IDS_W + (lx + 2)];
-            const float maa = s_maa[(ly + 1) * MAA_W + (lx + 1)];
+            const float maa = (nq > 0) ? s_maa[(ly + 1) * MAA_W + (lx + 1)] : ((id >= 0) ? 1.f : 0.f);
             const size_t gpix = (size_t)y * S.W + x;
             const size_t wp = ((size_t)b * S.wh + (y - S.wy0)) * S.ww + (x - S.wx0);
             float seg[3] = {1.f, 1.f, 1.f};
@@ -600,6 +651,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
             float depth = -s_m2[3];
             float gu = 0.f, gv = 0.f;  // dL/d(u,v)
             if (id >= 0) {
+                gtouch = true;
                 Shade sh;
                 constexpr bool EX = (MODE == MODE_RENDER);
                 // barycentrics stay on the exactly-rounded path in every mode: sliver triangles amplify a 1-ulp change of
@@ -671,13 +723,14 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                         const float diff = (depth - gt_d) * seg[0];
                         acc[17] += fabsf(diff);
                         acc[15] -= k_depth * sgn(diff) * seg[0];
+                        gtouch = true;
                     }
                     if (cfg.use_rgb) {
 #pragma unroll
                         for (int c = 0; c < 3; c++) acc[16] += fabsf((0.f - gt_rgb[c]) * seg[c]);
                     }
                 }
-                if (MODE == MODE_EXT && ext.d_depth) acc[15] -= ext.d_depth[wp];
+                if (MODE == MODE_EXT && ext.d_depth) { acc[15] -= ext.d_depth[wp]; gtouch = true; }
                 if (MODE == MODE_RENDER && out.rast) reinterpret_cast<float4*>(out.rast)[wp] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (MODE == MODE_LOSS && cfg.use_mask) {
@@ -729,18 +782,29 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                 }
                 const int tri = first_cov ? ida : idb;
                 const int qx = first_cov ? fx : sx, qy = first_cov ? fy : sy;
+                gtouch = true;
                 aa_grad_accum(S, s_mvp, tri, qx, qy, d, di, alpha, dd, acc);
             }
         }
 
         if (MODE != MODE_RENDER) {
-            // 7. CTA reduction of the accumulators, one partial row per tile (fixed order: deterministic)
+            // 7. CTA reduction of the accumulators, one partial row per tile (fixed order: deterministic). Warps that
+            //    touched no gradient accumulator (background rows) only reduce the four loss sums.
+            const int lane = tid & 31;
+            if (__any_sync(0xffffffffu, gtouch)) {
+                int idx;
+                bool valid;
+                const float r = warp_reduce_nacc(acc, lane, idx, valid);
+                if (valid) s_red[tid >> 5][idx] = r;
+            } else {
 #pragma unroll
-            for (int k = 0; k < NACC; k++) {
-                float v = acc[k];
+                for (int k = 16; k < NACC; k++) {
+                    float v = acc[k];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                if ((tid & 31) == 0) s_red[tid >> 5][k] = v;
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == k - 16) s_red[tid >> 5][k] = v;
+                }
+                if (lane < 16) s_red[tid >> 5][lane] = 0.f;
             }
             __syncthreads();
             if (tid < NACC) {

@@ -11,7 +11,8 @@ import numpy as np
 import torch
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libddope_b200.so")
+# DDOPE_B200_LIB: alternative build of the same library (A/B timing of compile-time variants); never a fallback
+_LIB_PATH = os.environ.get("DDOPE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libddope_b200.so")
 
 NUM_LOSSES = 4
 LOSS_KEYS = ("rgb", "depth", "mask_selection", "edge")  # reference add_loss_value keys, diffdope.py:559,577,605; "edge" is an extension
