@@ -2,6 +2,7 @@
 // No torch, no host threads, one stream per call.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -62,6 +63,11 @@ struct ddope_scene {
     unsigned int* arrive = nullptr;        // CTA arrival counter of iter_kernel's last-block scan
     std::vector<float> sched_host;         // staging of the per-iteration scalars (must outlive the async copy)
 };
+
+bool ddope::pdl_enabled() {
+    static const bool on = (getenv("DDOPE_NO_PDL") == nullptr);
+    return on;
+}
 
 extern "C" int ddope_abi_version(void) { return DDOPE_ABI_VERSION; }
 extern "C" const char* ddope_last_error(void) { return g_err.c_str(); }

@@ -94,6 +94,13 @@ __device__ __forceinline__ float orderable_float(unsigned int k) {
     return __uint_as_float(b);
 }
 
+// Programmatic dependent launch (PDL): the three kernels of an iteration are launched with
+// programmaticStreamSerialization, so the next kernel's CTAs are scheduled while the previous kernel drains;
+// pdl_wait() blocks until the previous kernel has completed and its writes are visible. Both are no-ops for
+// kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool same_sign(float a, float b) { return ((__float_as_int(a) ^ __float_as_int(b)) >= 0); }
 
 }  // namespace ddope

@@ -2,7 +2,26 @@
 #pragma once
 #include "ddope_common.cuh"
 
+#include <utility>
+
 namespace ddope {
+
+// Kernel launch with the programmatic-dependent-launch attribute (see pdl_wait / pdl_trigger); `pdl` false = plain launch.
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+bool pdl_enabled();  // api.cu: on unless DDOPE_NO_PDL is set
 
 // pose.cu
 // quat/trans -> HypState (M, MVP, loss ROI, tile prefix). roi_mode: 0 = window (render), 1 = tight (loss).

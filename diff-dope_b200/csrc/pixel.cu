@@ -394,6 +394,8 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
     __shared__ float s_gray[EDGE ? GRAY_W * GRAY_W : 1];
     __shared__ float s_dgx[EDGE ? DG_W * DG_W : 1], s_dgy[EDGE ? DG_W * DG_W : 1];
 
+    pdl_trigger();
+    pdl_wait();  // z-buffer of the preceding raster_kernel
     const int total = *total_tiles;
     const int tid = threadIdx.x;
     // pixel centre -> NDC: fx = xs*px + xo (nvdiffrast's xs = 2/W, xo = 1/W - 1), hoisted out of the pixel loop
@@ -829,9 +831,9 @@ static void launch_pixel(const SceneDev& S, const HypState* hyp, const int* tota
                          const unsigned long long* zbuf, float* partials, RenderOut out, ExtGrad ext, int num_sms, cudaStream_t st) {
     const int grid = pixel_grid(max_tiles, num_sms);
     if (S.tex4 && S.tex_filter == 1)
-        pixel_kernel<MODE, EDGE, true><<<grid, TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext);
+        launch_kernel(pdl_enabled(), pixel_kernel<MODE, EDGE, true>, dim3(grid), dim3(TILE_THREADS), 0, st, S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext);
     else
-        pixel_kernel<MODE, EDGE, false><<<grid, TILE_THREADS, 0, st>>>(S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext);
+        launch_kernel(pdl_enabled(), pixel_kernel<MODE, EDGE, false>, dim3(grid), dim3(TILE_THREADS), 0, st, S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext);
 }
 
 void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,

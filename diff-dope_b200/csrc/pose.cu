@@ -302,6 +302,8 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
                                                    float* __restrict__ pose_hist, float* __restrict__ loss_hist,
                                                    unsigned long long* __restrict__ zbuf, int* __restrict__ total_tiles,
                                                    unsigned int* __restrict__ arrive) {
+    pdl_trigger();
+    pdl_wait();  // partial sums of the preceding pixel_kernel
     const int b = blockIdx.y;
     if (blockIdx.x > 0) {
         if (!do_step) return;  // nothing was rasterised yet
@@ -393,9 +395,9 @@ void launch_iter(const SceneDev& S, const HypState* hyp_old, HypState* hyp_new, 
                  LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, const float* lr_sched, int it,
                  int do_step, int do_update, int do_pose, float* loss_table, float* grad_out, float* pose_hist,
                  float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, cudaStream_t st) {
-    iter_kernel<<<dim3(do_step ? 1 + CLEAR_CTAS : 1, B), ITER_THREADS, 0, st>>>(
-        S, hyp_old, hyp_new, partials, B, B_global, cfg, opt, quat, trans, lr_mult, lr_sched, it, do_step, do_update, do_pose,
-        loss_table, grad_out, pose_hist, loss_hist, zbuf, total_tiles, arrive);
+    launch_kernel(pdl_enabled(), iter_kernel, dim3(do_step ? 1 + CLEAR_CTAS : 1, B), dim3(ITER_THREADS), 0, st, S, hyp_old, hyp_new, partials, B,
+                  B_global, cfg, opt, quat, trans, lr_mult, lr_sched, it, do_step, do_update, do_pose, loss_table, grad_out, pose_hist,
+                  loss_hist, zbuf, total_tiles, arrive);
 }
 
 void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg, float* dmtx_out,

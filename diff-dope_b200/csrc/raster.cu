@@ -79,6 +79,8 @@ __device__ __forceinline__ void edge_setup32(int ax, int ay, int bx, int by, int
 
 __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, const HypState* __restrict__ hyp,
                                                                 unsigned long long* __restrict__ zbuf) {
+    pdl_trigger();
+    pdl_wait();  // hyp / z-buffer state of the preceding iter_kernel
     const int b = blockIdx.y;
     __shared__ float s_mvp[16];
     __shared__ int s_reg[4];
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
 }
 
 void launch_raster(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, cudaStream_t st) {
-    raster_kernel<<<dim3((S.T + RASTER_THREADS - 1) / RASTER_THREADS, B), RASTER_THREADS, 0, st>>>(S, hyp, zbuf);
+    launch_kernel(pdl_enabled(), raster_kernel, dim3((S.T + RASTER_THREADS - 1) / RASTER_THREADS, B), dim3(RASTER_THREADS), 0, st, S, hyp, zbuf);
 }
 
 }  // namespace ddope
