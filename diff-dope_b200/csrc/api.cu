@@ -264,6 +264,11 @@ extern "C" int ddope_scene_set_camera(ddope_scene* s, const float* proj16, int f
         s->dev.gt_rgb = s->dev.gt_depth = s->dev.gt_seg = nullptr;  // targets belong to the old frame size
     }
     s->dev.H = frame_h; s->dev.W = frame_w;
+    {   // nvdiffrast's pixel-centre mapping, in separately rounded float32 operations (same values as oracle/nvdr.py pixel_ndc)
+        volatile float w = (float)frame_w, h = (float)frame_h;
+        volatile float xs = 2.f / w, xo1 = 1.f / w, ys = 2.f / h, yo1 = 1.f / h;
+        s->dev.ndc_xs = xs; s->dev.ndc_xo = xo1 - 1.f; s->dev.ndc_ys = ys; s->dev.ndc_yo = yo1 - 1.f;
+    }
     s->have_camera = true;
     set_window(s, 0, 0, frame_h, frame_w);
     return 0;

@@ -48,6 +48,7 @@ struct SceneDev {
     int wy0, wx0, wh, ww;    // loss window
     int zy0, zx0, zh, zw;    // z-buffer region: window grown by 1 px, clipped to the frame
     float proj[16];
+    float ndc_xs, ndc_xo, ndc_ys, ndc_yo;  // pixel centre -> NDC: f = s*p + o with s = 2/W, o = 1/W - 1 (float32 ops, set_camera)
     float bbmin[3], bbmax[3];  // object-space AABB
 };
 

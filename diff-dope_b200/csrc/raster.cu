@@ -102,8 +102,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
     unsigned long long* zb = zbuf + (size_t)b * S.zh * S.zw;
-    const float xs = xdiv(2.f, (float)S.W), xo = xsub(xdiv(1.f, (float)S.W), 1.f);
-    const float ys = xdiv(2.f, (float)S.H), yo = xsub(xdiv(1.f, (float)S.H), 1.f);
+    const float xs = S.ndc_xs, xo = S.ndc_xo, ys = S.ndc_ys, yo = S.ndc_yo;
 
     TriRec* my = reinterpret_cast<TriRec*>(s_rec + threadIdx.x * REC_WORDS);
     int npx = 0;        // candidates of a small triangle

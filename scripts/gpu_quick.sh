@@ -13,3 +13,6 @@ echo "config 1 (B=1, 320 window, 50 iters) pdl / no pdl:" >> gpurun_out/${TAG}_k
 B=1 WIN=320 ITERS=50 timeout 300 python scripts/dev_time.py 2>&1 | grep "ms/iter" >> gpurun_out/${TAG}_kernels.log
 DDOPE_NO_PDL=1 B=1 WIN=320 ITERS=50 timeout 300 python scripts/dev_time.py 2>&1 | grep "ms/iter" >> gpurun_out/${TAG}_kernels.log
 tail -25 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_kernels.log
+for c in "4 128" "5 128" "3 128"; do set -- $c; CFG=$1 B=$2 ITERS=20 timeout 300 python scripts/dev_configs.py 2>&1 | tail -3 >> gpurun_out/${TAG}_configs.log; done
+NO_EDGE=1 CFG=5 B=128 ITERS=20 timeout 300 python scripts/dev_configs.py 2>&1 | tail -1 >> gpurun_out/${TAG}_configs.log
+cat gpurun_out/${TAG}_configs.log
