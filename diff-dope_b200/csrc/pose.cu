@@ -39,9 +39,8 @@ __device__ void canonical_mvp(const float* P, const float* M, float* out) {
 
 // Everything pixel/raster kernels need to know about one hypothesis, from its raw parameters (or an
 // explicit model matrix): q^, M, MVP, loss scales, loss ROI and its tile grid (tile_base is filled by
-// the scan that follows).
-__device__ void hyp_from_pose(const SceneDev& S, const float* qb, const float* tb, const float* mtx_b, float lr_b,
-                              int B_global, LossCfgDev cfg, int roi_mode, HypState& h) {
+// the scan that follows). Split in three so iter_kernel can spread the bounding-box corners over lanes.
+__device__ void hyp_pose_part(const SceneDev& S, const float* qb, const float* tb, const float* mtx_b, HypState& h) {
     if (mtx_b) {
         for (int k = 0; k < 16; k++) h.m[k] = mtx_b[k];
         h.qhat[0] = h.qhat[1] = h.qhat[2] = 0.f; h.qhat[3] = 1.f; h.qnorm = 1.f;
@@ -51,49 +50,70 @@ __device__ void hyp_from_pose(const SceneDev& S, const float* qb, const float* t
         canonical_pose(q, t, h.qhat, &h.qnorm, h.m);
     }
     canonical_mvp(S.proj, h.m, h.mvp);
+}
 
+// Screen position of corner c of the object-space AABB; false if it is behind the camera / absurdly far out
+// (the caller then falls back to the whole window). The ROI carries a 2 px safety margin: plain float math.
+__device__ __forceinline__ bool roi_corner(const SceneDev& S, const float* mvp, int c, float& sx, float& sy) {
+    const float px = (c & 1) ? S.bbmax[0] : S.bbmin[0];
+    const float py = (c & 2) ? S.bbmax[1] : S.bbmin[1];
+    const float pz = (c & 4) ? S.bbmax[2] : S.bbmin[2];
+    float cl[4];
+    xfm_exact(mvp, px, py, pz, cl);
+    if (!(cl[3] > 1e-6f)) return false;
+    const float iw = 1.f / cl[3];
+    sx = (cl[0] * iw * 0.5f + 0.5f) * (float)S.W;
+    sy = (cl[1] * iw * 0.5f + 0.5f) * (float)S.H;
+    return (fabsf(sx) < 1e6f) && (fabsf(sy) < 1e6f);
+}
+
+// ROI = (screen bbox of the AABB corners, grown) U (bbox of seg != 0), clipped to the window; tile grid.
+__device__ void hyp_roi_part(const SceneDev& S, bool full, float mnx, float mny, float mxx, float mxy, int roi_mode, HypState& h) {
     int x0 = S.wx0, y0 = S.wy0, x1 = S.wx0 + S.ww, y1 = S.wy0 + S.wh;  // window, exclusive end
-    if (roi_mode == 1) {
-        bool full = false;
-        float mnx = 1e30f, mny = 1e30f, mxx = -1e30f, mxy = -1e30f;
-        for (int c = 0; c < 8; c++) {
-            float px = (c & 1) ? S.bbmax[0] : S.bbmin[0];
-            float py = (c & 2) ? S.bbmax[1] : S.bbmin[1];
-            float pz = (c & 4) ? S.bbmax[2] : S.bbmin[2];
-            float cl[4];
-            xfm_exact(h.mvp, px, py, pz, cl);
-            if (!(cl[3] > 1e-6f)) { full = true; break; }
-            float sx = (cl[0] / cl[3] * 0.5f + 0.5f) * (float)S.W;
-            float sy = (cl[1] / cl[3] * 0.5f + 0.5f) * (float)S.H;
-            if (!(fabsf(sx) < 1e6f) || !(fabsf(sy) < 1e6f)) { full = true; break; }
-            mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx);
-            mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
-        }
-        if (!full) {
-            int ox0 = (int)floorf(mnx) - 2, ox1 = (int)ceilf(mxx) + 3;  // exclusive end
-            int oy0 = (int)floorf(mny) - 2, oy1 = (int)ceilf(mxy) + 3;
-            if (S.gt_seg != nullptr) {
-                int sx0 = S.seg_bbox[0], sy0 = S.seg_bbox[1], sx1 = S.seg_bbox[2], sy1 = S.seg_bbox[3];
-                if (sx0 <= sx1 && sy0 <= sy1) {
-                    ox0 = min(ox0, sx0); oy0 = min(oy0, sy0);
-                    ox1 = max(ox1, sx1 + 1); oy1 = max(oy1, sy1 + 1);
-                }
+    if (roi_mode == 1 && !full) {
+        int ox0 = (int)floorf(mnx) - 2, ox1 = (int)ceilf(mxx) + 3;  // exclusive end
+        int oy0 = (int)floorf(mny) - 2, oy1 = (int)ceilf(mxy) + 3;
+        if (S.gt_seg != nullptr) {
+            int sx0 = S.seg_bbox[0], sy0 = S.seg_bbox[1], sx1 = S.seg_bbox[2], sy1 = S.seg_bbox[3];
+            if (sx0 <= sx1 && sy0 <= sy1) {
+                ox0 = min(ox0, sx0); oy0 = min(oy0, sy0);
+                ox1 = max(ox1, sx1 + 1); oy1 = max(oy1, sy1 + 1);
             }
-            x0 = max(x0, ox0); y0 = max(y0, oy0);
-            x1 = min(x1, ox1); y1 = min(y1, oy1);
         }
+        x0 = max(x0, ox0); y0 = max(y0, oy0);
+        x1 = min(x1, ox1); y1 = min(y1, oy1);
     }
     if (x1 <= x0 || y1 <= y0) { x0 = x1 = S.wx0; y0 = y1 = S.wy0; }
     h.rx0 = x0; h.ry0 = y0; h.rx1 = x1; h.ry1 = y1;
     h.tiles_x = (x1 - x0 + TILE_W - 1) / TILE_W;
     h.tiles_y = (y1 - y0 + TILE_H - 1) / TILE_H;
-    double P = (double)S.wh * (double)S.ww;
-    double lr = (double)lr_b;
-    h.k_rgb = (float)((double)cfg.w_rgb * lr / ((double)B_global * P * 3.0));
-    h.k_depth = (float)((double)cfg.w_depth * lr / ((double)B_global * P));
-    h.k_mask = (float)((double)cfg.w_mask * lr / ((double)B_global * P * 3.0));
-    h.k_edge = (float)((double)cfg.w_edge * lr / ((double)B_global * P));
     h.tile_base = 0;
+}
+
+// d loss / d pixel value scales: w_k * lr_b / (B_global * P * C)
+__device__ void hyp_scales(const SceneDev& S, float lr_b, int B_global, LossCfgDev cfg, HypState& h) {
+    const double inv = (double)lr_b / ((double)B_global * ((double)S.wh * (double)S.ww));
+    h.k_rgb = (float)((double)cfg.w_rgb * inv / 3.0);
+    h.k_depth = (float)((double)cfg.w_depth * inv);
+    h.k_mask = (float)((double)cfg.w_mask * inv / 3.0);
+    h.k_edge = (float)((double)cfg.w_edge * inv);
+}
+
+__device__ void hyp_from_pose(const SceneDev& S, const float* qb, const float* tb, const float* mtx_b, float lr_b,
+                              int B_global, LossCfgDev cfg, int roi_mode, HypState& h) {
+    hyp_pose_part(S, qb, tb, mtx_b, h);
+    bool full = false;
+    float mnx = 1e30f, mny = 1e30f, mxx = -1e30f, mxy = -1e30f;
+    if (roi_mode == 1) {
+        for (int c = 0; c < 8; c++) {
+            float sx, sy;
+            if (!roi_corner(S, h.mvp, c, sx, sy)) { full = true; break; }
+            mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx);
+            mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
+        }
+    }
+    hyp_roi_part(S, full, mnx, mny, mxx, mxy, roi_mode, h);
+    hyp_scales(S, lr_b, B_global, cfg, h);
 }
 
 __global__ void __launch_bounds__(256) pose_kernel(SceneDev S, const float* __restrict__ quat,
@@ -347,10 +367,33 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
         __syncthreads();
     }
     if (!do_pose) return;
+    // next iteration's hypothesis state, built in shared memory: pose -> M, MVP by thread 0, the eight AABB corners
+    // by eight lanes, ROI + tile grid by lane 0; the loss scales do not change between iterations
+    __shared__ __align__(16) HypState s_n;
     if (threadIdx.x == 0) {
-        HypState h;
-        hyp_from_pose(S, s_theta, s_theta + 4, nullptr, lr_mult ? lr_mult[b] : 1.f, B_global, cfg, 1, h);
-        hyp_new[b] = h;
+        hyp_pose_part(S, s_theta, s_theta + 4, nullptr, s_n);
+        if (do_step) { s_n.k_rgb = s_h.k_rgb; s_n.k_depth = s_h.k_depth; s_n.k_mask = s_h.k_mask; s_n.k_edge = s_h.k_edge; }
+        else hyp_scales(S, lr_mult ? lr_mult[b] : 1.f, B_global, cfg, s_n);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float sx = 0.f, sy = 0.f;
+        bool ok = true;
+        if (lane < 8) ok = roi_corner(S, s_n.mvp, lane, sx, sy);
+        const bool full = __any_sync(0xffffffffu, !ok);
+        float mnx = (lane < 8) ? sx : 1e30f, mxx = (lane < 8) ? sx : -1e30f, mny = (lane < 8) ? sy : 1e30f, mxy = (lane < 8) ? sy : -1e30f;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+        if (lane == 0) hyp_roi_part(S, full, mnx, mny, mxx, mxy, 1, s_n);
+    }
+    __syncthreads();
+    {
+        constexpr int HW = sizeof(HypState) / 4;
+        if (threadIdx.x < HW) reinterpret_cast<unsigned int*>(&hyp_new[b])[threadIdx.x] = reinterpret_cast<const unsigned int*>(&s_n)[threadIdx.x];
     }
     // tile prefix over all hypotheses, by whichever CTA arrives last
     __threadfence();
