@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B per-kernel times of the default build and every diff-dope_b200/diffdope/_lib/alt_*.so
+# A/B per-kernel times of the default build and every diff-dope_b200/diffdope/_lib/alt_*.so (+ parity tests of the default build)
 TAG=${1:-ab}
 mkdir -p gpurun_out
 for i in 1 2 3; do
@@ -8,4 +8,6 @@ for alt in diff-dope_b200/diffdope/_lib/alt_*.so; do
   [ -f "$alt" ] && DDOPE_B200_LIB=$PWD/$alt ITERS=50 TAG=$(basename $alt) timeout 300 python scripts/dev_kernels.py >> gpurun_out/${TAG}_kernels.log 2>&1
 done
 done
-cat gpurun_out/${TAG}_kernels.log
+( time timeout 1200 python -m pytest tests -m gpu -q ) > gpurun_out/${TAG}_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
+tail -8 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_kernels.log
