@@ -38,6 +38,7 @@ struct ddope_scene {
     float* adam_state = nullptr;  // [B,14]
     int adam_cap = 0;
     int hyp_cur = 0;          // which half of `hyp` the current iteration reads
+    int cull_auto = 0;        // closed_mesh_orientation of the mesh
     float* vcol = nullptr;
     float4* tripos = nullptr;
     float4* tricol = nullptr;
@@ -150,6 +151,39 @@ static void build_opposites(const int32_t* tri, int T, std::vector<int>& opp) {
         }
 }
 
+// +1 / -1 if the mesh, after welding vertices with bit-identical positions (uv seams duplicate them), is a closed,
+// consistently oriented 2-manifold (every directed edge once, its reverse once) of positive / negative volume; else 0.
+// Same definition as oracle/nvdr.py closed_mesh_orientation.
+static int closed_mesh_orientation(const float* pos, int V, const int32_t* tri, int T) {
+    struct Key { uint32_t a, b, c; bool operator==(const Key& o) const { return a == o.a && b == o.b && c == o.c; } };
+    struct KeyHash { size_t operator()(const Key& k) const { return ((size_t)k.a * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.b * 0xC2B2AE3D27D4EB4Full) ^ ((size_t)k.c * 0x165667B19E3779F9ull); } };
+    std::unordered_map<Key, int, KeyHash> weld_of;
+    weld_of.reserve((size_t)V * 2);
+    std::vector<int> weld(V);
+    for (int v = 0; v < V; v++) {
+        Key k;
+        memcpy(&k.a, pos + 3 * v, 4); memcpy(&k.b, pos + 3 * v + 1, 4); memcpy(&k.c, pos + 3 * v + 2, 4);
+        auto it = weld_of.find(k);
+        if (it == weld_of.end()) it = weld_of.emplace(k, (int)weld_of.size()).first;
+        weld[v] = it->second;
+    }
+    std::unordered_map<uint64_t, int> edges;
+    edges.reserve((size_t)T * 6);
+    double vol = 0.0;
+    for (int t = 0; t < T; t++) {
+        const int v[3] = {weld[tri[3 * t]], weld[tri[3 * t + 1]], weld[tri[3 * t + 2]]};
+        if (v[0] == v[1] || v[1] == v[2] || v[2] == v[0]) return 0;
+        for (int i = 0; i < 3; i++)
+            if (++edges[((uint64_t)(uint32_t)v[i] << 32) | (uint32_t)v[(i + 1) % 3]] > 1) return 0;
+        const float* a = pos + 3 * tri[3 * t]; const float* b = pos + 3 * tri[3 * t + 1]; const float* c = pos + 3 * tri[3 * t + 2];
+        vol += (double)a[0] * ((double)b[1] * c[2] - (double)b[2] * c[1]) - (double)a[1] * ((double)b[0] * c[2] - (double)b[2] * c[0]) +
+               (double)a[2] * ((double)b[0] * c[1] - (double)b[1] * c[0]);
+    }
+    for (const auto& e : edges)
+        if (edges.find((e.first << 32) | (e.first >> 32)) == edges.end()) return 0;
+    return vol > 0.0 ? 1 : (vol < 0.0 ? -1 : 0);
+}
+
 extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, const int32_t* tri, int T,
                                   const float* uv, const float* tex, int tex_h, int tex_w, const float* vcol) {
     if (!out || !pos || !tri) return fail("ddope_scene_create: null pointer");
@@ -220,6 +254,8 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     SceneDev& d = s->dev;
     d.pos = s->pos; d.tri = s->tri; d.opp = s->opp; d.uv = s->uv; d.tex4 = s->tex4; d.vcol = s->vcol; d.tripos = s->tripos; d.tricol = s->tricol;
     d.V = V; d.T = T; d.tex_h = textured ? tex_h : 0; d.tex_w = textured ? tex_w : 0;
+    s->cull_auto = closed_mesh_orientation(pos, V, tri, T);
+    d.cull_sign = s->cull_auto;
     d.tex_levels = textured ? 1 : 0; d.tex_filter = DDOPE_TEX_LINEAR;
     for (int l = 0; l < MAX_MIP; l++) d.tex_off[l] = 0;
     d.gt_edge = nullptr;
@@ -331,6 +367,15 @@ extern "C" int ddope_scene_set_texture_filter(ddope_scene* s, int mode, int max_
     d.tex_filter = mode;
     return 0;
 }
+
+extern "C" int ddope_scene_set_culling(ddope_scene* s, int mode) {
+    if (!s) return fail("ddope_scene_set_culling: null scene");
+    if (mode != 0 && mode != 1) return fail("ddope_scene_set_culling: mode must be 0 (off) or 1 (auto)");
+    s->dev.cull_sign = mode ? s->cull_auto : 0;
+    return 0;
+}
+
+extern "C" int ddope_scene_mesh_orientation(const ddope_scene* s) { return s ? s->cull_auto : 0; }
 
 extern "C" int ddope_scene_set_optimizer(ddope_scene* s, const ddope_optim_cfg* cfg) {
     if (!s || !cfg) return fail("ddope_scene_set_optimizer: null pointer");

@@ -41,6 +41,8 @@ struct SceneDev {
     const float* gt_edge;   // [H,W] Sobel magnitude of the target's grey image, zero-padded at the loss window (edge loss) or null
     const int* seg_bbox;    // device int[4]: xmin,ymin,xmax,ymax of seg != 0 (inclusive); xmin > xmax if none
     int V, T, tex_h, tex_w;
+    int cull_sign;                   // +1 / -1: closed, consistently oriented mesh with positive / negative volume (back faces
+                                     // are skipped by the rasteriser); 0: open mesh or culling switched off
     int tex_levels, tex_filter;      // levels present in tex4; 0 = bilinear on level 0, 1 = trilinear over the chain
     unsigned int tex_off[MAX_MIP];   // texel offset of each level in tex4
     int seg_pix_stride, seg_ch_stride;
@@ -62,6 +64,8 @@ struct __align__(16) HypState {
     int rx0, ry0, rx1, ry1;        // loss ROI in frame pixels, [rx0,rx1) x [ry0,ry1)
     int tiles_x, tiles_y, tile_base;
     float k_edge;
+    int face;  // sign of the snapped window-space area of a front-facing triangle (0: rasterise both orientations)
+    int pad[3];
 };
 
 struct LossCfgDev {

@@ -50,6 +50,13 @@ __device__ void hyp_pose_part(const SceneDev& S, const float* qb, const float* t
         canonical_pose(q, t, h.qhat, &h.qnorm, h.m);
     }
     canonical_mvp(S.proj, h.m, h.mvp);
+    // front-face orientation in window space = mesh orientation x camera-to-window orientation x model-matrix orientation
+    const float* m = h.m;
+    const float detm = m[0] * (m[5] * m[10] - m[6] * m[9]) - m[1] * (m[4] * m[10] - m[6] * m[8]) + m[2] * (m[4] * m[9] - m[5] * m[8]);
+    const float detp = S.proj[0] * S.proj[5] - S.proj[1] * S.proj[4];
+    const int sm = (detm > 0.f) - (detm < 0.f), sp = (detp > 0.f) - (detp < 0.f);
+    h.face = S.cull_sign * sm * sp;
+    h.pad[0] = h.pad[1] = h.pad[2] = 0;
 }
 
 // Screen position of corner c of the object-space AABB; false if it is behind the camera / absurdly far out

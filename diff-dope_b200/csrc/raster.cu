@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
     pdl_wait();  // hyp / z-buffer state of the preceding iter_kernel
     const int b = blockIdx.y;
     __shared__ float s_mvp[16];
-    __shared__ int s_reg[4];
+    __shared__ int s_reg[5];
     __shared__ int s_rec[RASTER_THREADS * REC_WORDS];
     __shared__ int s_off[RASTER_THREADS];
     __shared__ int s_nlarge;
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
         s_reg[2] = max(h.ry0 - 1, S.zy0);
         s_reg[3] = min(h.ry1 + 1, S.zy0 + S.zh) - 1;
         if (h.rx1 <= h.rx0) { s_reg[0] = 1; s_reg[1] = 0; }
+        s_reg[4] = h.face;
         s_nlarge = 0;
     }
     __syncthreads();
@@ -128,7 +129,9 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
             X[1] = __float2int_rn(xmul(sx1, (float)SUBPIX)); Y[1] = __float2int_rn(xmul(sy1, (float)SUBPIX));
             X[2] = __float2int_rn(xmul(sx2, (float)SUBPIX)); Y[2] = __float2int_rn(xmul(sy2, (float)SUBPIX));
             const long long area2 = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(Y[1] - Y[0]) * (X[2] - X[0]);
-            if (area2 != 0) {
+            // back faces of a closed mesh cannot be the front-most surface: skipped (raster rule)
+            const int face = s_reg[4];
+            if (area2 != 0 && !(face != 0 && ((area2 > 0) != (face > 0)))) {
                 if (area2 < 0) {  // orientation-normalise (coverage only): swap v1 <-> v2
                     int tmp = X[1]; X[1] = X[2]; X[2] = tmp;
                     tmp = Y[1]; Y[1] = Y[2]; Y[2] = tmp;

@@ -73,6 +73,9 @@ def lib():
     L.ddope_scene_set_target.argtypes = [vp, vp, vp, vp, ci, vp]
     L.ddope_scene_set_window.argtypes = [vp, ci, ci, ci, ci]
     L.ddope_scene_set_texture_filter.argtypes = [vp, ci, ci]
+    L.ddope_scene_set_culling.argtypes = [vp, ci]
+    L.ddope_scene_mesh_orientation.argtypes = [vp]
+    L.ddope_scene_mesh_orientation.restype = ci
     L.ddope_scene_set_optimizer.argtypes = [vp, ctypes.POINTER(OptimCfg)]
     L.ddope_render.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
     L.ddope_render_mtx.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
@@ -86,6 +89,7 @@ def lib():
         "ddope_scene_destroy", "ddope_scene_set_camera", "ddope_scene_set_target", "ddope_scene_set_window",
         "ddope_render", "ddope_render_mtx", "ddope_render_bwd", "ddope_loss_grad", "ddope_optimize",
         "ddope_profile_begin", "ddope_profile_end", "ddope_scene_set_texture_filter", "ddope_scene_set_optimizer",
+        "ddope_scene_set_culling",
     ):
         getattr(L, name).restype = ci
     if L.ddope_abi_version() != 2:
@@ -183,6 +187,14 @@ class NativeScene:
         if mode not in modes:
             raise RuntimeError("ddope_b200: unknown texture filter %r" % (mode,))
         _check(lib().ddope_scene_set_texture_filter(self._h, modes[mode], int(max_levels)))
+
+    def set_culling(self, auto=True):
+        """Back-face culling of closed, consistently oriented meshes (default on); False rasterises every triangle."""
+        _check(lib().ddope_scene_set_culling(self._h, 1 if auto else 0))
+
+    def mesh_orientation(self):
+        """+1 / -1: closed mesh of positive / negative volume (culling applies); 0: open or inconsistent mesh."""
+        return int(lib().ddope_scene_mesh_orientation(self._h))
 
     def set_optimizer(self, kind="sgd", beta1=0.9, beta2=0.999, eps=1e-8, step0=0):
         """'sgd' (reference, default) or 'adam' (extension; torch.optim.Adam's algebra)."""

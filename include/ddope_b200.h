@@ -142,6 +142,15 @@ int ddope_scene_set_target(ddope_scene* s, const float* rgb_dev, const float* de
  * ground truth" (the reference always uses the full frame; default after set_camera). */
 int ddope_scene_set_window(ddope_scene* s, int y0, int x0, int h, int w);
 
+/* Back-face culling. mode 1 (default) = automatic: if the mesh, after welding vertices with bit-identical
+ * positions, is a closed and consistently oriented 2-manifold, triangles facing away from the camera are not
+ * rasterised. They can never be the front-most surface, so coverage is unchanged; compared with the reference's
+ * GL context (no culling, diffdope/diffdope.py:1312) the winning triangle can differ only where a back and a front
+ * face tie in depth within float rounding on a silhouette. mode 0 = rasterise every triangle. Open or inconsistently
+ * oriented meshes are never culled. ddope_scene_mesh_orientation: +1 / -1 (closed, positive / negative volume) or 0. */
+int ddope_scene_set_culling(ddope_scene* s, int mode);
+int ddope_scene_mesh_orientation(const ddope_scene* s);
+
 /* Extensions (defaults = reference behaviour). max_levels <= 0: the full chain down to 1x1. */
 int ddope_scene_set_texture_filter(ddope_scene* s, int mode, int max_levels);
 int ddope_scene_set_optimizer(ddope_scene* s, const ddope_optim_cfg* cfg);

@@ -207,8 +207,46 @@ def pixel_ndc(px, py, W, H):
     return xs * px.astype(F) + xo, ys * py.astype(F) + yo
 
 
-def rasterize(clip, tri, H, W):
+def closed_mesh_orientation(pos, tri):
+    """+1 / -1 if the mesh, after welding vertices with bit-identical positions (uv seams duplicate them), is a
+    closed, consistently oriented 2-manifold -- every directed edge occurs exactly once and so does its reverse --
+    with positive / negative enclosed volume; 0 otherwise (no culling possible)."""
+    pos = np.ascontiguousarray(pos, dtype=F)
+    tri = np.asarray(tri, dtype=np.int64)
+    _, weld = np.unique(pos.view(np.uint32).reshape(-1, 3), axis=0, return_inverse=True)
+    t = weld.reshape(-1)[tri]
+    if ((t[:, 0] == t[:, 1]) | (t[:, 1] == t[:, 2]) | (t[:, 2] == t[:, 0])).any():
+        return 0
+    a = np.concatenate([t[:, 0], t[:, 1], t[:, 2]])
+    b = np.concatenate([t[:, 1], t[:, 2], t[:, 0]])
+    n = int(weld.max()) + 1
+    fwd = a * n + b
+    if np.unique(fwd).size != fwd.size:
+        return 0
+    if not np.array_equal(np.sort(fwd), np.sort(b * n + a)):
+        return 0
+    p = pos.astype(np.float64)
+    vol = np.einsum("ij,ij->i", p[tri[:, 0]], np.cross(p[tri[:, 1]], p[tri[:, 2]])).sum()
+    return int(np.sign(vol))
+
+
+def face_signs(cull_sign, proj, M):
+    """Sign of the snapped window-space area of a FRONT-facing triangle per batch entry: mesh orientation x
+    orientation of the camera-to-window map x orientation of the model matrix (0 = do not cull)."""
+    P = np.asarray(proj, dtype=np.float64)
+    M = np.asarray(M, dtype=np.float64)
+    dp = np.sign(P[0, 0] * P[1, 1] - P[0, 1] * P[1, 0])
+    dm = np.sign(np.linalg.det(M[:, :3, :3]))
+    return (cull_sign * dp * dm).astype(np.int64)
+
+
+def rasterize(clip, tri, H, W, face_sign=None):
     """Restates `dr.rasterize(glctx, pos_clip, tri, [H,W])` (`diffdope/diffdope.py:198-200`).
+
+    face_sign [B] (optional, from `face_signs`): where non-zero, triangles whose snapped area has the other sign
+    are back faces of a closed mesh and are skipped. They can never be the front-most surface, so coverage is
+    unchanged; the winner can differ from a no-culling rasteriser only where a back and a front face tie in depth
+    within float rounding on a silhouette (the raster rule).
 
     clip [B,V,4] float32, tri [T,3] int. Returns rast_out [B,H,W,4] float32 =
     (u, v, z/w, tri_id+1), all-zero at background. The pixel-derivative output
@@ -224,6 +262,8 @@ def rasterize(clip, tri, H, W):
         X, Y, ok = snap_vertices(clip[b], W, H)
         ev, area2 = _edge_fns(X, Y, tri)
         tri_ok = ok[tri[:, 0]] & ok[tri[:, 1]] & ok[tri[:, 2]] & (area2 != 0)
+        if face_sign is not None and face_sign[b] != 0:
+            tri_ok &= np.sign(area2) == face_sign[b]
         xmin = np.minimum(np.minimum(ev[0], ev[2]), ev[4])
         xmax = np.maximum(np.maximum(ev[0], ev[2]), ev[4])
         ymin = np.minimum(np.minimum(ev[1], ev[3]), ev[5])

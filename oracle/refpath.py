@@ -61,8 +61,8 @@ def xfm_points(points, matrix):
 
 class _Rasterize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pos_clip, tri, H, W):
-        rast = nvdr.rasterize(pos_clip.detach().numpy(), tri, H, W)
+    def forward(ctx, pos_clip, tri, H, W, face_sign=None):
+        rast = nvdr.rasterize(pos_clip.detach().numpy(), tri, H, W, face_sign)
         ctx.tri, ctx.H, ctx.W = tri, H, W
         r = torch.from_numpy(rast)
         ctx.save_for_backward(pos_clip, r)
@@ -72,7 +72,7 @@ class _Rasterize(torch.autograd.Function):
     def backward(ctx, d_rast):
         pos_clip, rast = ctx.saved_tensors
         g = nvdr.rasterize_grad(pos_clip.detach().numpy(), ctx.tri, rast.numpy(), d_rast.numpy(), ctx.H, ctx.W)
-        return torch.from_numpy(g), None, None, None
+        return torch.from_numpy(g), None, None, None, None
 
 
 class _Interpolate(torch.autograd.Function):
@@ -176,6 +176,8 @@ class Mesh:
         self.tex = None if tex is None else np.ascontiguousarray(tex, dtype=F)
         self.vtx_color = None if vtx_color is None else np.ascontiguousarray(vtx_color, dtype=F)
         self.opp = nvdr.build_edge_opposites(self.tri)
+        self.cull_sign = nvdr.closed_mesh_orientation(self.pos, self.tri)  # 0: open / inconsistent mesh, nothing is culled
+        self.cull = True  # back-face culling of closed meshes (the raster rule); False = rasterise every triangle
         self.texture_filter = "linear"  # or "linear-mipmap-linear" (extension)
         self._mips = None
 
@@ -206,7 +208,8 @@ def render(mesh, proj, quat_raw, trans, H, W):
     pos = torch.from_numpy(mesh.pos)
     pos_b = pos[None].expand(B, -1, -1)
     pos_clip = xfm_points(pos_b, mvp)
-    rast = _Rasterize.apply(pos_clip, mesh.tri, H, W)
+    face = nvdr.face_signs(mesh.cull_sign if mesh.cull else 0, proj, M_c)
+    rast = _Rasterize.apply(pos_clip, mesh.tri, H, W, face)
 
     posw = torch.cat([pos, torch.ones(pos.shape[0], 1)], dim=1)
     gb_pos = _Interpolate.apply(posw, rast, mesh.tri)

@@ -321,3 +321,36 @@ def test_full_size_properties():
     total = l1.sum(-1)
     assert (total[-1] < total[0]).float().mean().item() > 0.9, "the loss must go down for almost every hypothesis"
     assert ex.sc.last_launch_count() == 3 * iters + 1  # prologue + (raster, pixel, iter) per iteration
+
+
+def test_backface_culling_rule(ex_half):
+    """The library detects the closed example mesh (uv-seam duplicates welded), culls back faces by default, and
+    the result equals the no-culling render: identical coverage, identical winners in these views."""
+    ex = ex_half
+    assert ex.sc.mesh_orientation() == 1 and ex.oracle_mesh().cull_sign == 1
+    B = 4
+    qs, ts = su.perturbed_poses(ex.q, ex.t, B, rot_deg=25.0)
+    qd, td = torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda()
+    on = ex.sc.render(qd, td, want=("rast", "rgb", "mask"))
+    try:
+        ex.sc.set_culling(False)
+        off = ex.sc.render(qd, td, want=("rast", "rgb", "mask"))
+    finally:
+        ex.sc.set_culling(True)
+    assert torch.equal(on["rast"][..., 3] > 0, off["rast"][..., 3] > 0)
+    assert torch.equal(on["mask"], off["mask"])
+    assert float((on["rast"][..., 3] != off["rast"][..., 3]).float().mean()) < 1e-4
+    # open mesh (one triangle removed): nothing is culled, both orientations rasterise
+    n = ex.n
+    sc2 = n.NativeScene(ex.arr["pos"], ex.arr["tri"][:-1], ex.arr["uv"], ex.arr["tex"])
+    assert sc2.mesh_orientation() == 0
+    # a mirrored model matrix: the other orientation becomes the front, coverage still equals the unculled render
+    mtx = on_m = ex.sc.render(qd[:1], td[:1], want=("mtx",))["mtx"].clone()
+    mtx[:, :3, 0] *= -1.0
+    a = ex.sc.render_mtx(mtx)
+    try:
+        ex.sc.set_culling(False)
+        b = ex.sc.render_mtx(mtx)
+    finally:
+        ex.sc.set_culling(True)
+    assert (a[3][..., 3] > 0).sum() > 1000 and torch.equal(a[3][..., 3] > 0, b[3][..., 3] > 0)

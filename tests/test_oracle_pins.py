@@ -394,3 +394,37 @@ def test_ext_adam_oracle_first_step_is_lr():
     o = refpath.run_optimization(mesh, P, q0, t0, gt, np.ones(1, np.float32), losses, hyper, H, W)
     lr0 = refpath.lr_schedule(0, 1, 0.01, 0.5)
     assert np.allclose(np.abs(o["poses"][1] - o["poses"][0]), lr0, rtol=1e-3)
+
+
+def test_closed_mesh_detection_and_culling_preserves_coverage():
+    """Raster rule: back faces of a closed, consistently oriented mesh are skipped. Coverage must not change,
+    and the winner may differ from the no-culling render only on silhouette ties (none in these views)."""
+    v, f, col = _cube()
+    assert nvdr.closed_mesh_orientation(v, f) == 1
+    assert nvdr.closed_mesh_orientation(v, f[:, ::-1]) == -1          # inside-out
+    assert nvdr.closed_mesh_orientation(v, f[:-1]) == 0               # a hole
+    g = f.copy()
+    g[3] = g[3, ::-1]
+    assert nvdr.closed_mesh_orientation(v, g) == 0                    # one flipped triangle
+    # duplicated seam vertices (same position, different index) still weld into a closed surface
+    v2 = np.concatenate([v, v[:1]])
+    f2 = f.copy()
+    f2[0, 0] = 8
+    assert nvdr.closed_mesh_orientation(v2, f2) == 1
+    arr = su.example_mesh_arrays()
+    assert nvdr.closed_mesh_orientation(arr["pos"], arr["tri"]) == 1  # 2548 index-level seam edges, closed after welding
+    mesh = refpath.Mesh(arr["pos"], arr["tri"], arr["uv"], arr["tex"])
+    q, t = su.example_pose()
+    qs, ts = su.perturbed_poses(q, t, 4, rot_deg=25.0)
+    P = su.projection()
+    H, W = 135, 240
+    r1 = refpath.render(mesh, P, torch.from_numpy(qs), torch.from_numpy(ts), H, W)["rast_out"].numpy()
+    mesh.cull = False
+    r0 = refpath.render(mesh, P, torch.from_numpy(qs), torch.from_numpy(ts), H, W)["rast_out"].numpy()
+    assert (r0[..., 3] > 0).sum() > 1000
+    assert np.array_equal(r0[..., 3] > 0, r1[..., 3] > 0)
+    assert (r0[..., 3] != r1[..., 3]).mean() < 1e-4
+    # a mirrored model matrix flips which orientation is the front
+    M = np.eye(4)[None].repeat(2, 0)
+    M[1, 0, 0] = -1
+    assert list(nvdr.face_signs(1, P, M)) == [1, -1]
