@@ -61,7 +61,14 @@ struct ddope_scene {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;  // (start, stop) per launch
     std::vector<int> prof_class;           // kernel class of each pair
-    unsigned int* arrive = nullptr;        // CTA arrival counter of iter_kernel's last-block scan
+    unsigned int* arrive = nullptr;        // CTA arrival counters of iter_kernel's last-block scan, one per part
+    // ddope_optimize / ddope_loss_grad split the hypotheses into up to MAX_PARTS contiguous parts that run on internal
+    // streams forked from (and joined back into) the caller's stream: the issue-bound raster kernel of one part overlaps
+    // the latency-bound pixel kernel of the other (measured: 158 -> 149 us per iteration at 64 hypotheses).
+    static constexpr int MAX_PARTS = 2;
+    cudaStream_t part_stream[MAX_PARTS] = {nullptr, nullptr};
+    cudaEvent_t part_done[MAX_PARTS] = {nullptr, nullptr};
+    cudaEvent_t fork_event = nullptr;
     std::vector<float> sched_host;         // staging of the per-iteration scalars (must outlive the async copy)
 };
 
@@ -247,9 +254,9 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     CK(cudaMalloc(&s->seg_bbox, sizeof(int) * 4));
     int init_bbox[4] = {1 << 30, 1 << 30, -1, -1};
     CK(cudaMemcpy(s->seg_bbox, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&s->total_tiles, sizeof(int) * 2));  // [0] tile count, [1] pixel kernel work counter
-    CK(cudaMalloc(&s->arrive, sizeof(unsigned int)));
-    CK(cudaMemset(s->arrive, 0, sizeof(unsigned int)));
+    CK(cudaMalloc(&s->total_tiles, sizeof(int) * 2 * ddope_scene::MAX_PARTS));  // per part: [0] tile count, [1] pixel kernel work counter
+    CK(cudaMalloc(&s->arrive, sizeof(unsigned int) * ddope_scene::MAX_PARTS));
+    CK(cudaMemset(s->arrive, 0, sizeof(unsigned int) * ddope_scene::MAX_PARTS));
 
     SceneDev& d = s->dev;
     d.pos = s->pos; d.tri = s->tri; d.opp = s->opp; d.uv = s->uv; d.tex4 = s->tex4; d.vcol = s->vcol; d.tripos = s->tripos; d.tricol = s->tricol;
@@ -279,6 +286,11 @@ extern "C" int ddope_scene_destroy(ddope_scene* s) {
     cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex4); cudaFree(s->vcol); cudaFree(s->gt_edge); cudaFree(s->adam_state); cudaFree(s->tripos); cudaFree(s->tricol);
     cudaFree(s->seg_bbox); cudaFree(s->total_tiles); cudaFree(s->hyp); cudaFree(s->zbuf); cudaFree(s->partials);
     cudaFree(s->lr_sched); cudaFree(s->xfm_scratch); cudaFree(s->arrive);
+    for (int p = 0; p < ddope_scene::MAX_PARTS; p++) {
+        if (s->part_stream[p]) cudaStreamDestroy(s->part_stream[p]);
+        if (s->part_done[p]) cudaEventDestroy(s->part_done[p]);
+    }
+    if (s->fork_event) cudaEventDestroy(s->fork_event);
     delete s;
     return 0;
 }
@@ -549,37 +561,100 @@ static OptimDev optim_dev(const ddope_scene* s, int n_iters) {
     return o;
 }
 
+// One contiguous part of the hypotheses of a call: offset views into the shared buffers + the stream it runs on.
+struct Part {
+    int b0, B;               // first hypothesis, count
+    cudaStream_t st;
+    int* total_tiles;        // this part's [tile count, work counter]
+    unsigned int* arrive;
+    float* partials;         // this part's tile rows start at index 0 here
+    unsigned long long* zbuf;
+};
+
+static size_t tiles_per_hyp(const ddope_scene* s) {
+    const SceneDev& d = s->dev;
+    return (size_t)((d.ww + TILE_W - 1) / TILE_W) * ((d.wh + TILE_H - 1) / TILE_H);
+}
+
+// Split B hypotheses into parts and fork the internal streams from the caller's stream.
+static int fork_parts(ddope_scene* s, int B, cudaStream_t st, Part* parts, int* n_parts) {
+    static const int min_split = [] { const char* e = getenv("DDOPE_SPLIT_MIN_B"); return e ? atoi(e) : 32; }();
+    int n = (!s->profiling && min_split > 0 && B >= min_split) ? ddope_scene::MAX_PARTS : 1;
+    const int per = (B + n - 1) / n;
+    for (int p = 0; p < n; p++) {
+        Part& P = parts[p];
+        P.b0 = p * per;
+        P.B = (P.b0 + per <= B) ? per : B - P.b0;
+        P.total_tiles = s->total_tiles + 2 * p;
+        P.arrive = s->arrive + p;
+        P.partials = s->partials + (size_t)P.b0 * tiles_per_hyp(s) * NACC;
+        P.zbuf = s->zbuf + (size_t)P.b0 * s->dev.zh * s->dev.zw;
+        P.st = st;
+    }
+    if (n > 1) {
+        if (!s->fork_event) CK(cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming));
+        CK(cudaEventRecord(s->fork_event, st));
+        for (int p = 0; p < n; p++) {
+            if (!s->part_stream[p]) CK(cudaStreamCreateWithFlags(&s->part_stream[p], cudaStreamNonBlocking));
+            if (!s->part_done[p]) CK(cudaEventCreateWithFlags(&s->part_done[p], cudaEventDisableTiming));
+            CK(cudaStreamWaitEvent(s->part_stream[p], s->fork_event, 0));
+            parts[p].st = s->part_stream[p];
+        }
+    }
+    *n_parts = n;
+    return 0;
+}
+
+static int join_parts(ddope_scene* s, cudaStream_t st, const Part* parts, int n_parts) {
+    if (n_parts <= 1) return 0;
+    for (int p = 0; p < n_parts; p++) {
+        CK(cudaEventRecord(s->part_done[p], parts[p].st));
+        CK(cudaStreamWaitEvent(st, s->part_done[p], 0));
+    }
+    return 0;
+}
+
+static int max_tiles_of(const ddope_scene* s, int B) {
+    const size_t t = tiles_per_hyp(s) * (size_t)B;
+    return t > 0x7fffffffull ? 0x7fffffff : (int)t;
+}
+
 // [pose + tile prefix] of the first iteration
-static void enqueue_prologue(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
-                             LossCfgDev cfg, OptimDev opt, cudaStream_t st) {
-    ProfMark m(s, st, K_ITER);
-    s->hyp_cur = 0;
-    launch_iter(s->dev, s->hyp, s->hyp, s->partials, B, B_global, cfg, opt, quat, trans, lr_mult, s->lr_sched, 0, 0, 0, 1, nullptr,
-                nullptr, nullptr, nullptr, s->zbuf, s->total_tiles, s->arrive, st);
+static void enqueue_prologue(ddope_scene* s, const Part& P, float* quat, float* trans, const float* lr_mult, int B_global,
+                             LossCfgDev cfg, OptimDev opt) {
+    ProfMark m(s, P.st, K_ITER);
+    HypState* h = s->hyp + P.b0;
+    launch_iter(s->dev, h, h, P.partials, P.B, B_global, P.B, cfg, opt, quat + 4 * (size_t)P.b0, trans + 3 * (size_t)P.b0,
+                lr_mult ? lr_mult + P.b0 : nullptr, s->lr_sched, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr, P.zbuf, P.total_tiles,
+                P.arrive, P.st);
     s->launches += 1;
 }
 
 // raster + pixel of iteration `it`, then one launch that finishes it (step, z-buffer restore) and, if more
-// follow, sets up the next one
-static void enqueue_iteration(ddope_scene* s, float* quat, float* trans, const float* lr_mult, int B, int B_global,
-                              LossCfgDev cfg, OptimDev opt, int it, int do_update, int more, float* loss_table, float* grad,
-                              float* pose_hist, float* loss_hist, cudaStream_t st) {
-    HypState* cur = s->hyp + (size_t)s->hyp_cur * s->hyp_cap;
-    HypState* nxt = s->hyp + (size_t)(s->hyp_cur ^ 1) * s->hyp_cap;
+// follow, sets up the next one. hyp_cur (which half of `hyp` is current) is toggled by the caller once per iteration.
+static void enqueue_iteration(ddope_scene* s, const Part& P, float* quat, float* trans, const float* lr_mult, int B_global,
+                              int B_hist, LossCfgDev cfg, OptimDev opt, int it, int do_update, int more, float* loss_table,
+                              float* grad, float* pose_hist, float* loss_hist) {
+    HypState* cur = s->hyp + (size_t)s->hyp_cur * s->hyp_cap + P.b0;
+    HypState* nxt = s->hyp + (size_t)(s->hyp_cur ^ 1) * s->hyp_cap + P.b0;
     {
-        ProfMark m(s, st, K_RASTER);
-        launch_raster(s->dev, cur, B, s->zbuf, st);
+        ProfMark m(s, P.st, K_RASTER);
+        launch_raster(s->dev, cur, P.B, P.zbuf, P.st);
     }
     {
-        ProfMark m(s, st, K_PIXEL);
-        launch_pixel_loss(s->dev, cur, s->total_tiles, B, max_tiles(s, B), cfg, s->zbuf, s->partials, s->num_sms, st);
+        ProfMark m(s, P.st, K_PIXEL);
+        launch_pixel_loss(s->dev, cur, P.total_tiles, P.B, max_tiles_of(s, P.B), cfg, P.zbuf, P.partials, s->num_sms, P.st);
     }
     {
-        ProfMark m(s, st, K_ITER);
-        launch_iter(s->dev, cur, nxt, s->partials, B, B_global, cfg, opt, quat, trans, lr_mult, s->lr_sched, it, 1, do_update, more,
-                    loss_table, grad, pose_hist, loss_hist, s->zbuf, s->total_tiles, s->arrive, st);
+        ProfMark m(s, P.st, K_ITER);
+        OptimDev o = opt;
+        if (o.state) o.state += 14 * (size_t)P.b0;
+        launch_iter(s->dev, cur, nxt, P.partials, P.B, B_global, B_hist, cfg, o, quat + 4 * (size_t)P.b0, trans + 3 * (size_t)P.b0,
+                    lr_mult ? lr_mult + P.b0 : nullptr, s->lr_sched, it, 1, do_update, more,
+                    loss_table ? loss_table + NLOSS * (size_t)P.b0 : nullptr, grad ? grad + 7 * (size_t)P.b0 : nullptr,
+                    pose_hist ? pose_hist + 7 * (size_t)P.b0 : nullptr, loss_hist ? loss_hist + NLOSS * (size_t)P.b0 : nullptr, P.zbuf,
+                    P.total_tiles, P.arrive, P.st);
     }
-    s->hyp_cur ^= 1;
     s->launches += 3;
 }
 
@@ -594,9 +669,16 @@ extern "C" int ddope_loss_grad(ddope_scene* s, const float* quat, const float* t
     if (int r = prepare_edge(s, cfg, st)) return r;
     s->launches = 0;
     OptimDev opt = {0, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr};
-    enqueue_prologue(s, const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B, B_global, to_dev(cfg), opt, st);
-    enqueue_iteration(s, const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B, B_global, to_dev(cfg), opt, 0, 0, 0,
-                      loss_table, grad, nullptr, nullptr, st);
+    Part parts[ddope_scene::MAX_PARTS];
+    int n_parts = 1;
+    if (int r = fork_parts(s, B, st, parts, &n_parts)) return r;
+    s->hyp_cur = 0;
+    for (int p = 0; p < n_parts; p++) {
+        enqueue_prologue(s, parts[p], const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B_global, to_dev(cfg), opt);
+        enqueue_iteration(s, parts[p], const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B_global, B, to_dev(cfg), opt, 0, 0,
+                          0, loss_table, grad, nullptr, nullptr);
+    }
+    if (int r = join_parts(s, st, parts, n_parts)) return r;
     CK(cudaGetLastError());
     return 0;
 }
@@ -641,10 +723,18 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     LossCfgDev c = to_dev(cfg);
     OptimDev opt = optim_dev(s, n_iters);
     s->launches = 0;
-    enqueue_prologue(s, quat, trans, lr_mult, B, B_global, c, opt, st);
-    for (int it = 0; it < n_iters; it++)
-        enqueue_iteration(s, quat, trans, lr_mult, B, B_global, c, opt, it, 1, it + 1 < n_iters, nullptr, nullptr, pose_hist,
-                          loss_hist, st);
+    Part parts[ddope_scene::MAX_PARTS];
+    int n_parts = 1;
+    if (int r = fork_parts(s, B, st, parts, &n_parts)) return r;
+    s->hyp_cur = 0;
+    for (int p = 0; p < n_parts; p++) enqueue_prologue(s, parts[p], quat, trans, lr_mult, B_global, c, opt);
+    for (int it = 0; it < n_iters; it++) {
+        for (int p = 0; p < n_parts; p++)
+            enqueue_iteration(s, parts[p], quat, trans, lr_mult, B_global, B, c, opt, it, 1, it + 1 < n_iters, nullptr, nullptr,
+                              pose_hist, loss_hist);
+        s->hyp_cur ^= 1;
+    }
+    if (int r = join_parts(s, st, parts, n_parts)) return r;
     CK(cudaGetLastError());
     return 0;
 }

@@ -4,6 +4,8 @@
 // mask + silhouette antialias, the three masked L1 losses, and their analytic backward accumulated
 // straight into dL/dMVP (rows x,y,w) and dL/dM (row z) -- no [B,H,W,*] intermediate and no [B,V,4]
 // vertex-gradient buffer ever exists. A persistent grid walks (hypothesis, tile) work items.
+#include <cstdlib>
+
 #include "ddope_launch.h"
 
 namespace ddope {
@@ -820,7 +822,8 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
 }
 
 static int pixel_grid(int max_tiles, int num_sms) {
-    int g = num_sms * 4;
+    static const int per_sm = [] { const char* e = getenv("DDOPE_PIXEL_CTAS_PER_SM"); int v = e ? atoi(e) : 4; return v >= 1 && v <= 8 ? v : 4; }();
+    int g = num_sms * per_sm;
     if (g > max_tiles) g = max_tiles;
     return g < 1 ? 1 : g;
 }

@@ -321,7 +321,7 @@ constexpr int CLEAR_CTAS = 3;  // CTAs per hypothesis that restore the z-buffer 
 // invariant is "all EMPTY between iterations"; hyp_old / hyp_new alternate so nothing is read after it is rewritten.
 __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const HypState* __restrict__ hyp_old,
                                                    HypState* __restrict__ hyp_new,
-                                                   const float* __restrict__ partials, int B, int B_global,
+                                                   const float* __restrict__ partials, int B, int B_global, int B_hist,
                                                    LossCfgDev cfg, OptimDev opt, float* __restrict__ quat,
                                                    float* __restrict__ trans, const float* __restrict__ lr_mult,
                                                    const float* __restrict__ lr_sched, int it, int do_step, int do_update,
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
         __syncthreads();
         reduce_tile_partials(s_h, partials, s_sum);
         if (threadIdx.x == 0)
-            step_from_sums(S, s_h, s_sum, b, B, cfg, opt, s_theta, quat, trans, lr_sched, it, do_update, loss_table, grad_out,
+            step_from_sums(S, s_h, s_sum, b, B_hist, cfg, opt, s_theta, quat, trans, lr_sched, it, do_update, loss_table, grad_out,
                            pose_hist, loss_hist, nullptr);
     } else {
         __syncthreads();
@@ -442,11 +442,11 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
 }
 
 void launch_iter(const SceneDev& S, const HypState* hyp_old, HypState* hyp_new, const float* partials, int B, int B_global,
-                 LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, const float* lr_sched, int it,
+                 int B_hist, LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, const float* lr_sched, int it,
                  int do_step, int do_update, int do_pose, float* loss_table, float* grad_out, float* pose_hist,
                  float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, cudaStream_t st) {
     launch_kernel(pdl_enabled(), iter_kernel, dim3(do_step ? 1 + CLEAR_CTAS : 1, B), dim3(ITER_THREADS), 0, st, S, hyp_old, hyp_new, partials, B,
-                  B_global, cfg, opt, quat, trans, lr_mult, lr_sched, it, do_step, do_update, do_pose, loss_table, grad_out, pose_hist,
+                  B_global, B_hist, cfg, opt, quat, trans, lr_mult, lr_sched, it, do_step, do_update, do_pose, loss_table, grad_out, pose_hist,
                   loss_hist, zbuf, total_tiles, arrive);
 }
 
