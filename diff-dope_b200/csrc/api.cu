@@ -65,9 +65,9 @@ struct ddope_scene {
     // ddope_optimize / ddope_loss_grad split the hypotheses into up to MAX_PARTS contiguous parts that run on internal
     // streams forked from (and joined back into) the caller's stream: the issue-bound raster kernel of one part overlaps
     // the latency-bound pixel kernel of the other (measured: 158 -> 149 us per iteration at 64 hypotheses).
-    static constexpr int MAX_PARTS = 2;
-    cudaStream_t part_stream[MAX_PARTS] = {nullptr, nullptr};
-    cudaEvent_t part_done[MAX_PARTS] = {nullptr, nullptr};
+    static constexpr int MAX_PARTS = 4;
+    cudaStream_t part_stream[MAX_PARTS] = {};
+    cudaEvent_t part_done[MAX_PARTS] = {};
     cudaEvent_t fork_event = nullptr;
     std::vector<float> sched_host;         // staging of the per-iteration scalars (must outlive the async copy)
 };
@@ -578,8 +578,14 @@ static size_t tiles_per_hyp(const ddope_scene* s) {
 
 // Split B hypotheses into parts and fork the internal streams from the caller's stream.
 static int fork_parts(ddope_scene* s, int B, cudaStream_t st, Part* parts, int* n_parts) {
-    static const int min_split = [] { const char* e = getenv("DDOPE_SPLIT_MIN_B"); return e ? atoi(e) : 32; }();
-    int n = (!s->profiling && min_split > 0 && B >= min_split) ? ddope_scene::MAX_PARTS : 1;
+    // measured on B200 (bench workload, us per iteration): B=16: 62 -> 52 (2 parts); B=32: 95 -> 80 (2); B=64: 158 -> 141 (2),
+    // 136 (3), 138 (4); B=128: 296 -> 277 (2), 269 (4). DDOPE_PARTS overrides (1 = no split).
+    static const int forced = [] { const char* e = getenv("DDOPE_PARTS"); return e ? atoi(e) : 0; }();
+    int n = B < 8 ? 1 : (B < 48 ? 2 : (B < 96 ? 3 : 4));
+    if (forced > 0) n = forced;
+    if (n > ddope_scene::MAX_PARTS) n = ddope_scene::MAX_PARTS;
+    if (s->profiling || n < 1) n = 1;
+    if (n > B) n = B;
     const int per = (B + n - 1) / n;
     for (int p = 0; p < n; p++) {
         Part& P = parts[p];

@@ -200,10 +200,10 @@ int ddope_optimize(ddope_scene* s, float* quat_dev, float* trans_dev, const floa
                    const ddope_loss_cfg* cfg, float* pose_hist_dev, float* loss_hist_dev,
                    void* stream);
 
-/* Streams: ddope_loss_grad / ddope_optimize order all their work on `stream`. For 32 or more hypotheses they fork
- * two internal streams from it (event wait), run one contiguous half of the hypotheses on each -- the issue-bound
- * raster kernel of one half overlaps the latency-bound pixel kernel of the other -- and join them back into `stream`
- * before returning; the caller sees ordinary stream semantics and bit-identical results. */
+/* Streams: ddope_loss_grad / ddope_optimize order all their work on `stream`. For 8 or more hypotheses they fork
+ * two to four internal streams from it (event wait), run one contiguous part of the hypotheses on each -- the
+ * issue-bound raster kernel of one part overlaps the latency-bound pixel kernel of another -- and join them back
+ * into `stream` before returning; the caller sees ordinary stream semantics and bit-identical results. */
 
 /* Number of kernels the last ddope_optimize / ddope_loss_grad / ddope_render call on this
  * scene launched (for bench.py's gpu_launches). */

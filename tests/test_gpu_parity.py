@@ -320,8 +320,9 @@ def test_full_size_properties():
     assert torch.isfinite(f1).all() and torch.isfinite(l1).all()
     total = l1.sum(-1)
     assert (total[-1] < total[0]).float().mean().item() > 0.9, "the loss must go down for almost every hypothesis"
-    # prologue + (raster, pixel, iter) per iteration, for each of the two parts a batch of >= 32 hypotheses is split
-    # into (internal streams, include/ddope_b200.h); the split changes no bit of the result (asserted above: 32+32 == 64)
+    # prologue + (raster, pixel, iter) per iteration, for each of the two parts a batch of 32 hypotheses is split
+    # into (internal streams, include/ddope_b200.h); the split changes no bit of the result (asserted above: 32+32 == 64,
+    # where the 64 ran as three parts)
     assert ex.sc.last_launch_count() == 2 * (3 * iters + 1)
 
 
