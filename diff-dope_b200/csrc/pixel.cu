@@ -315,6 +315,8 @@ __device__ void aa_grad_accum(const SceneDev& S, const float* mvp, int tri, int 
 }
 
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+// k * sgn(v) with abs'(0) = 0 (torch's subgradient, pinned in tests/test_oracle_pins.py)
+__device__ __forceinline__ float ksgn(float k, float v) { return (v == 0.f) ? 0.f : copysignf(k, v); }
 
 // Sum each of the NACC accumulators over the warp by recursive halving: at every step a lane keeps one half of
 // its values and trades the other half with its partner, so 20 values cost 10+5+3+2+1 = 21 shuffles instead of
@@ -444,18 +446,23 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
             constexpr int ROWS_PER_WARP = (IDS_H + 7) / 8;
             int idr[ROWS_PER_WARP][2];
 #pragma unroll
+            const unsigned int vw = (unsigned int)(vx1 - vx0);
             for (int k = 0; k < ROWS_PER_WARP; k++) {
                 const int iy = warp + 8 * k;
                 const int y = oy - 2 + iy;
+                // row tests are warp-uniform; the column tests use one unsigned compare per range
+                const bool row_in = iy < IDS_H && (unsigned int)y < (unsigned int)S.H;
+                const bool row_z = row_in && y >= vy0 && y < vy1;
+                const unsigned long long* zrow = zb + (size_t)(y - S.zy0) * S.zw - S.zx0;
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
                     const int ix = lane + 32 * half;
                     const int x = ox - 2 + ix;
                     int id = ID_OUTSIDE;
-                    if (iy < IDS_H && ix < IDS_W && x >= 0 && y >= 0 && x < S.W && y < S.H) {
+                    if (row_in && (half == 0 || ix < IDS_W) && (unsigned int)x < (unsigned int)S.W) {
                         id = ID_NONE;
-                        if (x >= vx0 && x < vx1 && y >= vy0 && y < vy1) {
-                            const unsigned long long key = zb[(size_t)(y - S.zy0) * S.zw + (x - S.zx0)];
+                        if (row_z && (unsigned int)(x - vx0) < vw) {
+                            const unsigned long long key = zrow[x];
                             if (key != EMPTY_KEY) id = (int)(unsigned int)(key & 0xFFFFFFFFull);
                         }
                     }
@@ -672,7 +679,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                 if (MODE == MODE_LOSS && cfg.use_depth) {
                     const float diff = (depth - gt_d) * seg[0];
                     acc[17] += fabsf(diff);
-                    gd = k_depth * sgn(diff) * seg[0];
+                    gd = ksgn(k_depth, diff) * seg[0];
                 }
                 if (MODE == MODE_EXT && ext.d_depth) gd = ext.d_depth[wp];
                 if (MODE != MODE_RENDER && gd != 0.f) {
@@ -707,7 +714,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                             if (cfg.use_rgb) {
                                 const float diff = (rgb[c] - gt_rgb[c]) * seg[c];
                                 acc[16] += fabsf(diff);
-                                dy += k_rgb * sgn(diff) * seg[c];
+                                dy += ksgn(k_rgb, diff) * seg[c];
                             }
                         } else {
                             dy = ext.d_rgb[wp * 3 + c];
@@ -725,7 +732,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                     if (cfg.use_depth) {
                         const float diff = (depth - gt_d) * seg[0];
                         acc[17] += fabsf(diff);
-                        acc[15] -= k_depth * sgn(diff) * seg[0];
+                        acc[15] -= ksgn(k_depth, diff) * seg[0];
                         gtouch = true;
                     }
                     if (cfg.use_rgb) {

@@ -29,7 +29,7 @@ for i, r in enumerate(data):
     agg[key][0] += int(r[ie]); agg[key][1] += int(r[sm])
 ti = sum(v[0] for v in agg.values()); ts = sum(v[1] for v in agg.values()) or 1
 srcs = {}
-top = sorted(agg.items(), key=lambda kv: -kv[1][1])[: int(sys.argv[4]) if len(sys.argv) > 4 else 40]
+top = sorted(agg.items(), key=lambda kv: -kv[1][0 if os.environ.get("BY_INST") else 1])[: int(sys.argv[4]) if len(sys.argv) > 4 else 40]
 for (f, ln), (ins, sa) in top:
     if f not in srcs:
         pth = os.path.join(os.path.dirname(lib), "..", "..", "csrc", f)

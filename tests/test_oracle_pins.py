@@ -428,3 +428,135 @@ def test_closed_mesh_detection_and_culling_preserves_coverage():
     M = np.eye(4)[None].repeat(2, 0)
     M[1, 0, 0] = -1
     assert list(nvdr.face_signs(1, P, M)) == [1, -1]
+
+
+# ----------------------------------------------------------------------------------------------
+# independent cross-checks of the oracle's geometry (nvdiffrast itself is not available: these pin the
+# restated rasterise / interpolate / depth arithmetic against first-principles computations instead)
+
+
+def _raycast(pos_cam, tri, P, H, W):
+    """Brute-force float64 ray casting through every pixel centre (Moeller-Trumbore): front-most triangle id,
+    3-D barycentrics (= perspective-correct attribute weights) and camera-space depth -z."""
+    P = np.asarray(P, dtype=np.float64)
+    xs = (np.arange(W) + 0.5) * 2.0 / W - 1.0
+    ys = (np.arange(H) + 0.5) * 2.0 / H - 1.0
+    X, Y = np.meshgrid(xs, ys)
+    # clip = P [x,y,z,1], w = -z: x_ndc = (P00 x + P02 z)/(-z), y_ndc = (P11 y + P12 z)/(-z); on the plane z = -1
+    # that is x_ndc = P00 x - P02, so the ray through (x_ndc, y_ndc) has direction ((x_ndc + P02)/P00, (y_ndc + P12)/P11, -1)
+    d = np.stack([(X + P[0, 2]) / P[0, 0], (Y + P[1, 2]) / P[1, 1], -np.ones_like(X)], -1).reshape(-1, 3)
+    best_t = np.full(d.shape[0], np.inf)
+    best_id = np.full(d.shape[0], -1)
+    best_uv = np.zeros((d.shape[0], 2))
+    for k, (a, b, c) in enumerate(tri):
+        v0, v1, v2 = pos_cam[a], pos_cam[b], pos_cam[c]
+        e1, e2 = v1 - v0, v2 - v0
+        pv = np.cross(d, e2)
+        det = pv @ e1
+        with np.errstate(all="ignore"):
+            inv = 1.0 / det
+            tv = -v0  # ray origin is the camera centre
+            bu = (pv @ tv) * inv
+            qv = np.cross(tv, e1)
+            bv = (d @ qv) * inv
+            t = (qv @ e2) * inv
+        hit = (np.abs(det) > 1e-12) & (bu >= 0) & (bv >= 0) & (bu + bv <= 1) & (t > 0) & (t < best_t)
+        best_t[hit] = t[hit]
+        best_id[hit] = k
+        # nvdiffrast's (u, v) are the weights of vertex 0 and vertex 1
+        best_uv[hit, 0] = (1 - bu - bv)[hit]
+        best_uv[hit, 1] = bu[hit]
+    depth = np.where(best_id >= 0, best_t, 0.0)  # direction has z = -1: t is exactly -z
+    return best_id.reshape(H, W), best_uv.reshape(H, W, 2), depth.reshape(H, W)
+
+
+def test_oracle_matches_ray_casting():
+    v, f, col = _cube()
+    mesh = refpath.Mesh(v, f, vtx_color=col)
+    H, W = 72, 96
+    P = refpath.projection_matrix(110.0, 105.0, 47.3, 37.1, W, H)
+    q = np.array([[0.31, -0.22, 0.12, 0.91]], dtype=np.float32)
+    t = np.array([[0.12, -0.07, -3.5]], dtype=np.float32)
+    r = refpath.render(mesh, P, torch.from_numpy(q), torch.from_numpy(t), H, W)
+    M = r["mtx"][0].numpy().astype(np.float64)
+    pos_cam = v.astype(np.float64) @ M[:3, :3].T + M[:3, 3]
+    ids, uv, depth = _raycast(pos_cam, f, P, H, W)
+    rast = r["rast_out"][0].numpy()
+    oid = rast[..., 3].astype(np.int64) - 1
+    assert (oid >= 0).sum() > 400
+    # interior pixels (same triangle in the 3x3 neighbourhood of the ray-cast image) are away from every edge, where
+    # neither the 1/256 px snapping nor a tie rule can matter: there the two must agree exactly on the winner
+    interior = np.ones_like(ids, bool)
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            interior &= np.roll(np.roll(ids, dy, 0), dx, 1) == ids
+    interior &= ids >= 0
+    assert interior.sum() > 250
+    assert np.array_equal(oid[interior], ids[interior])
+    assert np.abs(rast[..., 0][interior] - uv[..., 0][interior]).max() < 2e-5
+    assert np.abs(rast[..., 1][interior] - uv[..., 1][interior]).max() < 2e-5
+    assert np.abs(r["depth"][0].numpy()[interior] - depth[interior]).max() < 2e-5
+    # everywhere: coverage differs only on the silhouette ring (snapping), winners only next to an edge
+    cov_diff = (oid >= 0) != (ids >= 0)
+    assert cov_diff.sum() <= 0.02 * (ids >= 0).sum()
+    # interpolated vertex colour = barycentric blend of the ray-cast weights
+    want = (uv[..., 0:1] * col[f[ids.clip(0), 0]] + uv[..., 1:2] * col[f[ids.clip(0), 1]] + (1 - uv[..., 0:1] - uv[..., 1:2]) * col[f[ids.clip(0), 2]])
+    assert np.abs(r["rgb"][0].numpy()[interior] - want[interior]).max() < 3e-5
+
+
+def test_oracle_coverage_matches_opencv_polygon_fill():
+    """Silhouette of the example mesh against OpenCV's polygon rasteriser fed with the same 1/256 px fixed-point
+    vertices (an independent implementation with a different fill rule: boundary pixels may differ)."""
+    import cv2
+
+    arr = su.example_mesh_arrays()
+    q, t = su.example_pose()
+    H, W = 270, 480
+    P = su.projection()
+    qh, M = nvdr.canonical_pose(q[None], t[None])
+    clip = nvdr.canonical_xfm_points(arr["pos"][None], nvdr.canonical_mvp(P, M))
+    cov = nvdr.rasterize(clip, arr["tri"], H, W)[0, ..., 3] > 0
+    X, Y, ok = nvdr.snap_vertices(clip[0], W, H)
+    assert ok.all()
+    img = np.zeros((H, W), np.uint8)
+    tri = arr["tri"]
+    # pixel centres sit at +0.5: shift by half a pixel so that cv2's integer pixel grid samples centres
+    pts = np.stack([X[tri] - 128, Y[tri] - 128], -1).astype(np.int32)
+    for p in pts:
+        cv2.fillConvexPoly(img, p, 1, lineType=cv2.LINE_8, shift=8)
+    cvcov = img > 0
+    inter, union = (cov & cvcov).sum(), (cov | cvcov).sum()
+    assert cov.sum() > 1200 and inter / union > 0.90, inter / union
+    # every disagreement lies on the silhouette ring: eroding the OpenCV fill by one pixel puts it inside ours, dilating ours covers it
+    k = np.ones((3, 3), np.uint8)
+    assert not (cv2.erode(img, k).astype(bool) & ~cov).any()
+    assert not (cvcov & ~cv2.dilate(cov.astype(np.uint8), k).astype(bool)).any()
+
+
+def test_antialiased_mask_equals_area_coverage_on_axis_aligned_edges():
+    """Closed form for the restated dr.antialias: for a straight, axis-aligned silhouette edge the blend weight is
+    the distance of the edge from the pixel-pair midpoint, so the antialiased mask equals the exact fraction of the
+    pixel that the shape covers."""
+    H, W = 56, 80
+    P = refpath.projection_matrix(90.0, 90.0, 40.0, 28.0, W, H).astype(np.float64)
+    d = 3.0
+    x0, x1, y0, y1 = 20.3, 60.7, 10.4, 40.6  # edges in pixel units
+
+    def cam(px, py):
+        nx, ny = px / W * 2 - 1, py / H * 2 - 1
+        return [(nx + P[0, 2]) * d / P[0, 0], (ny + P[1, 2]) * d / P[1, 1], 0.0]
+
+    v = np.array([cam(x0, y0), cam(x1, y0), cam(x1, y1), cam(x0, y1)], dtype=np.float32)
+    f = np.array([[0, 1, 2], [0, 2, 3]])
+    mesh = refpath.Mesh(v, f, vtx_color=np.ones((4, 3), np.float32))
+    q = np.array([[0.0, 0.0, 0.0, 1.0]], dtype=np.float32)
+    t = np.array([[0.0, 0.0, -d]], dtype=np.float32)
+    m = refpath.render(mesh, P, torch.from_numpy(q), torch.from_numpy(t), H, W)["mask"][0, ..., 0].numpy()
+    rows, cols = slice(13, 38), slice(23, 58)  # away from the corners
+    assert np.allclose(m[rows, 20], 0.7, atol=2e-3) and np.allclose(m[rows, 19], 0.0, atol=1e-6)    # left edge at 20.3
+    assert np.allclose(m[rows, 60], 0.7, atol=2e-3) and np.allclose(m[rows, 61], 0.0, atol=1e-6)    # right edge at 60.7
+    assert np.allclose(m[10, cols], 0.6, atol=2e-3) and np.allclose(m[9, cols], 0.0, atol=1e-6)     # bottom edge at 10.4
+    assert np.allclose(m[40, cols], 0.6, atol=2e-3) and np.allclose(m[41, cols], 0.0, atol=1e-6)    # top edge at 40.6
+    assert np.allclose(m[rows, cols], 1.0, atol=1e-6)
+    # total mask mass = area of the rectangle up to the four corner pixels
+    assert abs(m.sum() - (x1 - x0) * (y1 - y0)) < 1.0
