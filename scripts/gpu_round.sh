@@ -8,5 +8,5 @@ echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --steps 200 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launches.log 2>&1
-ITERS=6 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"raster_kernel|pixel_kernel|iter_kernel" -s 35 -c 3 -f -o gpurun_out/${TAG}_full python scripts/dev_kernels.py > gpurun_out/${TAG}_full.log 2>&1
+DDOPE_PARTS=1 ITERS=6 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"raster_kernel|pixel_kernel|iter_kernel" -s 35 -c 3 -f -o gpurun_out/${TAG}_full python scripts/dev_kernels.py > gpurun_out/${TAG}_full.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_bench.json; cat gpurun_out/${TAG}_bench_ref.json
