@@ -357,3 +357,57 @@ def test_backface_culling_rule(ex_half):
     finally:
         ex.sc.set_culling(True)
     assert (a[3][..., 3] > 0).sum() > 1000 and torch.equal(a[3][..., 3] > 0, b[3][..., 3] > 0)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_triangle_soups_match_oracle_bit_exact(seed):
+    """Random open triangle soups (nothing is culled): slivers, strips taller than wide and wider than tall (both
+    scanline orientations), triangles larger than 64 px (CTA path), degenerate and duplicated triangles, vertices
+    behind the camera and far outside the frame -- coverage, winners, barycentrics, z/w, colour, depth and the
+    antialiased mask against the oracle."""
+    from oracle import refpath
+
+    n = _nat()
+    rng = np.random.default_rng(seed)
+    H, W = 80, 112
+    P = refpath.projection_matrix(120.0, 115.0, 55.0, 41.0, W, H)
+    nt = 260
+    ctr = rng.uniform(-1.6, 1.6, (nt, 1, 3)) * np.array([1.3, 1.0, 0.6])
+    size = np.exp(rng.uniform(np.log(0.01), np.log(0.9), (nt, 1, 1)))
+    v = ctr + rng.normal(0, 1, (nt, 3, 3)) * size
+    v[:40, :, 0] = ctr[:40, :, 0] + rng.normal(0, 0.004, (40, 3))           # tall, thin strips
+    v[40:80, :, 1] = ctr[40:80, :, 1] + rng.normal(0, 0.004, (40, 3))       # wide, thin strips
+    v[80:84] = v[80:81]                                                      # duplicated triangles (lower index wins ties)
+    v[84, 2] = v[84, 1]                                                      # degenerate
+    v[85:90, :, 2] += 6.0                                                    # behind the camera (w <= 0) -> culled whole
+    v[90:93] *= 40.0                                                         # far outside the frame / huge
+    pos = v.reshape(-1, 3).astype(np.float32)
+    tri = np.arange(nt * 3, dtype=np.int32).reshape(nt, 3)
+    col = rng.random((nt * 3, 3)).astype(np.float32)
+    sc = n.NativeScene(pos, tri, vtx_color=col)
+    assert sc.mesh_orientation() == 0
+    sc.set_camera(P, H, W)
+    B = 3
+    q = rng.normal(0, 1, (B, 4)).astype(np.float32)
+    t = (np.array([[0.0, 0.0, -4.5]]) + rng.normal(0, 0.3, (B, 3))).astype(np.float32)
+    out = sc.render(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda())
+    mesh = refpath.Mesh(pos, tri, vtx_color=col)
+    r = refpath.render(mesh, P, torch.from_numpy(q), torch.from_numpy(t), H, W)
+    ro, rg = r["rast_out"].numpy(), out["rast"].cpu().numpy()
+    assert (ro[..., 3] > 0).mean() > 0.2, "the soup must cover a good part of the frame"
+    assert np.array_equal(ro[..., 3], rg[..., 3])
+    assert np.array_equal(ro[..., :3], rg[..., :3])
+    assert np.array_equal(r["rgb"].numpy(), out["rgb"].cpu().numpy())
+    assert np.array_equal(r["depth"].numpy(), out["depth"].cpu().numpy())
+    assert np.abs(r["mask"].numpy()[..., 0] - out["mask"].cpu().numpy()).max() <= 1.2e-7
+    # and the gradient of the three losses on this soup
+    gt = dict(rgb=rng.random((H, W, 3)).astype(np.float32), depth=(4 + rng.random((H, W))).astype(np.float32),
+              segmentation=np.repeat((rng.random((H, W, 1)) > 0.4).astype(np.float32), 3, -1))
+    g = {k: torch.from_numpy(x).cuda() for k, x in gt.items()}
+    sc.set_target(g["rgb"], g["depth"], g["segmentation"])
+    lr = su.lr_multipliers(B)
+    loss, grad = sc.loss_grad(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(lr).cuda(), _cfg(n, ALL))
+    logged, gq, gtr, _ = refpath.forward_backward(mesh, P, q, t, {k: torch.from_numpy(x) for k, x in gt.items()}, lr, ALL, H, W)
+    assert np.allclose(loss.cpu().numpy(), _loss_table(logged, B), rtol=1e-4, atol=1e-10)
+    go, gg = np.concatenate([gq, gtr], 1), grad.cpu().numpy()
+    assert np.abs(go - gg).max() <= 2e-4 * np.abs(go).max()
