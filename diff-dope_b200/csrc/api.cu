@@ -53,8 +53,6 @@ struct ddope_scene {
     size_t zbuf_cap = 0;
     float* partials = nullptr;
     size_t partials_cap = 0;
-    float* lr_sched = nullptr;
-    int lr_cap = 0;
     float* xfm_scratch = nullptr;
     int num_sms = 148;
     int64_t launches = 0;
@@ -69,7 +67,6 @@ struct ddope_scene {
     cudaStream_t part_stream[MAX_PARTS] = {};
     cudaEvent_t part_done[MAX_PARTS] = {};
     cudaEvent_t fork_event = nullptr;
-    std::vector<float> sched_host;         // staging of the per-iteration scalars (must outlive the async copy)
 };
 
 bool ddope::pdl_enabled() {
@@ -285,7 +282,7 @@ extern "C" int ddope_scene_destroy(ddope_scene* s) {
     if (!s) return 0;
     cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex4); cudaFree(s->vcol); cudaFree(s->gt_edge); cudaFree(s->adam_state); cudaFree(s->tripos); cudaFree(s->tricol);
     cudaFree(s->seg_bbox); cudaFree(s->total_tiles); cudaFree(s->hyp); cudaFree(s->zbuf); cudaFree(s->partials);
-    cudaFree(s->lr_sched); cudaFree(s->xfm_scratch); cudaFree(s->arrive);
+    cudaFree(s->xfm_scratch); cudaFree(s->arrive);
     for (int p = 0; p < ddope_scene::MAX_PARTS; p++) {
         if (s->part_stream[p]) cudaStreamDestroy(s->part_stream[p]);
         if (s->part_done[p]) cudaEventDestroy(s->part_done[p]);
@@ -552,12 +549,15 @@ struct ProfMark {
     }
 };
 
-static OptimDev optim_dev(const ddope_scene* s, int n_iters) {
+// Optimiser state for iteration `it` of a call: the per-iteration scalars are computed on the host in double, like torch's
+// Python side does (lr_t / (1 - beta1^t), sqrt(1 - beta2^t)), and travel as kernel arguments.
+static OptimDev optim_dev(const ddope_scene* s, float lr_t, int it) {
     OptimDev o;
     o.kind = s->optim.kind; o.beta1 = s->optim.beta1; o.beta2 = s->optim.beta2; o.eps = s->optim.eps;
     o.state = s->adam_state;
-    o.step_size = s->lr_sched ? s->lr_sched + n_iters : nullptr;
-    o.bc2_sqrt = s->lr_sched ? s->lr_sched + 2 * (size_t)n_iters : nullptr;
+    const double t = (double)s->optim.step0 + it + 1;
+    o.step_size = (float)((double)lr_t / (1.0 - std::pow((double)s->optim.beta1, t)));
+    o.bc2_sqrt = (float)std::sqrt(1.0 - std::pow((double)s->optim.beta2, t));
     return o;
 }
 
@@ -631,7 +631,7 @@ static void enqueue_prologue(ddope_scene* s, const Part& P, float* quat, float* 
     ProfMark m(s, P.st, K_ITER);
     HypState* h = s->hyp + P.b0;
     launch_iter(s->dev, h, h, P.partials, P.B, B_global, P.B, cfg, opt, quat + 4 * (size_t)P.b0, trans + 3 * (size_t)P.b0,
-                lr_mult ? lr_mult + P.b0 : nullptr, s->lr_sched, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr, P.zbuf, P.total_tiles,
+                lr_mult ? lr_mult + P.b0 : nullptr, 0.f, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr, P.zbuf, P.total_tiles,
                 P.arrive, P.st);
     s->launches += 1;
 }
@@ -639,7 +639,7 @@ static void enqueue_prologue(ddope_scene* s, const Part& P, float* quat, float* 
 // raster + pixel of iteration `it`, then one launch that finishes it (step, z-buffer restore) and, if more
 // follow, sets up the next one. hyp_cur (which half of `hyp` is current) is toggled by the caller once per iteration.
 static void enqueue_iteration(ddope_scene* s, const Part& P, float* quat, float* trans, const float* lr_mult, int B_global,
-                              int B_hist, LossCfgDev cfg, OptimDev opt, int it, int do_update, int more, float* loss_table,
+                              int B_hist, LossCfgDev cfg, OptimDev opt, float lr_t, int it, int do_update, int more, float* loss_table,
                               float* grad, float* pose_hist, float* loss_hist) {
     HypState* cur = s->hyp + (size_t)s->hyp_cur * s->hyp_cap + P.b0;
     HypState* nxt = s->hyp + (size_t)(s->hyp_cur ^ 1) * s->hyp_cap + P.b0;
@@ -656,7 +656,7 @@ static void enqueue_iteration(ddope_scene* s, const Part& P, float* quat, float*
         OptimDev o = opt;
         if (o.state) o.state += 14 * (size_t)P.b0;
         launch_iter(s->dev, cur, nxt, P.partials, P.B, B_global, B_hist, cfg, o, quat + 4 * (size_t)P.b0, trans + 3 * (size_t)P.b0,
-                    lr_mult ? lr_mult + P.b0 : nullptr, s->lr_sched, it, 1, do_update, more,
+                    lr_mult ? lr_mult + P.b0 : nullptr, lr_t, it, 1, do_update, more,
                     loss_table ? loss_table + NLOSS * (size_t)P.b0 : nullptr, grad ? grad + 7 * (size_t)P.b0 : nullptr,
                     pose_hist ? pose_hist + 7 * (size_t)P.b0 : nullptr, loss_hist ? loss_hist + NLOSS * (size_t)P.b0 : nullptr, P.zbuf,
                     P.total_tiles, P.arrive, P.st);
@@ -674,14 +674,14 @@ extern "C" int ddope_loss_grad(ddope_scene* s, const float* quat, const float* t
     if (int r = ensure_buffers(s, B, true, st)) return r;
     if (int r = prepare_edge(s, cfg, st)) return r;
     s->launches = 0;
-    OptimDev opt = {0, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr};
+    OptimDev opt = {0, 0.f, 0.f, 0.f, nullptr, 0.f, 0.f};
     Part parts[ddope_scene::MAX_PARTS];
     int n_parts = 1;
     if (int r = fork_parts(s, B, st, parts, &n_parts)) return r;
     s->hyp_cur = 0;
     for (int p = 0; p < n_parts; p++) {
         enqueue_prologue(s, parts[p], const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B_global, to_dev(cfg), opt);
-        enqueue_iteration(s, parts[p], const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B_global, B, to_dev(cfg), opt, 0, 0,
+        enqueue_iteration(s, parts[p], const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B_global, B, to_dev(cfg), opt, 0.f, 0, 0,
                           0, loss_table, grad, nullptr, nullptr);
     }
     if (int r = join_parts(s, st, parts, n_parts)) return r;
@@ -699,22 +699,6 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, true, st)) return r;
     if (int r = prepare_edge(s, cfg, st)) return r;
-    if (n_iters > s->lr_cap) {
-        if (s->lr_sched) CK(cudaFree(s->lr_sched));
-        CK(cudaMalloc(&s->lr_sched, sizeof(float) * 3 * (size_t)n_iters));
-        s->lr_cap = n_iters;
-    }
-    // per-iteration scalars, computed in double like torch's Python side: lr_t | lr_t / (1 - beta1^t) | sqrt(1 - beta2^t)
-    s->sched_host.resize(3 * (size_t)n_iters);
-    for (int it = 0; it < n_iters; it++) {
-        const double t = (double)s->optim.step0 + it + 1;
-        const double bc1 = 1.0 - std::pow((double)s->optim.beta1, t), bc2 = 1.0 - std::pow((double)s->optim.beta2, t);
-        s->sched_host[it] = lr_sched[it];
-        s->sched_host[n_iters + it] = (float)((double)lr_sched[it] / bc1);
-        s->sched_host[2 * (size_t)n_iters + it] = (float)std::sqrt(bc2);
-    }
-    // sized for lr_cap so the three sections stay at offsets 0, n_iters, 2 n_iters of this call
-    CK(cudaMemcpyAsync(s->lr_sched, s->sched_host.data(), sizeof(float) * 3 * (size_t)n_iters, cudaMemcpyHostToDevice, st));
     if (s->optim.kind == DDOPE_OPT_ADAM) {
         if (B > s->adam_cap) {
             if (s->optim.step0 > 0 && s->adam_state) return fail("ddope_optimize: Adam continuation (step0 > 0) with a larger batch than the stored moments");
@@ -727,7 +711,7 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
         }
     }
     LossCfgDev c = to_dev(cfg);
-    OptimDev opt = optim_dev(s, n_iters);
+    OptimDev opt = optim_dev(s, 0.f, 0);
     s->launches = 0;
     Part parts[ddope_scene::MAX_PARTS];
     int n_parts = 1;
@@ -735,9 +719,10 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     s->hyp_cur = 0;
     for (int p = 0; p < n_parts; p++) enqueue_prologue(s, parts[p], quat, trans, lr_mult, B_global, c, opt);
     for (int it = 0; it < n_iters; it++) {
+        opt = optim_dev(s, lr_sched[it], it);
         for (int p = 0; p < n_parts; p++)
-            enqueue_iteration(s, parts[p], quat, trans, lr_mult, B_global, B, c, opt, it, 1, it + 1 < n_iters, nullptr, nullptr,
-                              pose_hist, loss_hist);
+            enqueue_iteration(s, parts[p], quat, trans, lr_mult, B_global, B, c, opt, lr_sched[it], it, 1, it + 1 < n_iters, nullptr,
+                              nullptr, pose_hist, loss_hist);
         s->hyp_cur ^= 1;
     }
     if (int r = join_parts(s, st, parts, n_parts)) return r;

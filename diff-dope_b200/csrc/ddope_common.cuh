@@ -80,8 +80,8 @@ struct OptimDev {
     int kind;
     float beta1, beta2, eps;
     float* state;            // [B,14]: first and second moment of the 7 parameters
-    const float* step_size;  // [n_iters]: lr_t / (1 - beta1^t)
-    const float* bc2_sqrt;   // [n_iters]: sqrt(1 - beta2^t)
+    float step_size;         // this iteration's lr_t / (1 - beta1^t)
+    float bc2_sqrt;          // this iteration's sqrt(1 - beta2^t)
 };
 
 __device__ __forceinline__ void xfm_exact(const float* __restrict__ m, float x, float y, float z, float* c) {

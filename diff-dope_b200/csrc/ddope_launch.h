@@ -34,7 +34,7 @@ void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, 
 // Fused iteration boundary: [step of iteration it + z-buffer restore] + [pose, tile prefix of the next iteration].
 // B = hypotheses of this launch, B_global = divisor of the hypothesis mean, B_hist = row stride of the history tables.
 void launch_iter(const SceneDev& S, const HypState* hyp_old, HypState* hyp_new, const float* partials, int B, int B_global,
-                 int B_hist, LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, const float* lr_sched, int it,
+                 int B_hist, LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, float lr_t, int it,
                  int do_step, int do_update, int do_pose, float* loss_table, float* grad_out, float* pose_hist,
                  float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, cudaStream_t st);
 void launch_seg_bbox(const float* seg, int H, int W, int seg_c, int* bbox4, cudaStream_t st);

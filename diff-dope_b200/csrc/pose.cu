@@ -180,7 +180,7 @@ void launch_pose(const SceneDev& S, const float* quat, const float* trans, const
 // (qx,qy,qz,qw,x,y,z) the iteration rendered with and receives the updated ones.
 __device__ void step_from_sums(const SceneDev& S, const HypState& h, const float* a, int b, int B, LossCfgDev cfg,
                                OptimDev opt, float* theta, float* __restrict__ quat, float* __restrict__ trans,
-                               const float* __restrict__ lr_sched, int it, int do_update,
+                               float lr_t, int it, int do_update,
                                float* __restrict__ loss_table, float* __restrict__ grad_out,
                                float* __restrict__ pose_hist, float* __restrict__ loss_hist,
                                float* __restrict__ dmtx_out) {
@@ -238,7 +238,7 @@ __device__ void step_from_sums(const SceneDev& S, const HypState& h, const float
         if (opt.kind == 1) {  // torch.optim.Adam (_single_tensor_adam): lerp, addcmul, sqrt / bc2_sqrt + eps, addcdiv
             float* m = opt.state + 14 * (size_t)b;
             float* v = m + 7;
-            const float ss = opt.step_size[it], bc2s = opt.bc2_sqrt[it];
+            const float ss = opt.step_size, bc2s = opt.bc2_sqrt;
             for (int k = 0; k < 7; k++) {
                 const float mk = m[k] + (g[k] - m[k]) * (1.f - opt.beta1);
                 const float vk = v[k] * opt.beta2 + (1.f - opt.beta2) * (g[k] * g[k]);
@@ -247,7 +247,7 @@ __device__ void step_from_sums(const SceneDev& S, const HypState& h, const float
                 theta[k] -= ss * (mk / denom);
             }
         } else {
-            const float lr = lr_sched[it];
+            const float lr = lr_t;
             for (int k = 0; k < 7; k++) theta[k] -= lr * g[k];
         }
         for (int k = 0; k < 4; k++) quat[4 * b + k] = theta[k];
@@ -302,8 +302,8 @@ __global__ void __launch_bounds__(128) step_kernel(SceneDev S, const HypState* _
     const int b = blockIdx.x;
     reduce_tile_partials(hyp[b], partials, s_sum);
     if (threadIdx.x == 0) {
-        OptimDev none = {0, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr};
-        step_from_sums(S, hyp[b], s_sum, b, B, cfg, none, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
+        OptimDev none = {0, 0.f, 0.f, 0.f, nullptr, 0.f, 0.f};
+        step_from_sums(S, hyp[b], s_sum, b, B, cfg, none, nullptr, nullptr, nullptr, 0.f, 0, 0, nullptr, nullptr, nullptr,
                        nullptr, dmtx_out);
     }
 }
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
                                                    const float* __restrict__ partials, int B, int B_global, int B_hist,
                                                    LossCfgDev cfg, OptimDev opt, float* __restrict__ quat,
                                                    float* __restrict__ trans, const float* __restrict__ lr_mult,
-                                                   const float* __restrict__ lr_sched, int it, int do_step, int do_update,
+                                                   float lr_t, int it, int do_step, int do_update,
                                                    int do_pose, float* __restrict__ loss_table, float* __restrict__ grad_out,
                                                    float* __restrict__ pose_hist, float* __restrict__ loss_hist,
                                                    unsigned long long* __restrict__ zbuf, int* __restrict__ total_tiles,
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
         __syncthreads();
         reduce_tile_partials(s_h, partials, s_sum);
         if (threadIdx.x == 0)
-            step_from_sums(S, s_h, s_sum, b, B_hist, cfg, opt, s_theta, quat, trans, lr_sched, it, do_update, loss_table, grad_out,
+            step_from_sums(S, s_h, s_sum, b, B_hist, cfg, opt, s_theta, quat, trans, lr_t, it, do_update, loss_table, grad_out,
                            pose_hist, loss_hist, nullptr);
     } else {
         __syncthreads();
@@ -442,11 +442,11 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
 }
 
 void launch_iter(const SceneDev& S, const HypState* hyp_old, HypState* hyp_new, const float* partials, int B, int B_global,
-                 int B_hist, LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, const float* lr_sched, int it,
+                 int B_hist, LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, float lr_t, int it,
                  int do_step, int do_update, int do_pose, float* loss_table, float* grad_out, float* pose_hist,
                  float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, cudaStream_t st) {
     launch_kernel(pdl_enabled(), iter_kernel, dim3(do_step ? 1 + CLEAR_CTAS : 1, B), dim3(ITER_THREADS), 0, st, S, hyp_old, hyp_new, partials, B,
-                  B_global, B_hist, cfg, opt, quat, trans, lr_mult, lr_sched, it, do_step, do_update, do_pose, loss_table, grad_out, pose_hist,
+                  B_global, B_hist, cfg, opt, quat, trans, lr_mult, lr_t, it, do_step, do_update, do_pose, loss_table, grad_out, pose_hist,
                   loss_hist, zbuf, total_tiles, arrive);
 }
 
