@@ -149,3 +149,34 @@ def test_extension_errors(ex_q):
     t = torch.from_numpy(ex.t[None]).cuda()
     with pytest.raises(RuntimeError, match="edge loss needs the rgb target"):
         sc.loss_grad(q, t, torch.ones(1).cuda(), _cfg(n, EDGE_ONLY))
+
+
+def test_parts_and_shards_are_bit_identical_with_extensions(ex_q):
+    """16 hypotheses run as two internal parts (include/ddope_b200.h, "Streams"); four shards of 4 run unsplit.
+    With Adam, the edge loss and the mipmap filter switched on, every table must still agree bit for bit: per-part
+    offsets into the Adam moments, the history tables and the partial sums."""
+    ex = ex_q
+    B, iters = 16, 5
+    qs, ts = su.perturbed_poses(ex.q, ex.t, B)
+    lr = torch.from_numpy(su.lr_multipliers(B, 0.05, 2.0)).cuda()
+    sched = [0.004 * 0.5 ** (i / (iters - 1) + 1) for i in range(iters)]
+    cfg = _cfg(ex.n, FULL)
+    try:
+        ex.sc.set_optimizer("adam", beta1=0.9, beta2=0.99, eps=1e-8)
+        ex.sc.set_texture_filter("linear-mipmap-linear")
+        q, t = torch.from_numpy(qs).cuda().contiguous(), torch.from_numpy(ts).cuda().contiguous()
+        ph, lh = ex.sc.optimize(q, t, lr, sched, cfg)
+        assert ex.sc.last_launch_count() == 2 * (3 * iters + 1)
+        for lo in range(0, B, 4):
+            qk, tk = torch.from_numpy(qs[lo:lo + 4]).cuda().contiguous(), torch.from_numpy(ts[lo:lo + 4]).cuda().contiguous()
+            pk, lk = ex.sc.optimize(qk, tk, lr[lo:lo + 4].contiguous(), sched, cfg, b_global=B)
+            assert ex.sc.last_launch_count() == 3 * iters + 1
+            assert torch.equal(pk, ph[:, lo:lo + 4]) and torch.equal(lk, lh[:, lo:lo + 4])
+            assert torch.equal(qk, q[lo:lo + 4]) and torch.equal(tk, t[lo:lo + 4])
+        assert float(lh[..., 3].min()) > 0 and not torch.equal(ph[0], ph[-1])
+        # loss_grad splits too: its tables equal the first iteration of the optimisation
+        loss, grad = ex.sc.loss_grad(torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda(), lr, cfg)
+        assert torch.equal(loss, lh[0])
+    finally:
+        ex.sc.set_optimizer("sgd")
+        ex.sc.set_texture_filter("linear")
