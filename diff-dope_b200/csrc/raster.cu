@@ -26,7 +26,10 @@ void launch_clear(const SceneDev& S, const HypState* hyp, int B, unsigned long l
     clear_kernel<<<dim3(32, B), 128, 0, st>>>(S, hyp, zbuf);
 }
 
-constexpr int RASTER_THREADS = 256;
+#ifndef RASTER_THREADS_N
+#define RASTER_THREADS_N 128
+#endif
+constexpr int RASTER_THREADS = RASTER_THREADS_N;
 constexpr int SMALL_EXTENT = 64 * SUBPIX;  // bbox extent up to which int32 edge functions cannot overflow
 constexpr int REC_WORDS = 25;
 
