@@ -81,8 +81,10 @@ extern "C" int64_t ddope_last_launch_count(const ddope_scene* s) { return s ? s-
 // ---------------------------------------------------------------------------------------------
 // renderutils_plugin replacements
 
-static float* g_xfm_scratch = nullptr;
-static size_t g_xfm_scratch_cap = 0;
+// scratch of ddope_xfm_bwd_mtx's two-stage reduction: one per host thread (the entry points are re-entrant like the
+// reference plugin's, c_src/torch_bindings.cpp:147; a buffer is only replaced after a device synchronisation in cudaFree)
+static thread_local float* g_xfm_scratch = nullptr;
+static thread_local size_t g_xfm_scratch_cap = 0;
 
 extern "C" int ddope_xfm_fwd(const float* points, int Bp, int N, const float* matrix, int B, int is_points,
                              float* out, void* stream) {
@@ -200,6 +202,10 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     if ((uint64_t)T >= 0xFFFFFFFFull) return fail("ddope_scene_create: too many triangles");
 
     ddope_scene* s = new ddope_scene();
+    struct Guard {  // a failing CUDA call below returns early: release what was allocated so far
+        ddope_scene* p;
+        ~Guard() { if (p) ddope_scene_destroy(p); }
+    } guard{s};
     CK(cudaMalloc(&s->pos, sizeof(float) * 3 * V));
     CK(cudaMemcpy(s->pos, pos, sizeof(float) * 3 * V, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&s->tri, sizeof(int) * 3 * T));
@@ -274,6 +280,7 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, dev_id);
+    guard.p = nullptr;
     *out = s;
     return 0;
 }

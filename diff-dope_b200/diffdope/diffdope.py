@@ -144,7 +144,9 @@ def render_texture_batch(glctx, proj_cam, mtx, pos, pos_idx, resolution, uv=None
     uv0 = None if uv is None else (uv[0] if uv.dim() == 3 else uv)
     tex0 = None if tex is None else (tex[0] if tex.dim() == 4 else tex)
     vc0 = None if vtx_color is None else (vtx_color[0] if vtx_color.dim() == 3 else vtx_color)
-    key = (pos0.data_ptr(), idx0.data_ptr(), None if tex0 is None else tex0.data_ptr(), None if vc0 is None else vc0.data_ptr())
+    key = (pos0.data_ptr(), tuple(pos0.shape), pos0._version, idx0.data_ptr(), tuple(idx0.shape),
+           None if tex0 is None else (tex0.data_ptr(), tuple(tex0.shape), tex0._version),
+           None if vc0 is None else (vc0.data_ptr(), tuple(vc0.shape), vc0._version))
     cache = render_texture_batch.__dict__.setdefault("_scenes", {})
     sc = cache.get(key)
     if sc is None:
