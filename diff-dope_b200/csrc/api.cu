@@ -393,6 +393,13 @@ extern "C" int ddope_scene_set_culling(ddope_scene* s, int mode) {
 
 extern "C" int ddope_scene_mesh_orientation(const ddope_scene* s) { return s ? s->cull_auto : 0; }
 
+extern "C" int ddope_mesh_orientation(const float* pos, int V, const int32_t* tri, int T) {
+    if (!pos || !tri || V <= 0 || T <= 0) return 0;
+    for (int i = 0; i < 3 * T; i++)
+        if (tri[i] < 0 || tri[i] >= V) return 0;
+    return closed_mesh_orientation(pos, V, tri, T);
+}
+
 extern "C" int ddope_scene_set_optimizer(ddope_scene* s, const ddope_optim_cfg* cfg) {
     if (!s || !cfg) return fail("ddope_scene_set_optimizer: null pointer");
     if (cfg->kind != DDOPE_OPT_SGD && cfg->kind != DDOPE_OPT_ADAM) return fail("ddope_scene_set_optimizer: unknown optimizer kind");

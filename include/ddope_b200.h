@@ -150,6 +150,8 @@ int ddope_scene_set_window(ddope_scene* s, int y0, int x0, int h, int w);
  * oriented meshes are never culled. ddope_scene_mesh_orientation: +1 / -1 (closed, positive / negative volume) or 0. */
 int ddope_scene_set_culling(ddope_scene* s, int mode);
 int ddope_scene_mesh_orientation(const ddope_scene* s);
+/* The same classification for host arrays (pos [V,3], tri [T,3]); pure host code, needs no GPU. */
+int ddope_mesh_orientation(const float* pos_host, int V, const int32_t* tri_host, int T);
 
 /* Extensions (defaults = reference behaviour). max_levels <= 0: the full chain down to 1x1. */
 int ddope_scene_set_texture_filter(ddope_scene* s, int mode, int max_levels);

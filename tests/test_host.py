@@ -217,3 +217,31 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "hyp*iter/s"
+
+
+def test_mesh_orientation_host_function_matches_oracle():
+    """ddope_mesh_orientation (pure host code in the C-ABI library) and oracle.nvdr.closed_mesh_orientation classify
+    meshes identically: closed / inside-out / open / inconsistently wound / seam-duplicated."""
+    from oracle import nvdr
+
+    lib = ctypes.CDLL(LIB)
+    lib.ddope_mesh_orientation.restype = ctypes.c_int
+    lib.ddope_mesh_orientation.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+
+    def c_side(pos, tri):
+        p = np.ascontiguousarray(pos, dtype=np.float32)
+        t = np.ascontiguousarray(tri, dtype=np.int32)
+        return lib.ddope_mesh_orientation(p.ctypes.data, p.shape[0], t.ctypes.data, t.shape[0])
+
+    v = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], dtype=np.float32) * 0.5
+    f = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]], dtype=np.int32)
+    flipped = f.copy()
+    flipped[3] = flipped[3, ::-1]
+    v2 = np.concatenate([v, v[:1]])
+    f2 = f.copy()
+    f2[0, 0] = 8
+    arr = su.example_mesh_arrays()
+    cases = [(v, f, 1), (v, f[:, ::-1], -1), (v, f[:-1], 0), (v, flipped, 0), (v2, f2, 1), (arr["pos"], arr["tri"], 1), (arr["pos"], arr["tri"][:-1], 0)]
+    for pos, tri, want in cases:
+        assert c_side(pos, tri) == want == nvdr.closed_mesh_orientation(pos, tri)
+    assert c_side(v, np.array([[0, 1, 99]], np.int32)) == 0  # out-of-range index: not classified, no crash
