@@ -623,15 +623,20 @@ class Scene:
 
 
 class _LazyResult(dict):
-    """One entry of `optimization_results`: 'mtx' is stored, 'rgb' / 'depth' / 'mask' are rendered
-    from the stored pose the first time they are read (the reference keeps B*H*W*28 bytes per
+    """One entry of `optimization_results`: nothing is materialised until it is read. 'mtx' is built from the stored
+    pose of that iteration, 'rgb' / 'depth' / 'mask' are rendered from it (the reference keeps B*H*W*28 bytes per
     iteration on the host instead, `diffdope.py:1698-1703,595`)."""
 
-    def __init__(self, owner, index, mtx):
-        super().__init__(mtx=mtx)
+    def __init__(self, owner, index):
+        super().__init__()
         self._owner, self._index = owner, index
 
     def __missing__(self, key):
+        if key == "mtx":
+            ph = self._owner._pose_hist_host[self._index]
+            qn = ph[:, :4] / torch.norm(ph[:, :4], dim=-1, keepdim=True)
+            dict.__setitem__(self, "mtx", matrix_batch_44_from_position_quat(qn, ph[:, 4:]))
+            return dict.__getitem__(self, "mtx")
         if key not in ("rgb", "depth", "mask"):
             raise KeyError(key)
         r = self._owner._render_iteration(self._index)
@@ -641,6 +646,9 @@ class _LazyResult(dict):
 
     def __contains__(self, key):
         return key in ("rgb", "depth", "mask", "mtx") or dict.__contains__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
 
 
 @dataclass
@@ -820,9 +828,8 @@ class DiffDope:
         keys = {"rgb": "rgb", "depth": "depth", "mask": "mask_selection", "edge": "edge"}
         for k in kinds:
             self.losses_values[keys[k]] = lh[:, :, cols[k]].contiguous()
-        qn = ph[..., :4] / torch.norm(ph[..., :4], dim=-1, keepdim=True)
-        mtx = matrix_batch_44_from_position_quat(qn.reshape(-1, 4), ph[..., 4:].reshape(-1, 3)).reshape(ph.shape[0], B, 4, 4)
-        self.optimization_results = [_LazyResult(self, i, mtx[i]) for i in range(ph.shape[0])]
+        self._pose_hist_host = ph  # [iters, B, 7] host copy: 'mtx' of an iteration is built from it on first access
+        self.optimization_results = [_LazyResult(self, i) for i in range(ph.shape[0])]
         self.renders = self.optimization_results[-1]
 
     def _render_iteration(self, index, batch_index=None):
