@@ -245,3 +245,33 @@ def test_mesh_orientation_host_function_matches_oracle():
     for pos, tri, want in cases:
         assert c_side(pos, tri) == want == nvdr.closed_mesh_orientation(pos, tri)
     assert c_side(v, np.array([[0, 1, 99]], np.int32)) == 0  # out-of-range index: not classified, no crash
+
+
+def test_baseline_config_workloads_are_well_formed():
+    """tests/workloads.py: the stand-in workloads of BASELINE configs 3-5 have the sizes SURVEY.md 8(d) states, closed and
+    consistently oriented meshes (so the back-face rule applies), in-range uv and poses in front of the camera."""
+    import workloads as wl
+    from oracle import nvdr
+
+    c4 = wl.config4()
+    assert c4["pos"].shape == (5002, 3) and c4["tri"].shape == (10000, 3) and (c4["H"], c4["W"]) == (540, 720) and c4["B"] == 256
+    assert nvdr.closed_mesh_orientation(c4["pos"], c4["tri"]) == 1
+    assert np.allclose(np.abs(c4["pos"]).max(0), [0.5, 0.5, 0.3], atol=1e-3)
+    ang = 2 * np.degrees(np.arccos(abs(float(np.dot(c4["q0"], c4["q_gt"])))))
+    assert abs(ang - 10.0) < 1e-3 and abs(np.linalg.norm(c4["t0"] - c4["t_gt"]) - 0.04) < 1e-6
+    c5 = wl.config5(tex_size=64)
+    assert c5["pos"].shape == (25002, 3) and c5["tri"].shape == (50000, 3) and (c5["H"], c5["W"]) == (1024, 1024) and c5["B"] == 1024
+    assert nvdr.closed_mesh_orientation(c5["pos"], c5["tri"]) == 1
+    assert c5["uv"].min() >= 0 and c5["uv"].max() <= 1 and c5["tex"].shape == (64, 64, 3) and 0.3 < c5["tex"].mean() < 0.7
+    assert c5["losses"]["l1_edge"] and c5["t_gt"][2] < 0
+    c3 = wl.config3()
+    assert len(c3["objects"]) == 8 and (c3["H"], c3["W"]) == (480, 640) and c3["B"] == 128
+    scales = [np.abs(o["pos"]).max() for o in c3["objects"]]
+    assert np.allclose(np.array(scales) / scales[0], np.linspace(0.6, 1.3, 8) / 0.6, rtol=1e-5)
+    for o in c3["objects"]:
+        assert o["t_gt"][2] < -5 and abs(np.linalg.norm(o["q_gt"]) - 1) < 1e-5 and abs(np.linalg.norm(o["q0"]) - 1) < 1e-5
+    # cycled copies are shifted so that no two of the eight objects coincide
+    ts = np.array([o["t_gt"] for o in c3["objects"]])
+    assert min(np.linalg.norm(ts[i] - ts[j]) for i in range(8) for j in range(i)) > 0.1
+    tex = wl.procedural_texture(32, seed=0)
+    assert np.array_equal(tex, wl.procedural_texture(32, seed=0)) and tex.dtype == np.float32
