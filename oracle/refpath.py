@@ -10,7 +10,9 @@ published hand-written backward; `dd.xfm_points` follows `diffdope/c_src/mesh.cu
 PARITY UNPINNED for the nvdiffrast ops (see `oracle/nvdr.py`). The parts that live
 in the reference tree are pinned by tests/test_oracle_pins.py: SURVEY.md Appendix D, and golden
 vectors produced by the reference's own functions (pose -> matrix, projection, the three losses with
-their gradients, image loading; tests/golden/make_reference_vectors.py).
+their gradients, image loading; tests/golden/make_reference_vectors.py), and the output of the
+reference's own unmodified run_optimization loop executed on the CPU with the four nvdiffrast ops served
+by oracle/nvdr.py (tests/golden/make_reference_run.py).
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import this module.

@@ -257,3 +257,37 @@ def test_extension_config_keys_through_the_api():
     q1, t1 = c._pose_hist[1, :, :4].cpu(), c._pose_hist[1, :, 4:].cpu()
     lr0 = 0.01 * 0.1 ** 1.0
     assert np.allclose((q1 - q0).abs().numpy(), lr0, rtol=5e-3) and np.allclose((t1 - t0).abs().numpy(), lr0, rtol=5e-3)
+
+
+def test_api_matches_the_reference_loop_fixture():
+    """The product's DiffDope API on the GPU against tests/golden/reference_run.npz: the output of the reference's own,
+    unmodified run_optimization executed on the CPU (nvdiffrast ops served by the oracle; make_reference_run.py).
+    Same config, same seeded learning-rate draws, same start pose."""
+    import diffdope as dd
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_run.npz"))
+    cfg = _cfg(**{"scene.image_resize": float(g["resize"]), "hyperparameters.batchsize": 2, "hyperparameters.nb_iterations": 3,
+                  "hyperparameters.learning_rates_bound": [0.05, 0.5], "losses.l1_rgb_with_mask": True, "losses.l1_depth_with_mask": True,
+                  "losses.l1_mask": True})
+    random.seed(0)
+    d = dd.DiffDope(cfg=cfg)
+    assert np.allclose(d.learning_rates.cpu().numpy(), g["lr"])
+    q0, t0 = d.object3d.pose_tensors()
+    assert np.allclose(torch.cat([q0, t0], 1).cpu().numpy(), g["pose0"], atol=1e-6)
+    d.run_optimization()
+    assert list(d.losses_values.keys()) == list(g["loss_keys"])
+    H, W = d.resolution
+    for k in d.losses_values:
+        ours, ref = d.losses_values[k].numpy(), g["loss_" + k]
+        assert ours.shape == ref.shape
+        assert np.allclose(ours, ref, rtol=5e-4, atol=2.0 / (H * W)), k
+    qf, tf = d.object3d.pose_tensors()
+    assert np.abs(torch.cat([qf, tf], 1).cpu().numpy() - g["final"]).max() < 1e-4
+    assert int(d.get_argmin()) == int(g["argmin"])
+    assert np.abs(d.get_pose() - g["best_pose"]).max() < 1e-4
+    for i in range(4):
+        assert np.abs(d.optimization_results[i]["mtx"].numpy() - g["mtx"][i]).max() < 1e-4
+    res0 = d.optimization_results[0]
+    assert np.allclose(res0["rgb"].numpy()[:, ::7, ::9], g["rgb0_sample"], atol=1e-6)
+    assert np.allclose(res0["depth"].numpy()[:, ::7, ::9], g["depth0_sample"], atol=1e-5)
+    assert np.allclose(d.optimization_results[-1]["mask"].numpy()[:, ::7, ::9], g["mask_last_sample"], atol=1e-4)

@@ -663,3 +663,43 @@ def test_reference_vectors_image_loading(refvec):
             assert list(im.shape) == list(g["img_%s_shape" % key])
             assert np.allclose(float(im.astype(np.float64).sum()), float(g["img_%s_sum" % key]), rtol=1e-7)
             assert np.array_equal(im[::37, ::41], g["img_%s_sample" % key])
+
+
+REFRUN = os.path.join(os.path.dirname(__file__), "golden", "reference_run.npz")
+
+
+def test_oracle_reproduces_the_reference_loop_run_on_cpu():
+    """tests/golden/reference_run.npz is the output of the reference's own, unmodified `DiffDope.run_optimization`
+    (4 iterations, 2 hypotheses, rgb + depth + mask losses, quarter resolution) executed on the CPU with the four
+    nvdiffrast ops served by the oracle's restatements (make_reference_run.py). The oracle's restatement of
+    everything around those ops -- render-graph wiring, depth sign, background masking, loss structure, logging keys,
+    schedule over nb_iterations+1 steps, SGD on the raw parameters, argmin, get_pose -- must reproduce it."""
+    g = np.load(REFRUN)
+    assert list(g["loss_keys"]) == ["rgb", "depth", "mask_selection"]
+    arr = su.example_mesh_arrays()
+    gt = {k: torch.from_numpy(v) for k, v in su.example_targets(float(g["resize"])).items()}
+    H, W = gt["rgb"].shape[:2]
+    q, t = su.example_pose()
+    pose0 = g["pose0"]
+    assert np.allclose(pose0[:, :4], q, atol=1e-6) and np.allclose(pose0[:, 4:], t, atol=1e-6)
+    assert np.allclose(g["lr"], su.lr_multipliers(2, 0.05, 0.5))
+    cfg = dict(l1_rgb_with_mask=True, weight_rgb=0.7, l1_depth_with_mask=True, weight_depth=1.0, l1_mask=True, weight_mask=1.0)
+    hyper = dict(nb_iterations=3, base_lr=20.0, lr_decay=0.1, learning_rate_base=1)
+    for cull in (False, True):  # a GL context does not cull; the back-face rule must not change anything here
+        mesh = refpath.Mesh(arr["pos"], arr["tri"], arr["uv"], arr["tex"])
+        mesh.cull = cull
+        o = refpath.run_optimization(mesh, su.projection(), pose0[:, :4], pose0[:, 4:], gt, g["lr"], cfg, hyper, H, W)
+        for k in ("rgb", "depth", "mask_selection"):
+            assert o["losses"][k].shape == g["loss_" + k].shape == (4, 2)
+            assert np.allclose(o["losses"][k], g["loss_" + k], rtol=2e-6, atol=1e-10), k
+        assert np.abs(o["final"] - g["final"]).max() < 2e-6
+        assert np.abs(o["mtx"] - g["mtx"]).max() < 2e-6
+        assert refpath.argmin_hypothesis(o["losses"]) == int(g["argmin"])
+        assert np.abs(o["mtx"][-1][int(g["argmin"])] - g["best_pose"]).max() < 2e-6
+    # render conventions of the first iteration: background rgb 0, background depth = -t_z, mask in [0,1]
+    r = refpath.render(refpath.Mesh(arr["pos"], arr["tri"], arr["uv"], arr["tex"]), su.projection(), torch.from_numpy(pose0[:, :4]),
+                       torch.from_numpy(pose0[:, 4:]), H, W)
+    assert np.allclose(r["rgb"].numpy()[:, ::7, ::9], g["rgb0_sample"], atol=1e-6)
+    assert np.allclose(r["depth"].numpy()[:, ::7, ::9], g["depth0_sample"], atol=1e-5)
+    assert np.isclose(float(r["rgb"].double().sum()), float(g["rgb_sum"][0]), rtol=1e-6)
+    assert np.isclose(float(r["depth"].double().sum()), float(g["depth_sum"][0]), rtol=1e-6)
