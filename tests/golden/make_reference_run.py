@@ -27,7 +27,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-for p in (ROOT, os.path.join(ROOT, "diff-dope_b200"), os.path.join(ROOT, "diff-dope_b200", "compat"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "diff-dope_b200"), os.path.join(ROOT, "diff-dope_b200", "compat"), os.path.join(ROOT, "tests"), HERE):
     sys.path.insert(0, p)
 
 import make_reference_vectors as mrv  # noqa: E402  (the stand-in machinery)
@@ -103,6 +103,57 @@ def install_shims():
     torch.nn.Module.cuda = lambda self, *a, **k: self
 
 
+from cube_scenario import CUBE_C, CUBE_CAM, CUBE_F, CUBE_Q, CUBE_T, CUBE_V, cube_targets  # noqa: E402
+
+
+def run_untextured(ref, cfg_base):
+    """Second scenario: the vertex-colour branch (diffdope.py:229-231,1677-1686) on a cube, default loss config
+    (mask only) AND all three, 3 hypotheses x 3 iterations."""
+    import tempfile
+
+    import cv2
+    from omegaconf import OmegaConf
+
+    tmp = tempfile.mkdtemp()
+    ply = os.path.join(tmp, "cube.ply")
+    with open(ply, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 8\nproperty float x\nproperty float y\nproperty float z\nproperty uchar red\n"
+                "property uchar green\nproperty uchar blue\nelement face 12\nproperty list uchar int vertex_indices\nend_header\n")
+        for v, c in zip(CUBE_V, CUBE_C):
+            f.write("%.9g %.9g %.9g %d %d %d\n" % (v[0], v[1], v[2], c[0], c[1], c[2]))
+        for t in CUBE_F:
+            f.write("3 %d %d %d\n" % tuple(t))
+    rgb, depth, seg = cube_targets()
+    cv2.imwrite(os.path.join(tmp, "rgb.png"), rgb[..., ::-1])
+    cv2.imwrite(os.path.join(tmp, "depth.png"), depth)
+    cv2.imwrite(os.path.join(tmp, "seg.png"), seg)
+    out = {}
+    for tag, all_losses in (("cube_mask", False), ("cube_all", True)):
+        cfg = OmegaConf.create(OmegaConf.to_container(cfg_base))
+        cfg.camera = CUBE_CAM
+        cfg.scene.path_img, cfg.scene.path_depth, cfg.scene.path_segmentation = [os.path.join(tmp, n) for n in ("rgb.png", "depth.png", "seg.png")]
+        cfg.scene.image_resize = 1.0
+        cfg.losses.l1_rgb_with_mask = all_losses
+        cfg.losses.l1_depth_with_mask = all_losses
+        cfg.losses.l1_mask = True
+        cfg.hyperparameters.batchsize = 3
+        cfg.hyperparameters.nb_iterations = 2
+        cfg.hyperparameters.learning_rates_bound = [0.05, 0.5]
+        obj = ref.Object3D(position=list(CUBE_T / 0.01), rotation=list(CUBE_Q), batchsize=3, opencv2opengl=False, model_path=ply, scale=0.01)
+        random.seed(1)
+        d = ref.DiffDope(cfg=cfg, object3d=obj)
+        out[tag + "_lr"] = d.learning_rates.numpy().copy()
+        d.run_optimization()
+        out[tag + "_final"] = np.stack([getattr(obj, n).detach().numpy().copy() for n in ("qx", "qy", "qz", "qw", "x", "y", "z")], 1)
+        out[tag + "_keys"] = np.array(list(d.losses_values.keys()))
+        for k, v in d.losses_values.items():
+            out[tag + "_loss_" + k] = v.numpy()
+        out[tag + "_rgb0_sample"] = d.optimization_results[0]["rgb"][:, ::5, ::7].numpy()
+        out[tag + "_argmin"] = np.array(int(d.get_argmin()))
+        print(tag, "keys", list(d.losses_values.keys()), "final[0]", out[tag + "_final"][0])
+    return out
+
+
 def main():
     from omegaconf import OmegaConf  # the repo's stand-in (compat/)
 
@@ -146,6 +197,7 @@ def main():
                argmin=np.array(int(ddope.get_argmin())), best_pose=np.asarray(ddope.get_pose()),
                loss_keys=np.array(list(ddope.losses_values.keys())),
                **{"loss_" + k: v.numpy() for k, v in ddope.losses_values.items()})
+    out.update(run_untextured(ref, cfg))
     np.savez_compressed(os.path.join(HERE, "reference_run.npz"), **out)
     print("wrote reference_run.npz; keys", list(ddope.losses_values.keys()), "argmin", int(ddope.get_argmin()))
     print("losses first/last:", {k: (v[0].numpy(), v[-1].numpy()) for k, v in ddope.losses_values.items()})

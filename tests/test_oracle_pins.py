@@ -703,3 +703,43 @@ def test_oracle_reproduces_the_reference_loop_run_on_cpu():
     assert np.allclose(r["depth"].numpy()[:, ::7, ::9], g["depth0_sample"], atol=1e-5)
     assert np.isclose(float(r["rgb"].double().sum()), float(g["rgb_sum"][0]), rtol=1e-6)
     assert np.isclose(float(r["depth"].double().sum()), float(g["depth_sum"][0]), rtol=1e-6)
+
+
+def _cube_reference_scenario():
+    """Inputs of the untextured scenario of tests/golden/make_reference_run.py, as the reference's loaders produce them."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("cube_scenario", os.path.join(os.path.dirname(__file__), "golden", "cube_scenario.py"))
+    mrr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mrr)
+    rgb, depth, seg = mrr.cube_targets()
+    gt = dict(rgb=np.ascontiguousarray((rgb / 255.0)[::-1], dtype=np.float32), depth=np.ascontiguousarray((depth / 100)[::-1], dtype=np.float32),
+              segmentation=np.ascontiguousarray((seg / 255.0)[::-1], dtype=np.float32))
+    pos = (mrr.CUBE_V.astype(np.float32) * np.float32(0.01)).astype(np.float32)
+    col = (mrr.CUBE_C[..., :3] / 255.0).astype(np.float32)
+    c = mrr.CUBE_CAM
+    P = refpath.projection_matrix(c["fx"], c["fy"], c["cx"], c["cy"], c["im_width"], c["im_height"])
+    return dict(pos=pos, tri=mrr.CUBE_F, col=col, gt=gt, P=P, q=mrr.CUBE_Q.astype(np.float32), t=mrr.CUBE_T.astype(np.float32), H=mrr.CUBE_HW[0], W=mrr.CUBE_HW[1])
+
+
+def test_oracle_reproduces_the_reference_loop_untextured_branch():
+    """Same as above for the vertex-colour branch of the reference (`diffdope.py:229-231,1677-1686`, Mesh loader's else
+    branch), with the default loss configuration (mask only) and with all three losses; 3 hypotheses x 3 iterations."""
+    g = np.load(REFRUN)
+    s = _cube_reference_scenario()
+    gt = {k: torch.from_numpy(v) for k, v in s["gt"].items()}
+    mesh = refpath.Mesh(s["pos"], s["tri"], vtx_color=s["col"])
+    mesh.cull = False
+    for tag, cfg in (("cube_mask", dict(l1_mask=True, weight_mask=1.0)),
+                     ("cube_all", dict(l1_rgb_with_mask=True, weight_rgb=0.7, l1_depth_with_mask=True, weight_depth=1.0, l1_mask=True, weight_mask=1.0))):
+        assert list(g[tag + "_keys"]) == list(k for k in ("rgb", "depth", "mask_selection") if ("l1_rgb_with_mask" in cfg or k == "mask_selection"))
+        lr = g[tag + "_lr"]
+        assert np.allclose(lr, su.lr_multipliers(3, 0.05, 0.5, seed=1))
+        hyper = dict(nb_iterations=2, base_lr=20.0, lr_decay=0.1, learning_rate_base=1)
+        o = refpath.run_optimization(mesh, s["P"], np.tile(s["q"], (3, 1)), np.tile(s["t"], (3, 1)), gt, lr, cfg, hyper, s["H"], s["W"])
+        for k in g[tag + "_keys"]:
+            assert np.allclose(o["losses"][k], g[tag + "_loss_" + k], rtol=3e-6, atol=1e-10), (tag, k)
+        assert np.abs(o["final"] - g[tag + "_final"]).max() < 3e-6
+        assert refpath.argmin_hypothesis(o["losses"]) == int(g[tag + "_argmin"])
+    r = refpath.render(mesh, s["P"], torch.from_numpy(np.tile(s["q"], (3, 1))), torch.from_numpy(np.tile(s["t"], (3, 1))), s["H"], s["W"])
+    assert np.allclose(r["rgb"].numpy()[:, ::5, ::7], g["cube_all_rgb0_sample"], atol=1e-6)
