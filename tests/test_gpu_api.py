@@ -291,3 +291,48 @@ def test_api_matches_the_reference_loop_fixture():
     assert np.allclose(res0["rgb"].numpy()[:, ::7, ::9], g["rgb0_sample"], atol=1e-6)
     assert np.allclose(res0["depth"].numpy()[:, ::7, ::9], g["depth0_sample"], atol=1e-5)
     assert np.allclose(d.optimization_results[-1]["mask"].numpy()[:, ::7, ::9], g["mask_last_sample"], atol=1e-4)
+
+
+def test_api_matches_the_reference_loop_fixture_untextured(tmp_path):
+    """Vertex-colour branch: the product's API on the GPU (own PLY reader, own image loader, untextured kernels) against
+    the reference's unmodified loop run on the CPU (tests/golden/reference_run.npz, scenario cube_*)."""
+    import importlib.util
+
+    import cv2
+    import diffdope as dd
+    from omegaconf import OmegaConf
+
+    spec = importlib.util.spec_from_file_location("cube_scenario", os.path.join(os.path.dirname(__file__), "golden", "cube_scenario.py"))
+    cs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cs)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_run.npz"))
+    ply = str(tmp_path / "cube.ply")
+    with open(ply, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 8\nproperty float x\nproperty float y\nproperty float z\nproperty uchar red\n"
+                "property uchar green\nproperty uchar blue\nelement face 12\nproperty list uchar int vertex_indices\nend_header\n")
+        for v, c in zip(cs.CUBE_V, cs.CUBE_C):
+            f.write("%.9g %.9g %.9g %d %d %d\n" % (v[0], v[1], v[2], c[0], c[1], c[2]))
+        for t in cs.CUBE_F:
+            f.write("3 %d %d %d\n" % tuple(t))
+    rgb, depth, seg = cs.cube_targets()
+    cv2.imwrite(str(tmp_path / "rgb.png"), rgb[..., ::-1])
+    cv2.imwrite(str(tmp_path / "depth.png"), depth)
+    cv2.imwrite(str(tmp_path / "seg.png"), seg)
+    for tag, all_losses in (("cube_mask", False), ("cube_all", True)):
+        cfg = _cfg(**{"scene.image_resize": 1.0, "hyperparameters.batchsize": 3, "hyperparameters.nb_iterations": 2,
+                      "hyperparameters.learning_rates_bound": [0.05, 0.5], "losses.l1_rgb_with_mask": all_losses,
+                      "losses.l1_depth_with_mask": all_losses, "losses.l1_mask": True})
+        cfg.camera = OmegaConf.create(dict(cs.CUBE_CAM))
+        cfg.scene.path_img, cfg.scene.path_depth, cfg.scene.path_segmentation = str(tmp_path / "rgb.png"), str(tmp_path / "depth.png"), str(tmp_path / "seg.png")
+        obj = dd.Object3D(position=list(cs.CUBE_T / 0.01), rotation=list(cs.CUBE_Q), batchsize=3, opencv2opengl=False, model_path=ply, scale=0.01)
+        random.seed(1)
+        d = dd.DiffDope(cfg=cfg, object3d=obj)
+        assert np.allclose(d.learning_rates.cpu().numpy(), g[tag + "_lr"])
+        d.run_optimization()
+        assert list(d.losses_values.keys()) == list(g[tag + "_keys"])
+        for k in d.losses_values:
+            assert np.allclose(d.losses_values[k].numpy(), g[tag + "_loss_" + k], rtol=5e-4, atol=2.0 / (72 * 96)), (tag, k)
+        qf, tf = d.object3d.pose_tensors()
+        assert np.abs(torch.cat([qf, tf], 1).cpu().numpy() - g[tag + "_final"]).max() < 2e-4
+        assert int(d.get_argmin()) == int(g[tag + "_argmin"])
+        assert np.allclose(d.optimization_results[0]["rgb"].numpy()[:, ::5, ::7], g[tag + "_rgb0_sample"], atol=1e-6)
