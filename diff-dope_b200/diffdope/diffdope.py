@@ -242,9 +242,10 @@ def make_grid_overlay_batch(foreground, background=None, alpha=0.5, row=2, final
     if add_contour:
         cnts = cv2.findContours(gray, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
         cnts = cnts[0] if len(cnts) == 2 else cnts[1]
-        col = tuple(int(255 * c) for c in reversed(list(color_countour)))
+        # the reference draws (36, 255, 12) whatever `color_countour` says (`diffdope.py:514`): kept, so images look the same
         out = np.ascontiguousarray(out)
-        cv2.drawContours(out, list(cnts), -1, col, thickness=1, lineType=cv2.LINE_AA)
+        for c in cnts:
+            cv2.drawContours(out, [c], -1, (36, 255, 12), thickness=1, lineType=cv2.LINE_AA)
     if flip_result:
         out = cv2.flip(out, 0)
     return out

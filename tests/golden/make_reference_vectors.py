@@ -109,6 +109,19 @@ def main():
         out["img_%s_shape" % key] = np.array(im.shape)
         out["img_%s_sum" % key] = np.array(float(im.double().sum()))
         out["img_%s_sample" % key] = im[::37, ::41].numpy()
+    # visualisation helpers (diffdope.py:313-528): grid + overlay + contour of a small synthetic batch
+    yy, xx = np.mgrid[0:40, 0:56]
+    fg = np.zeros((3, 40, 56, 3), np.float32)
+    for k in range(3):
+        blob = ((yy - 18 - 2 * k) ** 2 + (xx - 25 - 3 * k) ** 2) < (9 + k) ** 2
+        fg[k][blob] = [0.9 - 0.2 * k, 0.3 + 0.2 * k, 0.5]
+    bg = rng.random((3, 40, 56, 3)).astype(np.float32)
+    out["viz_fg"], out["viz_bg"] = fg, bg
+    out["viz_overlay"] = ref.make_grid_overlay_batch(background=torch.from_numpy(bg), foreground=torch.from_numpy(fg), alpha=0.7, row=2, final_width=300,
+                                                     add_background=True, add_contour=True, color_countour=[0.46, 0.73, 0], flip_result=True)
+    out["viz_overlay_plain"] = ref.make_grid_overlay_batch(background=torch.from_numpy(bg), foreground=torch.from_numpy(fg), alpha=0.5, row=3, final_width=200,
+                                                           add_background=False, add_contour=True, flip_result=False)  # add_contour=False crashes in the reference (alpha_img unbound)
+    out["viz_grid"] = ref.make_grid(torch.from_numpy(fg).permute(0, 3, 1, 2), nrow=2).numpy()
     # schedule (formula at diffdope.py:1657-1661 with nb_iterations=60, base_lr=20, lr_decay=0.1)
     out["sched"] = np.array([20 * 0.1 ** (it / 60 + 1) for it in range(61)], dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)

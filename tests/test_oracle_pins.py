@@ -743,3 +743,22 @@ def test_oracle_reproduces_the_reference_loop_untextured_branch():
         assert refpath.argmin_hypothesis(o["losses"]) == int(g[tag + "_argmin"])
     r = refpath.render(mesh, s["P"], torch.from_numpy(np.tile(s["q"], (3, 1))), torch.from_numpy(np.tile(s["t"], (3, 1))), s["H"], s["W"])
     assert np.allclose(r["rgb"].numpy()[:, ::5, ::7], g["cube_all_rgb0_sample"], atol=1e-6)
+
+
+def test_reference_vectors_visualisation_helpers(refvec):
+    """`make_grid` / `make_grid_overlay_batch` (`diffdope.py:337-528`, the image side of render_img / make_animation):
+    the product's helpers produce the reference's images bit for bit on the same batch (grid layout, alpha overlay,
+    contour, flip, resize)."""
+    import diffdope as dd
+
+    g = refvec
+    fg, bg = torch.from_numpy(g["viz_fg"]), torch.from_numpy(g["viz_bg"])
+    a = dd.make_grid_overlay_batch(background=bg, foreground=fg, alpha=0.7, row=2, final_width=300, add_background=True, add_contour=True,
+                                   color_countour=[0.46, 0.73, 0], flip_result=True)
+    assert a.dtype == np.uint8 and np.array_equal(a, g["viz_overlay"])
+    b = dd.make_grid_overlay_batch(background=bg, foreground=fg, alpha=0.5, row=3, final_width=200, add_background=False, add_contour=True, flip_result=False)
+    assert np.array_equal(b, g["viz_overlay_plain"])
+    assert np.array_equal(dd.make_grid(fg.permute(0, 3, 1, 2), nrow=2).numpy(), g["viz_grid"])
+    # the reference crashes with add_contour=False (alpha_img unbound, diffdope.py:493-514); the product returns the plain overlay
+    c = dd.make_grid_overlay_batch(background=bg, foreground=fg, alpha=0.5, row=3, final_width=200, add_background=True, add_contour=False, flip_result=False)
+    assert c.shape == b.shape
