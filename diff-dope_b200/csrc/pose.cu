@@ -56,6 +56,17 @@ __device__ void hyp_pose_part(const SceneDev& S, const float* qb, const float* t
     const float detp = S.proj[0] * S.proj[5] - S.proj[1] * S.proj[4];
     const int sm = (detm > 0.f) - (detm < 0.f), sp = (detp > 0.f) - (detp < 0.f);
     h.face = S.cull_sign * sm * sp;
+    if (h.face != 0) {
+        // a camera inside the (bounding box of the) object sees back faces: nothing is culled for this hypothesis.
+        // camera centre in object space = -R^-1 t, R^-1 by the adjugate (M need not be rigid when given explicitly)
+        const float id = 1.f / detm;
+        const float tx = m[3], ty = m[7], tz = m[11];
+        const float cx = -id * ((m[5] * m[10] - m[6] * m[9]) * tx + (m[2] * m[9] - m[1] * m[10]) * ty + (m[1] * m[6] - m[2] * m[5]) * tz);
+        const float cy = -id * ((m[6] * m[8] - m[4] * m[10]) * tx + (m[0] * m[10] - m[2] * m[8]) * ty + (m[2] * m[4] - m[0] * m[6]) * tz);
+        const float cz = -id * ((m[4] * m[9] - m[5] * m[8]) * tx + (m[1] * m[8] - m[0] * m[9]) * ty + (m[0] * m[5] - m[1] * m[4]) * tz);
+        const bool outside = cx < S.bbmin[0] || cx > S.bbmax[0] || cy < S.bbmin[1] || cy > S.bbmax[1] || cz < S.bbmin[2] || cz > S.bbmax[2];
+        if (!outside) h.face = 0;  // also taken when the position is NaN
+    }
     h.pad[0] = h.pad[1] = h.pad[2] = 0;
 }
 

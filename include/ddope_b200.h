@@ -147,7 +147,7 @@ int ddope_scene_set_window(ddope_scene* s, int y0, int x0, int h, int w);
  * rasterised. They can never be the front-most surface, so coverage is unchanged; compared with the reference's
  * GL context (no culling, diffdope/diffdope.py:1312) the winning triangle can differ only where a back and a front
  * face tie in depth within float rounding on a silhouette. mode 0 = rasterise every triangle. Open or inconsistently
- * oriented meshes are never culled. ddope_scene_mesh_orientation: +1 / -1 (closed, positive / negative volume) or 0. */
+ * oriented meshes are never culled, nor is a hypothesis whose camera centre lies inside the object's bounding box. ddope_scene_mesh_orientation: +1 / -1 (closed, positive / negative volume) or 0. */
 int ddope_scene_set_culling(ddope_scene* s, int mode);
 int ddope_scene_mesh_orientation(const ddope_scene* s);
 /* The same classification for host arrays (pos [V,3], tri [T,3]); pure host code, needs no GPU. */

@@ -230,14 +230,23 @@ def closed_mesh_orientation(pos, tri):
     return int(np.sign(vol))
 
 
-def face_signs(cull_sign, proj, M):
+def face_signs(cull_sign, proj, M, bbmin=None, bbmax=None):
     """Sign of the snapped window-space area of a FRONT-facing triangle per batch entry: mesh orientation x
-    orientation of the camera-to-window map x orientation of the model matrix (0 = do not cull)."""
+    orientation of the camera-to-window map x orientation of the model matrix (0 = do not cull). A camera inside
+    the object's bounding box (bbmin / bbmax, object space) sees back faces: 0 for that entry."""
     P = np.asarray(proj, dtype=np.float64)
     M = np.asarray(M, dtype=np.float64)
     dp = np.sign(P[0, 0] * P[1, 1] - P[0, 1] * P[1, 0])
     dm = np.sign(np.linalg.det(M[:, :3, :3]))
-    return (cull_sign * dp * dm).astype(np.int64)
+    face = (cull_sign * dp * dm).astype(np.int64)
+    if bbmin is not None:
+        for b in range(M.shape[0]):
+            if face[b] != 0:
+                cam = -np.linalg.solve(M[b, :3, :3], M[b, :3, 3])
+                outside = (cam < np.asarray(bbmin, np.float64)).any() or (cam > np.asarray(bbmax, np.float64)).any()
+                if not outside:
+                    face[b] = 0
+    return face
 
 
 def rasterize(clip, tri, H, W, face_sign=None):

@@ -212,7 +212,7 @@ def render(mesh, proj, quat_raw, trans, H, W):
     pos = torch.from_numpy(mesh.pos)
     pos_b = pos[None].expand(B, -1, -1)
     pos_clip = xfm_points(pos_b, mvp)
-    face = nvdr.face_signs(mesh.cull_sign if mesh.cull else 0, proj, M_c)
+    face = nvdr.face_signs(mesh.cull_sign if mesh.cull else 0, proj, M_c, mesh.pos.min(0), mesh.pos.max(0))
     rast = _Rasterize.apply(pos_clip, mesh.tri, H, W, face)
 
     posw = torch.cat([pos, torch.ones(pos.shape[0], 1)], dim=1)

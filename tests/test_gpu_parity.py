@@ -357,6 +357,22 @@ def test_backface_culling_rule(ex_half):
     finally:
         ex.sc.set_culling(True)
     assert (a[3][..., 3] > 0).sum() > 1000 and torch.equal(a[3][..., 3] > 0, b[3][..., 3] > 0)
+    # camera inside the object's bounding box: back faces are what it sees, nothing may be culled (bit-exact vs the oracle)
+    from oracle import refpath
+
+    v = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], dtype=np.float32) * 2.0
+    f = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]], dtype=np.int32)
+    col = np.random.default_rng(3).random((8, 3)).astype(np.float32)
+    P = refpath.projection_matrix(60.0, 60.0, 48.0, 32.0, 96, 64)
+    cube = n.NativeScene(v, f, vtx_color=col)
+    assert cube.mesh_orientation() == 1
+    cube.set_camera(P, 64, 96)
+    q2 = np.array([[0.1, 0.2, 0.05, 0.97], [0.1, 0.2, 0.05, 0.97]], dtype=np.float32)
+    t2 = np.array([[0.1, 0.0, -0.3], [0.0, 0.0, -9.0]], dtype=np.float32)
+    og = cube.render(torch.from_numpy(q2).cuda(), torch.from_numpy(t2).cuda(), want=("rast", "rgb"))
+    oo = refpath.render(refpath.Mesh(v, f, vtx_color=col), P, torch.from_numpy(q2), torch.from_numpy(t2), 64, 96)
+    assert float((og["rast"][0, ..., 3] > 0).float().mean()) > 0.5
+    assert np.array_equal(oo["rast_out"].numpy(), og["rast"].cpu().numpy()) and np.array_equal(oo["rgb"].numpy(), og["rgb"].cpu().numpy())
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])

@@ -428,6 +428,14 @@ def test_closed_mesh_detection_and_culling_preserves_coverage():
     M = np.eye(4)[None].repeat(2, 0)
     M[1, 0, 0] = -1
     assert list(nvdr.face_signs(1, P, M)) == [1, -1]
+    # a camera inside the object's bounding box sees back faces: nothing is culled for that hypothesis
+    big = refpath.Mesh(v * 4, f, vtx_color=col)  # cube of half-size 2
+    q2 = np.array([[0.1, 0.2, 0.05, 0.97], [0.1, 0.2, 0.05, 0.97]], dtype=np.float32)
+    t2 = np.array([[0.1, 0.0, -0.3], [0.0, 0.0, -9.0]], dtype=np.float32)
+    _, M2 = nvdr.canonical_pose(q2, t2)
+    assert list(nvdr.face_signs(1, P, M2, big.pos.min(0), big.pos.max(0))) == [0, 1]
+    r2 = refpath.render(big, P, torch.from_numpy(q2), torch.from_numpy(t2), 64, 96)["rast_out"].numpy()
+    assert (r2[0, ..., 3] > 0).mean() > 0.5 and (r2[1, ..., 3] > 0).mean() > 0.02
 
 
 # ----------------------------------------------------------------------------------------------
