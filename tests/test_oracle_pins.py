@@ -770,3 +770,49 @@ def test_reference_vectors_visualisation_helpers(refvec):
     # the reference crashes with add_contour=False (alpha_img unbound, diffdope.py:493-514); the product returns the plain overlay
     c = dd.make_grid_overlay_batch(background=bg, foreground=fg, alpha=0.5, row=3, final_width=200, add_background=True, add_contour=False, flip_result=False)
     assert c.shape == b.shape
+
+
+def test_textured_interior_gradient_matches_finite_differences():
+    """The texture -> interpolate -> rasterize -> xfm backward chain of the oracle against central finite differences, on
+    a smooth texture and a loss restricted to interior pixels (3 px away from the silhouette at every probed pose), where
+    the render is a smooth function of the pose. All seven pose parameters."""
+    v = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0], [0, 0, 0.3]], dtype=np.float32)
+    f = np.array([[0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4]])  # a shallow pyramid: four faces, non-trivial barycentrics
+    uv = np.array([[0.1, 0.1], [0.9, 0.1], [0.9, 0.9], [0.1, 0.9], [0.5, 0.5]], dtype=np.float32)
+    ty, tx = np.mgrid[0:64, 0:64] / 64.0
+    tex = np.stack([0.5 + 0.4 * np.sin(5 * tx + 2 * ty), 0.5 + 0.4 * np.cos(4 * ty - tx), 0.5 + 0.3 * np.sin(3 * tx * ty + 1)], -1).astype(np.float32)
+    mesh = refpath.Mesh(v, f, uv=uv, tex=tex)
+    H, W = 72, 96
+    P = refpath.projection_matrix(130.0, 130.0, 48.0, 36.0, W, H)
+    q0 = np.array([[0.12, -0.09, 0.05, 0.985]], dtype=np.float64)
+    t0 = np.array([[0.05, -0.03, -5.0]], dtype=np.float64)
+    base = refpath.render(mesh, P, torch.tensor(q0, dtype=torch.float32), torch.tensor(t0, dtype=torch.float32), H, W)
+    cov = base["rast_out"][0, ..., 3].numpy() > 0
+    import cv2
+
+    interior = cv2.erode(cov.astype(np.uint8), np.ones((9, 9), np.uint8)).astype(bool)  # 4 px inside the silhouette
+    assert interior.sum() > 600
+    yy, xx = np.mgrid[0:H, 0:W]
+    wgt = torch.tensor((interior * (1.0 + 0.5 * np.sin(xx / 6.0) * np.cos(yy / 5.0)))[..., None].astype(np.float32) * np.array([1.0, -0.7, 0.4], np.float32))
+
+    def L(q, t, grad=False):
+        qq = torch.tensor(q, dtype=torch.float32, requires_grad=True)
+        tt = torch.tensor(t, dtype=torch.float32, requires_grad=True)
+        r = refpath.render(mesh, P, qq, tt, H, W)
+        l = (r["rgb"][0] * wgt).sum() + 0.3 * (r["depth"][0] * wgt[..., 0]).sum()
+        if grad:
+            l.backward()
+            return float(l.detach()), np.concatenate([qq.grad.numpy()[0], tt.grad.numpy()[0]])
+        return float(l.detach())
+
+    _, g = L(q0, t0, True)
+    h = 2e-3
+    fd = []
+    for i in range(7):
+        qp, qm, tp, tm = q0.copy(), q0.copy(), t0.copy(), t0.copy()
+        (qp if i < 4 else tp)[0, i % 4 if i < 4 else i - 4] += h
+        (qm if i < 4 else tm)[0, i % 4 if i < 4 else i - 4] -= h
+        fd.append((L(qp, tp) - L(qm, tm)) / (2 * h))
+    fd = np.array(fd)
+    # the texture is piecewise bilinear: allow 3 % of the largest component
+    assert np.abs(g - fd).max() < 0.03 * np.abs(fd).max(), (g, fd)
