@@ -816,3 +816,44 @@ def test_textured_interior_gradient_matches_finite_differences():
     fd = np.array(fd)
     # the texture is piecewise bilinear: allow 3 % of the largest component
     assert np.abs(g - fd).max() < 0.03 * np.abs(fd).max(), (g, fd)
+
+
+def test_antialias_gradient_closed_form_centroid_shift():
+    """The silhouette gradient (restated AntialiasGradKernel + everything upstream of it) on a fronto-parallel rectangle:
+    sum_px x*mask = area * centroid_x in the continuous picture, so d/dt_x ~ area * fx / depth pixels per unit and
+    sum_px mask (= area) is invariant under a sideways translation. The analytic gradient must agree with a central
+    finite difference of the oracle's own forward pass and with the continuous value, both to 2 % of that value (the
+    remainder comes from the four corner pixels, where the pairwise blend is neither an exact area nor exactly
+    differentiated by the published gradient kernel)."""
+    H, W = 56, 80
+    fx = fy = 90.0
+    P = refpath.projection_matrix(fx, fy, 40.0, 28.0, W, H).astype(np.float64)
+    d = 3.0
+    x0, x1, y0, y1 = 20.3, 60.7, 10.4, 40.6
+
+    def cam(px, py):
+        nx, ny = px / W * 2 - 1, py / H * 2 - 1
+        return [(nx + P[0, 2]) * d / P[0, 0], (ny + P[1, 2]) * d / P[1, 1], 0.0]
+
+    v = np.array([cam(x0, y0), cam(x1, y0), cam(x1, y1), cam(x0, y1)], dtype=np.float32)
+    f = np.array([[0, 1, 2], [0, 2, 3]])
+    mesh = refpath.Mesh(v, f, vtx_color=np.ones((4, 3), np.float32))
+    yy, xx = np.mgrid[0:H, 0:W]
+    area = (x1 - x0) * (y1 - y0)
+    scale = area * fx / d
+
+    def value(wimg, tx, ty):
+        q = torch.tensor([[0.0, 0.0, 0.0, 1.0]])
+        t = torch.tensor([[tx, ty, -d]], dtype=torch.float32)
+        return float((refpath.render(mesh, P, q, t, H, W)["mask"][0, ..., 0] * wimg).sum())
+
+    for wnp, ideal in ((xx + 0.5, [scale, 0.0]), (yy + 0.5, [0.0, scale]), (np.ones((H, W)), [0.0, 0.0])):
+        wimg = torch.tensor(wnp.astype(np.float32))
+        q = torch.tensor([[0.0, 0.0, 0.0, 1.0]], requires_grad=True)
+        t = torch.tensor([[0.0, 0.0, -d]], requires_grad=True)
+        (refpath.render(mesh, P, q, t, H, W)["mask"][0, ..., 0] * wimg).sum().backward()
+        got = t.grad.numpy()[0, :2]
+        h = 2e-3
+        fd = np.array([(value(wimg, h, 0.0) - value(wimg, -h, 0.0)) / (2 * h), (value(wimg, 0.0, h) - value(wimg, 0.0, -h)) / (2 * h)])
+        assert np.allclose(got, fd, rtol=1e-3, atol=0.02 * scale), (got, fd)
+        assert np.allclose(got, ideal, rtol=0.02, atol=0.02 * scale), (got, ideal)
