@@ -42,7 +42,7 @@ def _gather_dim(t_local, B, dim, per, ws):
 
 
 def gather_hypotheses(B, pose_hist, loss_hist, final):
-    """pose_hist [n,Bl,7], loss_hist [n,Bl,3], final [Bl,7] -> global [n,B,7], [n,B,3], [B,7]."""
+    """pose_hist [n,Bl,7], loss_hist [n,Bl,K], final [Bl,7] -> global [n,B,7], [n,B,K], [B,7]."""
     rank, ws = world()
     if ws == 1:
         return pose_hist, loss_hist, final
