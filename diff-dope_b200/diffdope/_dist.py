@@ -2,7 +2,7 @@
 
 Hypotheses are independent, so rank r of G refines the contiguous block
 [lo, hi) of the B hypotheses with the *global* B kept in the loss-mean divisor; the only
-communication is one all-gather of the per-hypothesis tables at the end of the run, after
+communication is ONE all-gather of the packed per-hypothesis tables at the end of the run, after
 which every rank holds the same full tables and computes the same argmin.
 With `torch.distributed` uninitialised (or world_size 1) everything is a no-op."""
 import torch
@@ -42,12 +42,17 @@ def _gather_dim(t_local, B, dim, per, ws):
 
 
 def gather_hypotheses(B, pose_hist, loss_hist, final):
-    """pose_hist [n,Bl,7], loss_hist [n,Bl,K], final [Bl,7] -> global [n,B,7], [n,B,K], [B,7]."""
+    """pose_hist [n,Bl,7], loss_hist [n,Bl,K], final [Bl,7] -> global [n,B,7], [n,B,K], [B,7].
+    ONE all-gather: the three tables travel packed as [n+1, Bl, 7+K] (the final poses are the extra row)."""
     rank, ws = world()
     if ws == 1:
         return pose_hist, loss_hist, final
     per = (B + ws - 1) // ws
-    return (_gather_dim(pose_hist, B, 1, per, ws), _gather_dim(loss_hist, B, 1, per, ws), _gather_dim(final, B, 0, per, ws))
+    n, K = pose_hist.shape[0], loss_hist.shape[2]
+    last = torch.cat([final, final.new_zeros(final.shape[0], K)], dim=1).unsqueeze(0)
+    packed = torch.cat([torch.cat([pose_hist, loss_hist], dim=2), last], dim=0)
+    allp = _gather_dim(packed, B, 1, per, ws)
+    return allp[:n, :, :7].contiguous(), allp[:n, :, 7:].contiguous(), allp[n, :, :7].contiguous()
 
 
 def broadcast_from_rank0(t):
