@@ -275,3 +275,20 @@ def test_baseline_config_workloads_are_well_formed():
     assert min(np.linalg.norm(ts[i] - ts[j]) for i in range(8) for j in range(i)) > 0.1
     tex = wl.procedural_texture(32, seed=0)
     assert np.array_equal(tex, wl.procedural_texture(32, seed=0)) and tex.dtype == np.float32
+
+
+def test_bench_byte_model_matches_survey():
+    """bench.py's roofline numerator is SURVEY.md 8(d)'s algorithmic byte model for config 2: 23.99 MB per
+    hypothesis-iteration, split into the terms the pixel pass (17.10 MB) and the raster kernel (6.89 MB) move."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    m = bench.survey_bytes_per_hit()
+    assert abs(m["total"] / 1e6 - 23.99) < 0.01
+    assert abs(m["pixel_kernel"] / 1e6 - 17.10) < 0.01 and abs(m["raster_kernel"] / 1e6 - 6.89) < 0.01
+    assert abs(m["pixel_kernel"] + m["raster_kernel"] - m["total"]) < 1
+    assert bench.B_PER_GPU == 64 and bench.WINDOW == 640 and bench.METRIC.startswith("pose-hypotheses")
+    sched = bench.lr_schedule(200)
+    assert abs(sched[0] - 2.0) < 1e-12 and abs(sched[-1] - 0.2) < 1e-12
