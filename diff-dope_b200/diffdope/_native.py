@@ -281,7 +281,7 @@ class NativeScene:
         return loss, grad
 
     def optimize(self, quat, trans, lr_mult, lr_sched, cfg, b_global=None, keep_history=True):
-        """In-place SGD on quat [B,4] / trans [B,3]. Returns (pose_hist [n,B,7], loss_hist [n,B,3]) or (None, None)."""
+        """In-place SGD on quat [B,4] / trans [B,3]. Returns (pose_hist [n,B,7], loss_hist [n,B,4]) or (None, None)."""
         for t, n in ((quat, "quat"), (trans, "trans")):
             if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise RuntimeError("%s must be a contiguous cuda float32 tensor (updated in place)" % n)
@@ -293,6 +293,8 @@ class NativeScene:
         if keep_history:
             pose_hist = torch.empty(n, B, 7, device=quat.device)
             loss_hist = torch.empty(n, B, NUM_LOSSES, device=quat.device)
+        if B == 0:  # an empty shard (more ranks than hypotheses): nothing to enqueue, empty tables
+            return pose_hist, loss_hist
         _check(lib().ddope_optimize(self._h, _ptr(quat), _ptr(trans), _ptr(lr_mult), B, int(b_global or B), _hptr(sched), n,
                                     ctypes.byref(cfg), _ptr(pose_hist), _ptr(loss_hist), _stream()))
         return pose_hist, loss_hist

@@ -1,4 +1,4 @@
-"""CPU, world_size 2, gloo: the multi-GPU host logic (shard, all-gather of the result tables)."""
+"""CPU, world_size 2 and 4, gloo: the multi-GPU host logic (shard, all-gather of the result tables)."""
 import os
 import sys
 
@@ -28,18 +28,33 @@ def _worker(rank, world, port, B, out_dir):
     dist.destroy_process_group()
 
 
+def _run_world(tmp_path, world, B):
+    port = 29500 + (os.getpid() + 17 * B + 101 * world) % 2000
+    mp.spawn(_worker, args=(world, port, B, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(tmp_path, "r%d.pt" % r)) for r in range(world)]
+    n = 3
+    P = torch.arange(n * B * 7, dtype=torch.float32).reshape(n, B, 7)
+    L = torch.arange(n * B * 3, dtype=torch.float32).reshape(n, B, 3) * 0.5
+    F = torch.arange(B * 7, dtype=torch.float32).reshape(B, 7) + 100
+    for r in res:
+        assert torch.equal(r["P"], P) and torch.equal(r["L"], L) and torch.equal(r["F"], F)
+        assert torch.all(r["lr"] == 1.0)  # rank 0's draw is the job's
+    # the shards tile [0, B) in rank order; trailing ranks may be empty when B < world or B is ragged
+    assert res[0]["range"][0] == 0 and res[-1]["range"][1] == B
+    for a, b in zip(res[:-1], res[1:]):
+        assert a["range"][1] == b["range"][0] and a["range"][0] <= a["range"][1]
+    # every rank computes the same argmin from the gathered table
+    assert len({int(r["L"][-1].mean(-1).argmin()) for r in res}) == 1
+    return res
+
+
 def test_gather_hypotheses_world2(tmp_path):
     for B in (8, 7):
-        port = 29500 + (os.getpid() + B) % 2000
-        mp.spawn(_worker, args=(2, port, B, str(tmp_path)), nprocs=2, join=True)
-        res = [torch.load(os.path.join(tmp_path, "r%d.pt" % r)) for r in range(2)]
-        n = 3
-        P = torch.arange(n * B * 7, dtype=torch.float32).reshape(n, B, 7)
-        L = torch.arange(n * B * 3, dtype=torch.float32).reshape(n, B, 3) * 0.5
-        F = torch.arange(B * 7, dtype=torch.float32).reshape(B, 7) + 100
-        for r in res:
-            assert torch.equal(r["P"], P) and torch.equal(r["L"], L) and torch.equal(r["F"], F)
-            assert torch.all(r["lr"] == 1.0)  # rank 0's draw is the job's
-        assert res[0]["range"][0] == 0 and res[0]["range"][1] == res[1]["range"][0] and res[1]["range"][1] == B
-        # every rank computes the same argmin from the gathered table
-        assert int(res[0]["L"][-1].mean(-1).argmin()) == int(res[1]["L"][-1].mean(-1).argmin())
+        _run_world(tmp_path, 2, B)
+
+
+def test_gather_hypotheses_world4_ragged_and_empty_shards(tmp_path):
+    res = _run_world(tmp_path, 4, 5)  # shards of 2, 2, 1, 0 hypotheses
+    assert [r["range"] for r in res] == [(0, 2), (2, 4), (4, 5), (5, 5)]
+    res = _run_world(tmp_path, 4, 2)  # fewer hypotheses than ranks: two empty shards
+    assert [r["range"][1] - r["range"][0] for r in res] == [1, 1, 0, 0]
