@@ -1,4 +1,4 @@
-"""Minimal PLY mesh reader (ASCII and binary_little_endian).
+"""Minimal PLY mesh reader (ASCII, binary_little_endian and binary_big_endian).
 
 Replaces the `trimesh.load(path, force="mesh")` call of the reference
 (`diffdope/diffdope.py:784-842`) for the asset format its examples use: a PLY
@@ -62,7 +62,7 @@ def _parse_header(f):
                 elements[-1][2].append((tok[2], "scalar", tok[1]))
         elif tok[0] == "end_header":
             break
-    if fmt not in ("ascii", "binary_little_endian"):
+    if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
         raise ValueError("unsupported PLY format %r" % fmt)
     return fmt, elements, texture_file
 
@@ -73,6 +73,56 @@ def _triangulate(polys):
         for k in range(1, len(p) - 1):
             tris.append((p[0], p[k], p[k + 1]))
     return np.asarray(tris, dtype=np.int64).reshape(-1, 3)
+
+
+def _read_binary_lists(f, count, props, bo):
+    """Rows of a binary element that holds list properties. Meshes store a constant number of corners per face, so the
+    whole element is first tried as one fixed-size record array (the count fields must all equal the first row's);
+    mixed polygon sizes fall back to a row-by-row read."""
+    lists = {p[0]: [] for p in props if p[1] == "list"}
+    if count == 0:
+        return lists
+    start = f.tell()
+    # sizes of the first row
+    first, fields = [], []
+    for i, p in enumerate(props):
+        if p[1] == "list":
+            cdt = np.dtype(bo + _PLY_DTYPES[p[2]])
+            n = int(np.frombuffer(f.read(cdt.itemsize), dtype=cdt)[0])
+            f.seek(np.dtype(_PLY_DTYPES[p[3]]).itemsize * n, 1)
+            first.append(n)
+            fields += [("c%d" % i, cdt), ("v%d" % i, bo + _PLY_DTYPES[p[3]], (n,))]
+        else:
+            f.seek(np.dtype(_PLY_DTYPES[p[2]]).itemsize, 1)
+            fields.append(("s%d" % i, bo + _PLY_DTYPES[p[2]]))
+    f.seek(start)
+    dt = np.dtype(fields)
+    buf = f.read(dt.itemsize * count)
+    if len(buf) == dt.itemsize * count:
+        arr = np.frombuffer(buf, dtype=dt, count=count)
+        k = 0
+        uniform = True
+        for i, p in enumerate(props):
+            if p[1] == "list":
+                uniform = uniform and bool(np.all(arr["c%d" % i] == first[k]))
+                k += 1
+        if uniform:
+            for i, p in enumerate(props):
+                if p[1] == "list":
+                    lists[p[0]] = arr["v%d" % i].astype(np.int64 if np.dtype(_PLY_DTYPES[p[3]]).kind in "iu" else np.float64).tolist()
+            return lists
+    f.seek(start)
+    for _ in range(count):
+        for p in props:
+            if p[1] == "list":
+                cdt = np.dtype(bo + _PLY_DTYPES[p[2]])
+                idt = np.dtype(bo + _PLY_DTYPES[p[3]])
+                n = int(np.frombuffer(f.read(cdt.itemsize), dtype=cdt)[0])
+                vals = np.frombuffer(f.read(idt.itemsize * n), dtype=idt)
+                lists[p[0]].append([int(v) for v in vals] if idt.kind in "iu" else [float(v) for v in vals])
+            else:
+                f.seek(np.dtype(_PLY_DTYPES[p[2]]).itemsize, 1)
+    return lists
 
 
 def load_ply(path, load_texture=True):
@@ -100,23 +150,13 @@ def load_ply(path, load_texture=True):
                                 c += 1
                     data[name] = lists
             else:
+                bo = "<" if fmt == "binary_little_endian" else ">"
                 if not has_list:
-                    dt = np.dtype([(p[0], "<" + _PLY_DTYPES[p[2]]) for p in props])
+                    dt = np.dtype([(p[0], bo + _PLY_DTYPES[p[2]]) for p in props])
                     arr = np.frombuffer(f.read(dt.itemsize * count), dtype=dt, count=count)
                     data[name] = {p[0]: arr[p[0]].astype(np.float64) for p in props}
                 else:
-                    lists = {p[0]: [] for p in props if p[1] == "list"}
-                    for _ in range(count):
-                        for p in props:
-                            if p[1] == "list":
-                                cdt = np.dtype("<" + _PLY_DTYPES[p[2]])
-                                idt = np.dtype("<" + _PLY_DTYPES[p[3]])
-                                n = int(np.frombuffer(f.read(cdt.itemsize), dtype=cdt)[0])
-                                vals = np.frombuffer(f.read(idt.itemsize * n), dtype=idt)
-                                lists[p[0]].append([int(v) for v in vals])
-                            else:
-                                f.read(np.dtype(_PLY_DTYPES[p[2]]).itemsize)
-                    data[name] = lists
+                    data[name] = _read_binary_lists(f, count, props, bo)
 
     v = data["vertex"]
     mesh.vertices = np.stack([v["x"], v["y"], v["z"]], axis=1)

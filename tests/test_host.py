@@ -107,6 +107,42 @@ def test_ply_ascii_and_binary_roundtrip(tmp_path):
         assert m.faces.tolist() == [[0, 1, 2], [0, 1, 3], [0, 3, 2]]  # quad fan-triangulated
 
 
+def test_ply_binary_variants(tmp_path):
+    """binary_big_endian, all-triangle faces (vectorised read) with an extra scalar and a per-face texcoord list, empty face element."""
+    from diffdope._ply import load_ply
+
+    verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.5]], dtype=np.float32)
+    faces = [[0, 1, 2], [1, 3, 2], [0, 3, 1]]
+    for bo, fmt in (("<", "binary_little_endian"), (">", "binary_big_endian")):
+        header = ("ply\nformat %s 1.0\ncomment TextureFile missing.png\nelement vertex 4\nproperty double x\nproperty double y\nproperty double z\n"
+                  "property float nx\nproperty float ny\nproperty float nz\nelement face 3\nproperty uchar flags\n"
+                  "property list uchar uint vertex_index\nproperty list uchar float texcoord\nend_header\n" % fmt)
+        p = tmp_path / (fmt + ".ply")
+        with open(p, "wb") as f:
+            f.write(header.encode())
+            for v in verts:
+                f.write(struct.pack(bo + "3d3f", *[float(x) for x in v], 0.0, 0.0, 1.0))
+            for k, fc in enumerate(faces):
+                f.write(struct.pack(bo + "BB3IB6f", k, 3, *fc, 6, *[0.1 * k + 0.01 * j for j in range(6)]))
+        m = load_ply(str(p))
+        assert np.array_equal(m.vertices, verts.astype(np.float64))
+        assert np.array_equal(m.vertex_normals, np.tile([0.0, 0.0, 1.0], (4, 1)))
+        assert m.faces.tolist() == faces and m.faces.dtype == np.int64
+        assert m.texture_file == "missing.png" and m.texture_image is None and m.uv is None
+    # no faces at all
+    p = tmp_path / "points.ply"
+    with open(p, "wb") as f:
+        f.write(b"ply\nformat binary_little_endian 1.0\nelement vertex 1\nproperty float x\nproperty float y\nproperty float z\n"
+                b"element face 0\nproperty list uchar int vertex_indices\nend_header\n")
+        f.write(struct.pack("<3f", 1, 2, 3))
+    m = load_ply(str(p))
+    assert m.vertices.tolist() == [[1.0, 2.0, 3.0]] and m.faces.shape == (0, 3)
+    with pytest.raises(ValueError):
+        q = tmp_path / "bad.ply"
+        q.write_bytes(b"plx\n")
+        load_ply(str(q))
+
+
 def test_quaternion_helpers_match_scipy():
     from scipy.spatial.transform import Rotation as R
 
