@@ -2,8 +2,10 @@
 
 Hypotheses are independent, so rank r of G refines the contiguous block
 [lo, hi) of the B hypotheses with the *global* B kept in the loss-mean divisor; the only
-communication is ONE all-gather of the packed per-hypothesis tables at the end of the run, after
-which every rank holds the same full tables and computes the same argmin.
+communication of a run is ONE all-gather of the packed per-hypothesis tables at its end, after
+which every rank holds the same full tables and computes the same argmin. (When the learning-rate
+multipliers are drawn, at construction / `set_batchsize`, rank 0's draw is broadcast once so the job
+does not depend on each process's `random` state.)
 With `torch.distributed` uninitialised (or world_size 1) everything is a no-op."""
 import torch
 import torch.distributed as dist
@@ -56,8 +58,14 @@ def gather_hypotheses(B, pose_hist, loss_hist, final):
 
 
 def broadcast_from_rank0(t):
-    """Make rank 0's tensor (e.g. the randomly drawn learning-rate multipliers) the job's."""
+    """Make rank 0's tensor (the randomly drawn learning-rate multipliers) the job's, in place: every rank then
+    refines its block with the multipliers a single-GPU run with rank 0's `random` state would have drawn."""
     rank, ws = world()
     if ws > 1:
-        dist.broadcast(t, src=0)
+        if t.is_cuda and dist.get_backend() != "nccl":  # e.g. gloo in the CPU tests: stage through the host
+            h = t.cpu()
+            dist.broadcast(h, src=0)
+            t.copy_(h)
+        else:
+            dist.broadcast(t, src=0)
     return t

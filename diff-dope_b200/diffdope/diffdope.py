@@ -715,6 +715,9 @@ class DiffDope:
         self.optimizer = self._make_optimizer()
         lo, hi = self.cfg.hyperparameters.learning_rates_bound[0], self.cfg.hyperparameters.learning_rates_bound[1]
         self.learning_rates = torch.tensor([random.uniform(lo, hi) for _ in range(batchsize)]).float().cuda()
+        from . import _dist
+
+        _dist.broadcast_from_rank0(self.learning_rates)  # no-op unless torch.distributed is initialised with world_size > 1
 
     def cuda(self):
         self.object3d.cuda()
