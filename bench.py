@@ -342,6 +342,9 @@ def run_ours(args):
                  "the loss-ROI design touches far fewer DRAM bytes than the model (see traffic and DESIGN.md)" % (model["total"] / 1e6, model[dom] / 1e6, B),
         "kernel_ms_per_iteration": {k: v / max(n_prof, 1) for k, v in kms.items()},
     }
+    if traffic and dom_ms > 0:  # what the counters say the kernel really pulled from HBM (ncu capture) at the live kernel time
+        roofline["dram_gbs_from_traffic"] = float(traffic) / (dom_ms * 1e-3) / 1e9
+        roofline["dram_frac_from_traffic"] = roofline["dram_gbs_from_traffic"] / peak
 
     # ---- cpu baseline (bounded sample) ----------------------------------------------------------
     cpu = None
