@@ -309,7 +309,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
 
     # ---- e2e through the public API with host buffers -------------------------------------------
-    e2e = run_e2e(dev, K, B, B_global, rank, world, gt_host, lr_all, barrier)
+    e2e = run_e2e(dev, K, B, B_global, rank, world, gt_host, lr_all, barrier, raw=args.e2e_raw)
 
     if rank != 0:
         if world > 1:
@@ -375,9 +375,11 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(dev, K, B, B_global, rank, world, gt_host, lr_all, barrier):
+def run_e2e(dev, K, B, B_global, rank, world, gt_host, lr_all, barrier, raw=False):
     """K iterations through `DiffDope.run_optimization` with the target images, start poses and
-    learning-rate multipliers coming from pinned host memory and the result tables read back."""
+    learning-rate multipliers coming from pinned host memory and the result tables read back.
+    raw=True (--e2e-raw, off by default): the targets cross PCIe as the PNGs' uint8 / uint16 samples and are
+    converted on the device (`Image.set_raw`, bit-equal to the host pipeline) instead of as float32."""
     import torch.distributed as dist
     from omegaconf import OmegaConf
 
@@ -398,15 +400,30 @@ def run_e2e(dev, K, B, B_global, rank, world, gt_host, lr_all, barrier):
     H, W = gt_host["rgb"].shape[:2]
     ddope.window = su.centred_window(gt_host["segmentation"], WINDOW, H, W)
     pin = {k: torch.from_numpy(v).pin_memory() for k, v in gt_host.items()}
+    if raw:
+        import cv2
+
+        def samples(path, flag):
+            a = cv2.imread(path, flag)
+            a = a.view(np.int16) if a.dtype == np.uint16 else a
+            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+        pin = {"rgb": samples(cfg.scene.path_img, cv2.IMREAD_COLOR), "depth": samples(cfg.scene.path_depth, cv2.IMREAD_UNCHANGED),
+               "segmentation": samples(cfg.scene.path_segmentation, cv2.IMREAD_COLOR)}
     lr_pin = torch.from_numpy(lr_all.copy()).pin_memory()
     q0, t0 = ddope.object3d.pose_tensors()
     q_pin, t_pin = q0.cpu().pin_memory(), t0.cpu().pin_memory()
-    h2d = sum(v.numel() * 4 for v in pin.values()) + lr_pin.numel() * 4 + q_pin.numel() * 4 + t_pin.numel() * 4
+    h2d = sum(v.numel() * v.element_size() for v in pin.values()) + lr_pin.numel() * 4 + q_pin.numel() * 4 + t_pin.numel() * 4
 
     def job():
-        ddope.scene.tensor_rgb.img_tensor = pin["rgb"].to(dev, non_blocking=True)
-        ddope.scene.tensor_depth.img_tensor = pin["depth"].to(dev, non_blocking=True)
-        ddope.scene.tensor_segmentation.img_tensor = pin["segmentation"].to(dev, non_blocking=True)
+        if raw:
+            ddope.scene.tensor_rgb.set_raw(pin["rgb"], device=dev)
+            ddope.scene.tensor_depth.set_raw(pin["depth"], device=dev)
+            ddope.scene.tensor_segmentation.set_raw(pin["segmentation"], device=dev)
+        else:
+            ddope.scene.tensor_rgb.img_tensor = pin["rgb"].to(dev, non_blocking=True)
+            ddope.scene.tensor_depth.img_tensor = pin["depth"].to(dev, non_blocking=True)
+            ddope.scene.tensor_segmentation.img_tensor = pin["segmentation"].to(dev, non_blocking=True)
         for im in (ddope.scene.tensor_rgb, ddope.scene.tensor_depth, ddope.scene.tensor_segmentation):
             im._batchsize_set = False
             im.set_batchsize(B_global)
@@ -431,7 +448,8 @@ def run_e2e(dev, K, B, B_global, rank, world, gt_host, lr_all, barrier):
     total_ms = float(ms[1].item())  # wall clock of the whole call: host work is part of end-to-end
     d2h = K * B_global * (7 + 3) * 4
     return {"value": B_global * K / (total_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
-            "ms_per_step": total_ms / K, "api": "diffdope.DiffDope.run_optimization (host -> device -> host)"}
+            "ms_per_step": total_ms / K, "api": "diffdope.DiffDope.run_optimization (host -> device -> host)",
+            "targets_on_the_wire": "uint8 / uint16 samples, converted on the device" if raw else "float32"}
 
 
 def main():
@@ -441,6 +459,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-raw", action="store_true", help="e2e: upload the targets as integer samples (Image.set_raw)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -215,6 +215,29 @@ def test_camera_and_image_loading_follow_reference():
     assert np.array_equal(d.img_tensor.numpy(), su.example_targets(0.5)["depth"])
 
 
+def test_image_set_raw_is_bit_equal_to_the_host_pipeline():
+    """Extension: integer samples converted through a k/255.0 (k/depth_scale) table equal the cv2 float64 pipeline bit for bit."""
+    import cv2
+    import diffdope as dd
+
+    sc = os.path.join(su.DATA, "scene")
+    for name, depth in (("rgb.png", False), ("seg.png", False), ("depth.png", True)):
+        path = os.path.join(sc, name)
+        host = dd.Image(img_path=path, depth=depth)
+        raw = cv2.imread(path, cv2.IMREAD_UNCHANGED if depth else cv2.IMREAD_COLOR)
+        for src in (raw, torch.from_numpy(raw)):
+            im = dd.Image(depth=depth).set_raw(src)
+            assert im.img_tensor.dtype == torch.float32 and im.img_tensor.is_contiguous()
+            assert torch.equal(im.img_tensor, host.img_tensor)
+        assert torch.equal(dd.Image(depth=depth, flip_img=False).set_raw(raw).img_tensor, torch.flip(host.img_tensor, dims=[0]))
+    with pytest.raises(ValueError):
+        dd.Image(img_resize=0.5).set_raw(np.zeros((4, 4, 3), np.uint8))
+    with pytest.raises(ValueError):
+        dd.Image().set_raw(np.zeros((4, 4), np.uint8))
+    with pytest.raises(ValueError):
+        dd.Image(depth=True).set_raw(np.zeros((4, 4, 3), np.uint8))
+
+
 def test_mesh_and_object3d_follow_reference():
     import diffdope as dd
 
