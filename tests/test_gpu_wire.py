@@ -1,0 +1,44 @@
+"""GPU checks of the host-side edges added around the hot path: integer image samples converted on the device
+(`Image.set_raw`, extension) and the empty hypothesis shard of a rank that has nothing to refine."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+import scene_util as su
+
+pytestmark = pytest.mark.gpu
+
+
+def test_image_set_raw_on_the_device_equals_the_host_pipeline():
+    import diffdope as dd
+
+    sc = os.path.join(su.DATA, "scene")
+    for name, depth in (("rgb.png", False), ("seg.png", False), ("depth.png", True)):
+        path = os.path.join(sc, name)
+        host = dd.Image(img_path=path, depth=depth).img_tensor
+        raw = cv2.imread(path, cv2.IMREAD_UNCHANGED if depth else cv2.IMREAD_COLOR)
+        raw = raw.view(np.int16) if raw.dtype == np.uint16 else raw
+        pinned = torch.from_numpy(np.ascontiguousarray(raw)).pin_memory()
+        dev = dd.Image(depth=depth).set_raw(pinned, device="cuda").img_tensor
+        assert dev.is_cuda and dev.dtype == torch.float32 and dev.is_contiguous()
+        assert torch.equal(dev.cpu(), host)
+
+
+def test_empty_shard_enqueues_nothing():
+    from diffdope import _native as nat
+
+    arr = su.example_mesh_arrays()
+    gt = su.example_targets(0.25)
+    H, W = gt["rgb"].shape[:2]
+    sc = nat.NativeScene(arr["pos"], arr["tri"], arr["uv"], arr["tex"])
+    sc.set_camera(su.projection(), H, W)
+    g = {k: torch.from_numpy(v).cuda() for k, v in gt.items()}
+    sc.set_target(g["rgb"], g["depth"], g["segmentation"])
+    q = torch.empty(0, 4, device="cuda")
+    t = torch.empty(0, 3, device="cuda")
+    lr = torch.empty(0, device="cuda")
+    ph, lh = sc.optimize(q, t, lr, [1.0, 0.5, 0.25], nat.make_loss_cfg(True, True, True), b_global=4)
+    assert tuple(ph.shape) == (3, 0, 7) and tuple(lh.shape) == (3, 0, nat.NUM_LOSSES)
