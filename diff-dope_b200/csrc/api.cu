@@ -344,6 +344,7 @@ extern "C" int ddope_scene_set_target(ddope_scene* s, const float* rgb, const fl
     d.gt_rgb = rgb; d.gt_depth = depth; d.gt_seg = seg;
     s->gt_edge_dirty = true;
     d.seg_pix_stride = seg ? seg_c : 0;
+    d.seg_ch_stride = (seg && seg_c == 3) ? 1 : 0;  // a single-channel segmentation serves all three colour channels
     if (seg) {
         launch_seg_bbox(seg, d.H, d.W, seg_c, s->seg_bbox, (cudaStream_t)stream);
         CK(cudaGetLastError());

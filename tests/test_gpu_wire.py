@@ -42,3 +42,30 @@ def test_empty_shard_enqueues_nothing():
     lr = torch.empty(0, device="cuda")
     ph, lh = sc.optimize(q, t, lr, [1.0, 0.5, 0.25], nat.make_loss_cfg(True, True, True), b_global=4)
     assert tuple(ph.shape) == (3, 0, 7) and tuple(lh.shape) == (3, 0, nat.NUM_LOSSES)
+
+
+def test_three_channel_segmentation_with_differing_channels_matches_oracle():
+    """The reference multiplies per channel by a [H,W,3] segmentation (`diffdope.py:552-555,598`); its example's
+    channels are identical, so this case needs its own target: channel 1 switched off in the left half, channel 2 at
+    half weight."""
+    from oracle import refpath
+    from test_gpu_parity import ALL, Example, _cfg, _loss_table
+
+    ex = Example(0.5)
+    seg = ex.gt["segmentation"].copy()
+    seg[:, : ex.W // 2, 1] = 0.0
+    seg[..., 2] *= 0.5
+    ex.gt["segmentation"] = seg
+    ex.sc.set_target(ex.g["rgb"], ex.g["depth"], torch.from_numpy(seg).cuda())
+    B = 2
+    qs, ts = su.perturbed_poses(ex.q, ex.t, B)
+    lr = su.lr_multipliers(B)
+    loss, grad = ex.sc.loss_grad(torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda(), torch.from_numpy(lr).cuda(), _cfg(ex.n, ALL))
+    logged, gq, gtr, _ = refpath.forward_backward(ex.oracle_mesh(), ex.P, qs, ts, ex.gt_t(), lr, ALL, ex.H, ex.W)
+    assert np.allclose(loss.cpu().numpy(), _loss_table(logged, B), rtol=1e-4, atol=1e-10)
+    go, gg = np.concatenate([gq, gtr], 1), grad.cpu().numpy()
+    assert np.abs(go - gg).max() <= 1e-4 * np.abs(go).max()
+    # and it is a different problem from the identical-channel one
+    ex.sc.set_target(ex.g["rgb"], ex.g["depth"], ex.g["segmentation"])
+    loss_same, _ = ex.sc.loss_grad(torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda(), torch.from_numpy(lr).cuda(), _cfg(ex.n, ALL))
+    assert not np.allclose(loss.cpu().numpy()[:, [0, 2]], loss_same.cpu().numpy()[:, [0, 2]], rtol=1e-3)
