@@ -53,7 +53,6 @@ struct ddope_scene {
     size_t zbuf_cap = 0;
     float* partials = nullptr;
     size_t partials_cap = 0;
-    float* xfm_scratch = nullptr;
     int num_sms = 148;
     int64_t launches = 0;
     bool profiling = false;
@@ -81,10 +80,14 @@ extern "C" int64_t ddope_last_launch_count(const ddope_scene* s) { return s ? s-
 // ---------------------------------------------------------------------------------------------
 // renderutils_plugin replacements
 
-// scratch of ddope_xfm_bwd_mtx's two-stage reduction: one per host thread (the entry points are re-entrant like the
-// reference plugin's, c_src/torch_bindings.cpp:147; a buffer is only replaced after a device synchronisation in cudaFree)
-static thread_local float* g_xfm_scratch = nullptr;
-static thread_local size_t g_xfm_scratch_cap = 0;
+// scratch of ddope_xfm_bwd_mtx's two-stage reduction: one per (host thread, stream), so calls on different streams may
+// overlap and the entry points stay re-entrant like the reference plugin's (c_src/torch_bindings.cpp:147). A buffer is
+// only released through cudaFree, which synchronises the device first.
+struct XfmScratch {
+    float* ptr = nullptr;
+    size_t cap = 0;
+};
+static thread_local std::unordered_map<cudaStream_t, XfmScratch> g_xfm_scratch;
 
 extern "C" int ddope_xfm_fwd(const float* points, int Bp, int N, const float* matrix, int B, int is_points,
                              float* out, void* stream) {
@@ -116,12 +119,18 @@ extern "C" int ddope_xfm_bwd_mtx(const float* points, int Bp, int N, const float
         return 0;
     }
     size_t need = (size_t)B * xfm_bwd_mtx_blocks(N) * 16 * sizeof(float);
-    if (need > g_xfm_scratch_cap) {
-        if (g_xfm_scratch) CK(cudaFree(g_xfm_scratch));
-        CK(cudaMalloc(&g_xfm_scratch, need));
-        g_xfm_scratch_cap = need;
+    if (g_xfm_scratch.size() > 32 && g_xfm_scratch.find(st) == g_xfm_scratch.end()) {  // streams come and go: start over
+        for (auto& kv : g_xfm_scratch) cudaFree(kv.second.ptr);
+        g_xfm_scratch.clear();
     }
-    launch_xfm_bwd_mtx(points, Bp, N, grad, B, is_points, d_matrix, g_xfm_scratch, st);
+    XfmScratch& sc = g_xfm_scratch[st];
+    if (need > sc.cap) {
+        if (sc.ptr) CK(cudaFree(sc.ptr));
+        sc.ptr = nullptr; sc.cap = 0;
+        CK(cudaMalloc(&sc.ptr, need));
+        sc.cap = need;
+    }
+    launch_xfm_bwd_mtx(points, Bp, N, grad, B, is_points, d_matrix, sc.ptr, st);
     CK(cudaGetLastError());
     return 0;
 }
@@ -289,12 +298,13 @@ extern "C" int ddope_scene_destroy(ddope_scene* s) {
     if (!s) return 0;
     cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex4); cudaFree(s->vcol); cudaFree(s->gt_edge); cudaFree(s->adam_state); cudaFree(s->tripos); cudaFree(s->tricol);
     cudaFree(s->seg_bbox); cudaFree(s->total_tiles); cudaFree(s->hyp); cudaFree(s->zbuf); cudaFree(s->partials);
-    cudaFree(s->xfm_scratch); cudaFree(s->arrive);
+    cudaFree(s->arrive);
     for (int p = 0; p < ddope_scene::MAX_PARTS; p++) {
         if (s->part_stream[p]) cudaStreamDestroy(s->part_stream[p]);
         if (s->part_done[p]) cudaEventDestroy(s->part_done[p]);
     }
     if (s->fork_event) cudaEventDestroy(s->fork_event);
+    for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);  // a profile_begin without its profile_end
     delete s;
     return 0;
 }
