@@ -200,6 +200,23 @@ def test_hydra_shim_runs_a_main_with_overrides(tmp_path):
     assert "B 3 True" in out.stdout and "outputs" in out.stdout
 
 
+def test_reference_example_reaches_the_device_under_the_shims(tmp_path):
+    """The reference's own examples/simple_scene.py, unmodified, with the in-repo package and the hydra / omegaconf /
+    icecream stand-ins on the path: imports, config loading and `hydra.main` work, and without a GPU the first failure
+    is CUDA initialisation inside `DiffDope.__post_init__` -- not an import or config error. (With a GPU the same
+    script runs to the end: tests/test_gpu_api.py.)"""
+    ref = "/root/reference/examples/simple_scene.py"
+    if not os.path.exists(ref) or torch.cuda.is_available():
+        pytest.skip("needs the reference tree and no GPU")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(su.ROOT, "diff-dope_b200"), os.path.join(su.ROOT, "diff-dope_b200", "compat")]))
+    out = subprocess.run([sys.executable, ref, "hyperparameters.nb_iterations=2", "hydra.run.dir=%s" % tmp_path], capture_output=True, text=True,
+                         cwd=su.ROOT, env=env, timeout=300)
+    assert out.returncode != 0
+    assert "NVIDIA" in out.stderr or "CUDA" in out.stderr, out.stderr[-1500:]
+    assert "ImportError" not in out.stderr and "ModuleNotFoundError" not in out.stderr and "ConfigAttributeError" not in out.stderr
+    assert "__post_init__" in out.stderr
+
+
 def test_camera_and_image_loading_follow_reference():
     import diffdope as dd
 
