@@ -5,7 +5,7 @@ from . import _compat
 _compat.ensure()
 
 from .diffdope import *  # noqa: F401,F403,E402
-from .diffdope import (Camera, DiffDope, Image, Mesh, Object3D, Scene, dist_batch_lr, find_crop, interpolate,  # noqa: F401
+from .diffdope import (Camera, DiffDope, Image, Mesh, Object3D, Scene, dist_batch_lr, find_crop, getimg_stack, interpolate,  # noqa: F401
                        l1_depth_with_mask, l1_mask, l1_rgb_with_mask, make_grid, make_grid_image, make_grid_overlay_batch,
                        matrix_batch_44_from_position_quat, opencv_2_opengl, render_texture_batch,
                        l1_edge, run_optimization_batched, sobel_magnitude)  # the last three are extensions

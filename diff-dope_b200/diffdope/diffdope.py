@@ -193,14 +193,27 @@ def im_resize(image, width=None, height=None):
 
 
 @torch.no_grad()
-def make_grid(tensor, nrow=8, padding=2, pad_value=0.0):
-    """[B,C,H,W] -> [C, gridH, gridW] image grid (torchvision-style layout)."""
+def make_grid(tensor, nrow=8, padding=2, normalize=False, value_range=None, scale_each=False, pad_value=0.0):
+    """[B,C,H,W] -> [C, gridH, gridW] image grid (torchvision-style layout; same arguments, in the same order, as the
+    reference's copy of torchvision's function, `diffdope/diffdope.py:337-460`). normalize: map [lo, hi] -> [0, 1]
+    with lo / hi = `value_range`, or the minimum / maximum of the batch (of each image with `scale_each`)."""
     if isinstance(tensor, list):
         tensor = torch.stack(tensor, dim=0)
+    if tensor.dim() == 2:
+        tensor = tensor.unsqueeze(0)
     if tensor.dim() == 3:
+        if tensor.size(0) == 1:
+            tensor = tensor.expand(3, -1, -1)
         tensor = tensor.unsqueeze(0)
     if tensor.size(1) == 1:
         tensor = tensor.expand(-1, 3, -1, -1)
+    if normalize:
+        if value_range is not None and not isinstance(value_range, tuple):
+            raise TypeError("value_range has to be a tuple (min, max) if specified. min and max are numbers")
+        tensor = tensor.clone()
+        for t in (tensor if scale_each else [tensor]):
+            lo, hi = value_range if value_range is not None else (float(t.min()), float(t.max()))
+            t.clamp_(min=lo, max=hi).sub_(lo).div_(max(hi - lo, 1e-5))
     if tensor.size(0) == 1:
         return tensor[0]
     n = tensor.size(0)
@@ -212,6 +225,22 @@ def make_grid(tensor, nrow=8, padding=2, pad_value=0.0):
         y, x = divmod(k, xmaps)
         grid[:, y * hh + padding : y * hh + hh, x * ww + padding : x * ww + ww] = tensor[k]
     return grid
+
+
+def getimg_stack(color_imgs, depth=False, depth_max=3, w=1, h=1):
+    """h x w mosaic of the first image of each batch in `color_imgs`, rows flipped vertically; depth maps become three
+    grey channels scaled by `depth_max`, negative depths painted white (legacy helper, `diffdope/diffdope.py:277-309`,
+    kept with its indexing: tile (i, j) shows image i + j)."""
+    imgs = list(color_imgs)
+    if depth:
+        for k, d in enumerate(imgs):
+            d3 = d.unsqueeze(-1).repeat(*([1] * d.dim()), 3)
+            imgs[k] = torch.where(d3 < 0, torch.full_like(d3, float(depth_max)), d3) / depth_max
+    rows = []
+    for i in range(h):
+        tiles = [imgs[i + j][0].detach().cpu().numpy() if i + j < len(imgs) else np.zeros(imgs[-1][0].shape) for j in range(w)]
+        rows.append(np.concatenate(tiles, axis=1)[::-1])
+    return np.concatenate(rows, axis=0)
 
 
 @torch.no_grad()

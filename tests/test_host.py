@@ -217,6 +217,47 @@ def test_reference_example_reaches_the_device_under_the_shims(tmp_path):
     assert "__post_init__" in out.stderr
 
 
+_VIZ_CHECK = r"""
+import sys
+sys.path.insert(0, sys.argv[1] + '/tests/golden'); sys.path.insert(0, sys.argv[1] + '/diff-dope_b200')
+import numpy as np, torch
+import diffdope as dd  # before the stand-ins take over the name 'diffdope'
+import make_reference_vectors as mrv
+ref = mrv.import_reference()
+g = torch.Generator().manual_seed(0)
+t = torch.rand(5, 3, 6, 7, generator=g) * 3 - 1
+ok = []
+for kw in (dict(), dict(normalize=True), dict(normalize=True, value_range=(0.0, 1.5)), dict(normalize=True, scale_each=True),
+           dict(nrow=2, padding=1, pad_value=0.5), dict(normalize=True, scale_each=True, value_range=(-0.5, 2.0), nrow=3)):
+    ok.append(torch.equal(ref.make_grid(t.clone(), **kw), dd.make_grid(t.clone(), **kw)))
+t1, t3, t2 = torch.rand(4, 1, 5, 5, generator=g), torch.rand(3, 5, 5, generator=g), torch.rand(5, 5, generator=g)
+ok.append(torch.equal(ref.make_grid(t1, nrow=2), dd.make_grid(t1, nrow=2)))
+ok.append(torch.equal(ref.make_grid(t3), dd.make_grid(t3)))
+ok.append(torch.equal(ref.make_grid(t2), dd.make_grid(t2)))
+ok.append(torch.equal(ref.make_grid([t3, t3 * 0.5], nrow=1), dd.make_grid([t3, t3 * 0.5], nrow=1)))
+ok.append(torch.equal(ref.make_grid(t, 2, 1, True, None, False, 0.25), dd.make_grid(t, 2, 1, True, None, False, 0.25)))  # positional order
+imgs = [torch.rand(2, 4, 5, 3, generator=g) for _ in range(3)]
+for w, h in ((1, 1), (2, 1), (2, 2), (3, 2)):
+    ok.append(np.array_equal(ref.getimg_stack([i.clone() for i in imgs], w=w, h=h), dd.getimg_stack([i.clone() for i in imgs], w=w, h=h)))
+dep = [torch.rand(2, 4, 5, generator=g) * 4 - 1 for _ in range(2)]
+ok.append(np.array_equal(ref.getimg_stack([d.clone() for d in dep], depth=True, depth_max=3, w=2, h=1),
+                         dd.getimg_stack([d.clone() for d in dep], depth=True, depth_max=3, w=2, h=1)))
+print('VIZ', len(ok), all(ok), ok)
+"""
+
+
+def test_make_grid_options_and_getimg_stack_equal_the_reference_functions():
+    """`make_grid` (normalize / value_range / scale_each, same positional order) and the legacy `getimg_stack` give
+    bit for bit what the reference's own functions give (`diffdope/diffdope.py:277-309,337-460`), the reference module
+    being imported in a subprocess with inert stand-ins for its missing third-party imports."""
+    if not os.path.exists("/root/reference/diffdope/diffdope.py"):
+        pytest.skip("reference tree not on this box")
+    out = subprocess.run([sys.executable, "-c", _VIZ_CHECK, su.ROOT], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-1500:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("VIZ")][-1]
+    assert line.split()[1] == "16" and line.split()[2] == "True", line
+
+
 def test_camera_and_image_loading_follow_reference():
     import diffdope as dd
 
