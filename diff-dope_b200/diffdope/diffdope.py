@@ -184,11 +184,15 @@ def find_crop(img_tensor, percentage=0.1):
 
 @torch.no_grad()
 def im_resize(image, width=None, height=None):
+    """Resize keeping the aspect ratio, from the one of width / height that is given (`diffdope/diffdope.py:312-334`;
+    the ratio is formed first and then multiplied, so the truncated size is the reference's in every case)."""
     h, w = image.shape[:2]
     if width is None:
-        dim = (int(w * height / float(h)), height)
+        r = height / float(h)
+        dim = (int(w * r), height)
     else:
-        dim = (width, int(h * width / float(w)))
+        r = width / float(w)
+        dim = (width, int(h * r))
     return cv2.resize(image, dim)
 
 
