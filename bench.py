@@ -327,7 +327,13 @@ def run_ours(args):
         print("forward-only timing skipped:", e, file=sys.stderr)
 
     # ---- e2e through the public API with host buffers -------------------------------------------
-    e2e = run_e2e(dev, K, B, B_global, rank, world, gt_host, lr_all, barrier, raw=args.e2e_raw)
+    try:
+        e2e = run_e2e(dev, K, B, B_global, rank, world, gt_host, lr_all, barrier, raw=args.e2e_raw)
+    except Exception as e:  # keep the device-timed line if the API leg fails; the error is reported, not hidden
+        import traceback
+
+        traceback.print_exc(file=sys.stderr)
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "error": "%s: %s" % (type(e).__name__, e)}
 
     if rank != 0:
         if world > 1:
