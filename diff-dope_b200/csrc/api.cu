@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -80,14 +81,14 @@ extern "C" int64_t ddope_last_launch_count(const ddope_scene* s) { return s ? s-
 // ---------------------------------------------------------------------------------------------
 // renderutils_plugin replacements
 
-// scratch of ddope_xfm_bwd_mtx's two-stage reduction: one per (host thread, stream), so calls on different streams may
+// scratch of ddope_xfm_bwd_mtx's two-stage reduction: one per (host thread, device, stream), so calls on different streams may
 // overlap and the entry points stay re-entrant like the reference plugin's (c_src/torch_bindings.cpp:147). A buffer is
 // only released through cudaFree, which synchronises the device first.
 struct XfmScratch {
     float* ptr = nullptr;
     size_t cap = 0;
 };
-static thread_local std::unordered_map<cudaStream_t, XfmScratch> g_xfm_scratch;
+static thread_local std::map<std::pair<int, cudaStream_t>, XfmScratch> g_xfm_scratch;
 
 extern "C" int ddope_xfm_fwd(const float* points, int Bp, int N, const float* matrix, int B, int is_points,
                              float* out, void* stream) {
@@ -119,11 +120,18 @@ extern "C" int ddope_xfm_bwd_mtx(const float* points, int Bp, int N, const float
         return 0;
     }
     size_t need = (size_t)B * xfm_bwd_mtx_blocks(N) * 16 * sizeof(float);
-    if (g_xfm_scratch.size() > 32 && g_xfm_scratch.find(st) == g_xfm_scratch.end()) {  // streams come and go: start over
-        for (auto& kv : g_xfm_scratch) cudaFree(kv.second.ptr);
+    int dev_id = 0;
+    CK(cudaGetDevice(&dev_id));
+    const std::pair<int, cudaStream_t> key(dev_id, st);  // the legacy default stream (0) exists on every device
+    if (g_xfm_scratch.size() > 32 && g_xfm_scratch.find(key) == g_xfm_scratch.end()) {  // streams come and go: start over
+        for (auto& kv : g_xfm_scratch) {
+            cudaSetDevice(kv.first.first);
+            cudaFree(kv.second.ptr);
+        }
+        cudaSetDevice(dev_id);
         g_xfm_scratch.clear();
     }
-    XfmScratch& sc = g_xfm_scratch[st];
+    XfmScratch& sc = g_xfm_scratch[key];
     if (need > sc.cap) {
         if (sc.ptr) CK(cudaFree(sc.ptr));
         sc.ptr = nullptr; sc.cap = 0;
