@@ -1,5 +1,6 @@
 // C ABI of libddope_b200 (include/ddope_b200.h): scene objects, work buffers, kernel sequencing.
 // No torch, no host threads, one stream per call.
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +26,15 @@ static int fail(const std::string& msg) {
         if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));     \
     } while (0)
 
+// A ddope_scene owns one set of work buffers: two calls on the same scene from different host threads would corrupt each
+// other. Entry points that use the work buffers hold this for the duration of the (asynchronous) enqueue and fail otherwise.
+struct SceneBusy {
+    ddope_scene* s;
+    bool ok;
+    explicit SceneBusy(ddope_scene* s_);
+    ~SceneBusy();
+};
+
 struct ddope_scene {
     // owned device copies of the mesh
     float* pos = nullptr;
@@ -39,6 +49,7 @@ struct ddope_scene {
     float* adam_state = nullptr;  // [B,14]
     int adam_cap = 0;
     int hyp_cur = 0;          // which half of `hyp` the current iteration reads
+    int dbg_hyp_half = 0;     // the half the last enqueued iteration read (ddope_debug_read)
     int cull_auto = 0;        // closed_mesh_orientation of the mesh
     float* vcol = nullptr;
     float4* tripos = nullptr;
@@ -67,7 +78,29 @@ struct ddope_scene {
     cudaStream_t part_stream[MAX_PARTS] = {};
     cudaEvent_t part_done[MAX_PARTS] = {};
     cudaEvent_t fork_event = nullptr;
+    std::atomic<int> busy{0};
 };
+
+SceneBusy::SceneBusy(ddope_scene* s_) : s(s_), ok(false) {
+    int expect = 0;
+    ok = s && s->busy.compare_exchange_strong(expect, 1);
+}
+SceneBusy::~SceneBusy() {
+    if (ok) s->busy.store(0);
+}
+#define SCENE_GUARD(who)                                                                                                  \
+    SceneBusy busy_(s);                                                                                                   \
+    if (!busy_.ok) return fail(std::string(who) + ": this ddope_scene is in use by another call (a scene is not re-entrant; use one scene per host thread)")
+
+cudaError_t& ddope::launch_error_slot() {
+    static thread_local cudaError_t e = cudaSuccess;
+    return e;
+}
+#define CK_LAUNCH(who)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e_ = take_launch_error();                                                              \
+        if (e_ != cudaSuccess) return fail(std::string(who) + ": kernel launch failed: " + cudaGetErrorString(e_)); \
+    } while (0)
 
 bool ddope::pdl_enabled() {
     static const bool on = (getenv("DDOPE_NO_PDL") == nullptr);
@@ -330,9 +363,10 @@ extern "C" int ddope_scene_set_camera(ddope_scene* s, const float* proj16, int f
     if (!s || !proj16) return fail("ddope_scene_set_camera: null pointer");
     if (frame_h <= 0 || frame_w <= 0 || frame_h > 16384 || frame_w > 16384) return fail("ddope_scene_set_camera: bad frame size");
     memcpy(s->dev.proj, proj16, sizeof(float) * 16);
-    if (s->have_camera && (s->dev.H != frame_h || s->dev.W != frame_w)) {
-        s->dev.gt_rgb = s->dev.gt_depth = s->dev.gt_seg = nullptr;  // targets belong to the old frame size
-    }
+    // the borrowed target pointers belong to the previous camera setup: a caller must set them again (a loss call without
+    // ddope_scene_set_target then fails loudly instead of reading memory the caller may have released)
+    s->dev.gt_rgb = s->dev.gt_depth = s->dev.gt_seg = nullptr;
+    s->gt_edge_dirty = true;
     s->dev.H = frame_h; s->dev.W = frame_w;
     {   // nvdiffrast's pixel-centre mapping, in separately rounded float32 operations (same values as oracle/nvdr.py pixel_ndc)
         volatile float w = (float)frame_w, h = (float)frame_h;
@@ -512,6 +546,7 @@ static int render_common(ddope_scene* s, const float* quat, const float* trans, 
     if (!s || (!mtx_in && (!quat || !trans))) return fail(std::string(who) + ": null pointer");
     if (B <= 0 || B > 65535) return fail(std::string(who) + ": B must be in [1, 65535]");
     if (!s->have_camera) return fail(std::string(who) + ": set the camera first");
+    SCENE_GUARD(who);
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, false, st)) return r;
     LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
@@ -525,7 +560,7 @@ static int render_common(ddope_scene* s, const float* quat, const float* trans, 
         launch_copy_mtx(s->hyp, B, mtx, st);
         s->launches++;
     }
-    CK(cudaGetLastError());
+    CK_LAUNCH(who);
     return 0;
 }
 
@@ -544,6 +579,7 @@ extern "C" int ddope_render_bwd(ddope_scene* s, const float* mtx_in, int B, cons
     if (!s || !mtx_in || !d_mtx) return fail("ddope_render_bwd: null pointer");
     if (B <= 0 || B > 65535) return fail("ddope_render_bwd: B must be in [1, 65535]");
     if (!s->have_camera) return fail("ddope_render_bwd: set the camera first");
+    SCENE_GUARD("ddope_render_bwd");
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, true, st)) return r;
     LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
@@ -554,7 +590,7 @@ extern "C" int ddope_render_bwd(ddope_scene* s, const float* mtx_in, int B, cons
     launch_step(s->dev, s->hyp, s->partials, B, cfg, d_mtx, st);
     launch_clear(s->dev, s->hyp, B, s->zbuf, st);  // restore the z-buffer invariant
     s->launches = 5;
-    CK(cudaGetLastError());
+    CK_LAUNCH("ddope_render_bwd");
     return 0;
 }
 
@@ -620,6 +656,7 @@ static int fork_parts(ddope_scene* s, int B, cudaStream_t st, Part* parts, int* 
     if (s->profiling || n < 1) n = 1;
     if (n > B) n = B;
     const int per = (B + n - 1) / n;
+    n = (B + per - 1) / per;  // no empty trailing part (e.g. B = 5 with 4 forced parts: per = 2 -> 3 parts)
     for (int p = 0; p < n; p++) {
         Part& P = parts[p];
         P.b0 = p * per;
@@ -675,6 +712,7 @@ static void enqueue_iteration(ddope_scene* s, const Part& P, float* quat, float*
                               int B_hist, LossCfgDev cfg, OptimDev opt, float lr_t, int it, int do_update, int more, float* loss_table,
                               float* grad, float* pose_hist, float* loss_hist) {
     HypState* cur = s->hyp + (size_t)s->hyp_cur * s->hyp_cap + P.b0;
+    s->dbg_hyp_half = s->hyp_cur;
     HypState* nxt = s->hyp + (size_t)(s->hyp_cur ^ 1) * s->hyp_cap + P.b0;
     {
         ProfMark m(s, P.st, K_RASTER);
@@ -703,6 +741,7 @@ extern "C" int ddope_loss_grad(ddope_scene* s, const float* quat, const float* t
     if (!s || !quat || !trans) return fail("ddope_loss_grad: null pointer");
     if (B <= 0 || B > 65535 || B_global < B) return fail("ddope_loss_grad: need 1 <= B <= 65535 and B_global >= B");
     if (int r = check_loss_inputs(s, cfg, "ddope_loss_grad")) return r;
+    SCENE_GUARD("ddope_loss_grad");
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, true, st)) return r;
     if (int r = prepare_edge(s, cfg, st)) return r;
@@ -717,8 +756,9 @@ extern "C" int ddope_loss_grad(ddope_scene* s, const float* quat, const float* t
         enqueue_iteration(s, parts[p], const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B_global, B, to_dev(cfg), opt, 0.f, 0, 0,
                           0, loss_table, grad, nullptr, nullptr);
     }
-    if (int r = join_parts(s, st, parts, n_parts)) return r;
-    CK(cudaGetLastError());
+    const cudaError_t lerr = take_launch_error();
+    if (int r = join_parts(s, st, parts, n_parts)) return r;  // joined on the error path too: the caller's stream stays ordered
+    if (lerr != cudaSuccess) return fail(std::string("ddope_loss_grad: kernel launch failed: ") + cudaGetErrorString(lerr));
     return 0;
 }
 
@@ -729,6 +769,7 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     if (B <= 0 || B > 65535 || B_global < B) return fail("ddope_optimize: need 1 <= B <= 65535 and B_global >= B");
     if (n_iters <= 0) return fail("ddope_optimize: n_iters must be positive");
     if (int r = check_loss_inputs(s, cfg, "ddope_optimize")) return r;
+    SCENE_GUARD("ddope_optimize");
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, true, st)) return r;
     if (int r = prepare_edge(s, cfg, st)) return r;
@@ -751,15 +792,18 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     if (int r = fork_parts(s, B, st, parts, &n_parts)) return r;
     s->hyp_cur = 0;
     for (int p = 0; p < n_parts; p++) enqueue_prologue(s, parts[p], quat, trans, lr_mult, B_global, c, opt);
+    cudaError_t lerr = cudaSuccess;
     for (int it = 0; it < n_iters; it++) {
         opt = optim_dev(s, lr_sched[it], it);
         for (int p = 0; p < n_parts; p++)
             enqueue_iteration(s, parts[p], quat, trans, lr_mult, B_global, B, c, opt, lr_sched[it], it, 1, it + 1 < n_iters, nullptr,
                               nullptr, pose_hist, loss_hist);
         s->hyp_cur ^= 1;
+        lerr = take_launch_error();  // checked after every iteration's launches, not once at the end
+        if (lerr != cudaSuccess) break;
     }
-    if (int r = join_parts(s, st, parts, n_parts)) return r;
-    CK(cudaGetLastError());
+    if (int r = join_parts(s, st, parts, n_parts)) return r;  // joined on the error path too
+    if (lerr != cudaSuccess) return fail(std::string("ddope_optimize: kernel launch failed: ") + cudaGetErrorString(lerr));
     return 0;
 }
 
@@ -793,4 +837,18 @@ extern "C" int ddope_profile_end(ddope_scene* s, float* ms_out3, int* launches_o
     s->prof_events.clear();
     s->prof_class.clear();
     return 0;
+}
+
+extern "C" int64_t ddope_debug_read(ddope_scene* s, int what, void* dst, int64_t bytes) {
+    if (!s || !dst || bytes < 0) { fail("ddope_debug_read: bad argument"); return -1; }
+    if (cudaDeviceSynchronize() != cudaSuccess) { fail("ddope_debug_read: device error"); return -1; }
+    const void* src = nullptr;
+    size_t avail = 0;
+    if (what == 0) { src = s->partials; avail = s->partials_cap * sizeof(float); }
+    else if (what == 1) { src = s->hyp ? s->hyp + (size_t)s->dbg_hyp_half * s->hyp_cap : nullptr; avail = (size_t)s->hyp_cap * sizeof(HypState); }
+    else { fail("ddope_debug_read: unknown buffer"); return -1; }
+    if (!src) return 0;
+    const size_t n = (size_t)bytes < avail ? (size_t)bytes : avail;
+    if (cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost) != cudaSuccess) { fail("ddope_debug_read: copy failed"); return -1; }
+    return (int64_t)n;
 }

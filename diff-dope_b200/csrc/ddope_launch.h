@@ -6,6 +6,20 @@
 
 namespace ddope {
 
+// First launch failure seen by launch_kernel on this host thread since the last take_launch_error() (api.cu reads it after
+// every iteration it enqueues, so a bad launch configuration is reported by the call that made it, not hundreds of launches later).
+cudaError_t& launch_error_slot();
+inline void note_launch(cudaError_t e) {
+    if (e != cudaSuccess && launch_error_slot() == cudaSuccess) launch_error_slot() = e;
+}
+inline cudaError_t take_launch_error() {
+    cudaError_t e = launch_error_slot();
+    launch_error_slot() = cudaSuccess;
+    if (e == cudaSuccess) e = cudaGetLastError();  // plain <<< >>> launches report here
+    else cudaGetLastError();
+    return e;
+}
+
 // Kernel launch with the programmatic-dependent-launch attribute (see pdl_wait / pdl_trigger); `pdl` false = plain launch.
 template <typename... KArgs, typename... Args>
 inline void launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -19,7 +33,7 @@ inline void launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 bl
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+    note_launch(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
 bool pdl_enabled();  // api.cu: on unless DDOPE_NO_PDL is set
 

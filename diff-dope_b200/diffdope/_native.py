@@ -80,6 +80,8 @@ def lib():
     L.ddope_render.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
     L.ddope_render_mtx.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
     L.ddope_render_bwd.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
+    L.ddope_debug_read.argtypes = [vp, ci, vp, ctypes.c_int64]
+    L.ddope_debug_read.restype = ctypes.c_int64
     L.ddope_profile_begin.argtypes = [vp]
     L.ddope_profile_end.argtypes = [vp, vp, vp]
     L.ddope_loss_grad.argtypes = [vp, vp, vp, vp, ci, ci, ctypes.POINTER(LossCfg), vp, vp, vp]
@@ -310,6 +312,14 @@ class NativeScene:
         n = (ctypes.c_int * 3)()
         _check(lib().ddope_profile_end(self._h, ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(n, ctypes.c_void_p)))
         return {k: float(ms[i]) for i, k in enumerate(self.KERNELS)}, {k: int(n[i]) for i, k in enumerate(self.KERNELS)}
+
+    def debug_read(self, what, nbytes):
+        """Debug hook: raw bytes of an internal work buffer after the last call (0 = tile partial rows, 1 = HypState records)."""
+        buf = np.zeros(int(nbytes), dtype=np.uint8)
+        n = lib().ddope_debug_read(self._h, int(what), _hptr(buf), int(nbytes))
+        if n < 0:
+            _check(-1)
+        return buf[:n]
 
     def last_launch_count(self):
         return int(lib().ddope_last_launch_count(self._h))

@@ -144,11 +144,13 @@ def render_texture_batch(glctx, proj_cam, mtx, pos, pos_idx, resolution, uv=None
     uv0 = None if uv is None else (uv[0] if uv.dim() == 3 else uv)
     tex0 = None if tex is None else (tex[0] if tex.dim() == 4 else tex)
     vc0 = None if vtx_color is None else (vtx_color[0] if vtx_color.dim() == 3 else vtx_color)
-    key = (pos0.data_ptr(), tuple(pos0.shape), pos0._version, idx0.data_ptr(), tuple(idx0.shape),
-           None if tex0 is None else (tex0.data_ptr(), tuple(tex0.shape), tex0._version),
-           None if vc0 is None else (vc0.data_ptr(), tuple(vc0.shape), vc0._version))
+    srcs = (pos0, idx0, uv0, tex0, vc0)
+    key = tuple(None if a is None else (a.data_ptr(), tuple(a.shape), a._version) for a in srcs)
     cache = render_texture_batch.__dict__.setdefault("_scenes", {})
-    sc = cache.get(key)
+    hit = cache.get(key)
+    # an entry keeps (views of) its source tensors alive, so their storage cannot be freed and handed to another mesh
+    # while the entry exists: an equal (address, shape, version) key then really is the same, unmodified data
+    sc = hit[0] if hit is not None else None
     if sc is None:
         if len(cache) > 16:
             cache.clear()
@@ -156,7 +158,7 @@ def render_texture_batch(glctx, proj_cam, mtx, pos, pos_idx, resolution, uv=None
             sc = _native.NativeScene(pos0, idx0, uv=uv0, tex=tex0)
         else:
             sc = _native.NativeScene(pos0, idx0, vtx_color=vc0)
-        cache[key] = sc
+        cache[key] = (sc, srcs)
     proj0 = proj_cam[0] if proj_cam.dim() == 3 else proj_cam
     sc.set_camera(proj0, int(resolution[0]), int(resolution[1]))
     rgb, depth, mask, rast = render_mtx(sc, mtx)

@@ -128,7 +128,8 @@ int ddope_scene_create(ddope_scene** out, const float* pos_host, int V, const in
 int ddope_scene_destroy(ddope_scene* s);
 
 /* Camera.cam_proj (diffdope.py:679-742) and the render resolution
- * (Scene.get_resolution, diffdope.py:1231-1252). proj16 row-major, host. */
+ * (Scene.get_resolution, diffdope.py:1231-1252). proj16 row-major, host. Resets the loss window to the full frame and
+ * forgets the borrowed target pointers: call ddope_scene_set_target again before the next loss call. */
 int ddope_scene_set_camera(ddope_scene* s, const float* proj16_host, int frame_h, int frame_w);
 
 /* gt_tensors (diffdope.py:1646-1651): device pointers, BORROWED (must outlive the calls that
@@ -218,6 +219,12 @@ int64_t ddope_last_launch_count(const ddope_scene* s);
  * and the number of launches. */
 int ddope_profile_begin(ddope_scene* s);
 int ddope_profile_end(ddope_scene* s, float* ms_out3, int* launches_out3);
+
+/* Debug hook (tests / parity investigations only): synchronise and copy internal work buffers of the last
+ * ddope_loss_grad / ddope_optimize call to host memory. what 0 = per-tile partial rows [tiles,20] float32
+ * (12 dL/dMVP rows x,y,w + 4 dL/dM row z + 4 loss sums), 1 = the HypState records [B] (208 bytes each) the
+ * last iteration read. Copies min(bytes, available) and returns the number of bytes copied, negative on error. */
+int64_t ddope_debug_read(ddope_scene* s, int what, void* dst_host, int64_t bytes);
 
 #ifdef __cplusplus
 }

@@ -309,14 +309,16 @@ def forward_backward(mesh, proj, quat_raw, trans, gt, lr_mult, cfg_losses, H, W,
     return logged, q.grad.numpy().copy(), t.grad.numpy().copy(), r
 
 
-def run_optimization(mesh, proj, quat0, trans0, gt, lr_mult, cfg_losses, hyper, H, W, window=None, progress=False):
+def run_optimization(mesh, proj, quat0, trans0, gt, lr_mult, cfg_losses, hyper, H, W, window=None, progress=False, b_global=None, stop_after=None):
     """`DiffDope.run_optimization` (`diffdope/diffdope.py:1634-1714`): nb_iterations+1
     iterations of forward, logging, loss, backward, SGD step with the decayed rate.
 
     quat0 [B,4], trans0 [B,3]: initial parameter values (the reference starts every
     hypothesis at the same pose, `diffdope.py:1019-1026`). Returns dict with
     `poses` [iters, B, 7] (the parameters each iteration rendered with),
-    `mtx` [iters, B, 4, 4], `losses` {key: [iters, B]}, `final` (q, t after the last step)."""
+    `mtx` [iters, B, 4, 4], `losses` {key: [iters, B]}, `final` (q, t after the last step).
+    `b_global`: divisor of the hypothesis mean when the batch is a shard of a larger job.
+    `stop_after`: run only the first `stop_after` iterations of the schedule (tests at full size)."""
     nb = int(hyper["nb_iterations"])
     params = [torch.nn.Parameter(torch.tensor(np.asarray(quat0, dtype=F)[:, i].copy())) for i in range(4)]
     params += [torch.nn.Parameter(torch.tensor(np.asarray(trans0, dtype=F)[:, i].copy())) for i in range(3)]
@@ -327,7 +329,7 @@ def run_optimization(mesh, proj, quat0, trans0, gt, lr_mult, cfg_losses, hyper, 
         opt = torch.optim.SGD(params, lr=hyper.get("learning_rate_base", 1))
     lr = torch.as_tensor(np.asarray(lr_mult, dtype=F))
     poses, mtxs, hist = [], [], {}
-    for it in range(nb + 1):
+    for it in range(nb + 1 if stop_after is None else min(nb + 1, int(stop_after))):
         lr_t = lr_schedule(it, nb, hyper["base_lr"], hyper["lr_decay"])
         for g in opt.param_groups:
             g["lr"] = lr_t
@@ -340,6 +342,8 @@ def run_optimization(mesh, proj, quat0, trans0, gt, lr_mult, cfg_losses, hyper, 
         total, logged = losses(r, gt, lr, cfg_losses, window)
         for k, v in logged.items():
             hist.setdefault(k, []).append(v.numpy().copy())
+        if b_global is not None:
+            total = total * (q.shape[0] / float(b_global))
         total.backward()
         opt.step()
         if progress:

@@ -217,6 +217,16 @@ def test_reference_example_reaches_the_device_under_the_shims(tmp_path):
     assert "__post_init__" in out.stderr
 
 
+def test_shipped_reference_inputs_are_verbatim():
+    """tests/golden/reference_examples/simple_scene.py and tests/golden/configs/diffdope.yaml are the reference's files, byte for byte."""
+    pairs = [("tests/golden/reference_examples/simple_scene.py", "/root/reference/examples/simple_scene.py"),
+             ("tests/golden/configs/diffdope.yaml", "/root/reference/configs/diffdope.yaml")]
+    if not os.path.exists(pairs[0][1]):
+        pytest.skip("reference tree not on this box")
+    for mine, ref in pairs:
+        assert open(os.path.join(su.ROOT, mine), "rb").read() == open(ref, "rb").read(), mine
+
+
 _VIZ_CHECK = r"""
 import sys
 sys.path.insert(0, sys.argv[1] + '/tests/golden'); sys.path.insert(0, sys.argv[1] + '/diff-dope_b200')
