@@ -81,6 +81,10 @@ void launch_gt_edge(const SceneDev& S, float* out, cudaStream_t st);
 void launch_tex_pack(const float* tex3, size_t n, float4* out, cudaStream_t st);
 void launch_tex_mip(const float4* src, int sw, int sh, float4* dst, int dw, int dh, cudaStream_t st);
 
+// image.cu
+void launch_image_from_raw(const void* raw, int sample_bytes, int sh, int sw, int sc, int is_depth, double divisor, int flip, int half,
+                           float* out, int oh, int ow, int oc, cudaStream_t st);
+
 // xfm.cu
 void launch_xfm_fwd(const float* points, int Bp, int N, const float* matrix, int B, int is_points, float* out,
                     cudaStream_t st);

@@ -74,10 +74,13 @@ __device__ __forceinline__ float shade_zw(const Shade& s) {
 template <bool EX, bool GRAD>
 __device__ __forceinline__ void tex_bilinear(const float4* __restrict__ lvl, int tw, int th, float u, float v, float* rgb,
                                              float* du, float* dv) {
-    float tu = sub_<EX>(u, floorf(u)), tv = sub_<EX>(v, floorf(v));
-    tu = sub_<EX>(mul_<EX>(tu, (float)tw), 0.5f); tv = sub_<EX>(mul_<EX>(tv, (float)th), 0.5f);
+    // texel coordinates in separately rounded ops in every mode: floor() below is a discrete decision (which texel cell), and
+    // the uv gradient jumps from cell to cell -- a contracted multiply-add moves u*tw by 1 ulp (6e-5 texel at 2048 texels),
+    // which flips the cell of a few pixels per hypothesis and with it 1e-4 of the rgb gradient (measured at full resolution)
+    float tu = xsub(u, floorf(u)), tv = xsub(v, floorf(v));
+    tu = xsub(xmul(tu, (float)tw), 0.5f); tv = xsub(xmul(tv, (float)th), 0.5f);
     int iu0 = (int)floorf(tu), iv0 = (int)floorf(tv);
-    const float fu = sub_<EX>(tu, (float)iu0), fv = sub_<EX>(tv, (float)iv0);
+    const float fu = xsub(tu, (float)iu0), fv = xsub(tv, (float)iv0);
     int iu1 = iu0 + 1, iv1 = iv0 + 1;
     if (iu0 < 0) iu0 += tw;
     if (iv0 < 0) iv0 += th;
@@ -130,8 +133,9 @@ __device__ __forceinline__ void shade_color(const SceneDev& S, const Shade& sh, 
                                             float ys, float* rgb, float* g0, float* g1) {
     if (S.tex4) {
         const float2 t0 = make_float2(sh.v0.w, sh.vv.x), t1 = make_float2(sh.v1.w, sh.vv.y), t2 = make_float2(sh.v2.w, sh.vv.z);
-        const float tu = add_<EX>(add_<EX>(mul_<EX>(b0, t0.x), mul_<EX>(b1, t1.x)), mul_<EX>(b2, t2.x));
-        const float tv = add_<EX>(add_<EX>(mul_<EX>(b0, t0.y), mul_<EX>(b1, t1.y)), mul_<EX>(b2, t2.y));
+        // interpolated uv: separately rounded in every mode (it selects the texel cell, see tex_bilinear)
+        const float tu = xadd(xadd(xmul(b0, t0.x), xmul(b1, t1.x)), xmul(b2, t2.x));
+        const float tv = xadd(xadd(xmul(b0, t0.y), xmul(b1, t1.y)), xmul(b2, t2.y));
         float du[3], dv[3];
         if (!MIP) {
             tex_bilinear<EX, GRAD>(S.tex4, S.tex_w, S.tex_h, tu, tv, rgb, du, dv);

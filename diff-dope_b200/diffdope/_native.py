@@ -80,6 +80,8 @@ def lib():
     L.ddope_render.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
     L.ddope_render_mtx.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
     L.ddope_render_bwd.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
+    L.ddope_image_from_raw.argtypes = [vp, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, vp, vp]
+    L.ddope_image_from_raw.restype = ci
     L.ddope_debug_read.argtypes = [vp, ci, vp, ctypes.c_int64]
     L.ddope_debug_read.restype = ctypes.c_int64
     L.ddope_profile_begin.argtypes = [vp]
@@ -91,7 +93,7 @@ def lib():
         "ddope_scene_destroy", "ddope_scene_set_camera", "ddope_scene_set_target", "ddope_scene_set_window",
         "ddope_render", "ddope_render_mtx", "ddope_render_bwd", "ddope_loss_grad", "ddope_optimize",
         "ddope_profile_begin", "ddope_profile_end", "ddope_scene_set_texture_filter", "ddope_scene_set_optimizer",
-        "ddope_scene_set_culling",
+        "ddope_scene_set_culling", "ddope_image_from_raw",
     ):
         getattr(L, name).restype = ci
     if L.ddope_abi_version() != 2:
@@ -136,6 +138,24 @@ def _hptr(a):
 def make_loss_cfg(use_rgb, use_depth, use_mask, w_rgb=1.0, w_depth=1.0, w_mask=1.0, use_edge=False, w_edge=1.0):
     return LossCfg(int(bool(use_rgb)), int(bool(use_depth)), int(bool(use_mask)), float(w_rgb), float(w_depth), float(w_mask),
                    int(bool(use_edge)), float(w_edge))
+
+
+def image_from_raw(raw, is_depth, divisor, flip=True, resize_half=False):
+    """`ddope_image_from_raw`: raw cuda uint8 / uint16 (int16 view) samples [H,W,C] or [H,W] -> float32 [h,w,3] RGB or [h,w] depth,
+    bit-equal to the reference's host pipeline (`Image.__post_init__`, diffdope.py:1122-1152)."""
+    if not isinstance(raw, torch.Tensor) or not raw.is_cuda:
+        raise RuntimeError("raw samples must be a cuda tensor")
+    raw = raw.contiguous()
+    nbytes = raw.element_size()
+    if raw.dtype not in (torch.uint8, torch.uint16, torch.int16):
+        raise RuntimeError("raw samples must be uint8 or uint16")
+    H, W = int(raw.shape[0]), int(raw.shape[1])
+    C = 1 if raw.dim() == 2 else int(raw.shape[2])
+    oh, ow = (H // 2, W // 2) if resize_half else (H, W)
+    out = torch.empty((oh, ow) if is_depth else (oh, ow, 3), dtype=torch.float32, device=raw.device)
+    _check(lib().ddope_image_from_raw(_ptr(raw), nbytes, H, W, C, int(bool(is_depth)), float(divisor), int(bool(flip)), int(bool(resize_half)),
+                                      _ptr(out), _stream()))
+    return out
 
 
 class NativeScene:

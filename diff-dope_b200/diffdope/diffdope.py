@@ -601,42 +601,33 @@ class Image:
             log.info(f"Loaded image {self.img_path}, shape: {self.img_tensor.shape}")
         self._batchsize_set = False
 
-    _tables = {}
-
     def set_raw(self, raw, device=None):
-        """Extension (8-bit targets on the wire): take the file's samples as `cv2.imread` returns them -- uint8
-        [H,W,3|4] BGR for colour / segmentation, uint8 or uint16 [H,W] for depth (`IMREAD_UNCHANGED`) -- as a numpy
-        array or a (pinned) torch tensor, copy them to `device` in their integer type and build there the float32
-        tensor `__post_init__` builds on the host (`diffdope/diffdope.py:1122-1152`): a quarter (colour) or half
-        (depth) of the float32 bytes cross PCIe. Bit-equal to the host path: the value of sample k comes from a table
-        of k / 255.0 (k / depth_scale) computed in float64 and rounded to float32, exactly what the cv2 pipeline does.
-        Only for img_resize == 1 (resizing interpolates, it is not a per-sample map)."""
+        """Extension (integer targets on the wire): take the file's samples as `cv2.imread` returns them -- uint8 [H,W,3|4] BGR
+        for colour / segmentation, uint8 or uint16 [H,W] for depth (`IMREAD_UNCHANGED`) -- as a numpy array or a (pinned) torch
+        tensor, copy them to `device` in their integer type and build there, in one kernel (`ddope_image_from_raw`), the float32
+        tensor `__post_init__` builds on the host (`diffdope/diffdope.py:1122-1152`): BGR -> RGB, / 255.0 (/ depth_scale),
+        vertical flip, and the `img_resize` = 0.5 resize of the default config (2x2 area mean for colour, every second pixel for
+        depth, which is what cv2.resize computes at exactly 0.5x). A quarter (colour) or half (depth) of the float32 bytes cross
+        PCIe; the result is bit-equal to the host path. Other resize factors need the host pipeline."""
+        half = False
         if self.img_resize is not None and self.img_resize < 1.0:
-            raise ValueError("Image.set_raw: img_resize < 1 needs the host pipeline (cv2.resize)")
+            if float(self.img_resize) != 0.5:
+                raise ValueError("Image.set_raw: only img_resize 1 and 0.5 run on the device (cv2.resize at other factors: use the host pipeline)")
+            half = True
         t = raw if isinstance(raw, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(raw))
         if self.depth:
-            if t.dim() != 2 or t.dtype not in (torch.uint8, torch.uint16, torch.int16, torch.int32):
+            if t.dim() != 2 or t.dtype not in (torch.uint8, torch.uint16, torch.int16):
                 raise ValueError("Image.set_raw: depth samples must be a [H,W] uint8 / uint16 array")
-            n, scale = 65536, float(self.depth_scale)
         else:
             if t.dim() != 3 or t.shape[2] < 3 or t.dtype != torch.uint8:
                 raise ValueError("Image.set_raw: colour samples must be a [H,W,3|4] uint8 BGR array")
-            n, scale = 256, 255.0
-        if t.dtype == torch.uint16:  # few torch ops take uint16: reinterpret, the index below masks the sign away
+        if half and (t.shape[0] % 2 or t.shape[1] % 2):
+            raise ValueError("Image.set_raw: img_resize 0.5 on the device needs even image dimensions")
+        if t.dtype == torch.uint16:  # few torch ops take uint16: same bits as int16
             t = t.view(torch.int16)
-        dev = torch.device(device) if device is not None else t.device
-        key = (str(dev), n, scale)
-        lut = Image._tables.get(key)
-        if lut is None:
-            lut = torch.tensor(np.arange(n, dtype=np.float64) / scale).float().to(dev)
-            Image._tables[key] = lut
-        idx = t.to(dev, non_blocking=True).to(torch.int32) & (n - 1)
-        im = lut[idx]
-        if not self.depth:
-            im = im[:, :, :3].flip(-1)  # BGR -> RGB
-        if self.flip_img:
-            im = im.flip(0)
-        self.img_tensor = im.contiguous()
+        dev = torch.device(device) if device is not None else (t.device if t.is_cuda else torch.device("cuda"))
+        self.img_tensor = _native.image_from_raw(t.to(dev, non_blocking=True), self.depth, self.depth_scale if self.depth else 255.0,
+                                                 flip=bool(self.flip_img), resize_half=half)
         self._batchsize_set = False
         return self
 

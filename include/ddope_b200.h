@@ -158,6 +158,16 @@ int ddope_mesh_orientation(const float* pos_host, int V, const int32_t* tri_host
 int ddope_scene_set_texture_filter(ddope_scene* s, int mode, int max_levels);
 int ddope_scene_set_optimizer(ddope_scene* s, const ddope_optim_cfg* cfg);
 
+/* Image.__post_init__ (diffdope.py:1122-1152) on the device, for targets that cross PCIe as the file's integer samples
+ * (what cv2.imread returns) instead of float32: raw_dev [src_h, src_w, src_c] uint8 (sample_bytes 1) or uint16 (2).
+ * Colour / segmentation (is_depth 0): src_c >= 3 in BGR order -> out [oh, ow, 3] RGB = sample / divisor (255.0).
+ * Depth (is_depth 1): src_c == 1 -> out [oh, ow] = sample / divisor (depth_scale). flip != 0: vertical flip first, as the reference
+ * does. resize_half != 0: the reference's cv2.resize at img_resize = 0.5 of an even-sized image (bilinear = 2x2 area mean for
+ * colour, nearest = every second pixel for depth), oh = src_h / 2, ow = src_w / 2; else oh = src_h, ow = src_w.
+ * Bit-equal to the host pipeline (float64 arithmetic, one rounding to float32). */
+int ddope_image_from_raw(const void* raw_dev, int sample_bytes, int src_h, int src_w, int src_c, int is_depth, double divisor,
+                         int flip, int resize_half, float* out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (3) the hot path
  * ---------------------------------------------------------------------------------------- */

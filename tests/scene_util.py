@@ -101,3 +101,17 @@ def perturbed_poses(q, t, B, seed=1, rot_deg=3.0, trans=0.03):
     qs[1:] += rng.normal(0, np.deg2rad(rot_deg) / 2, size=(B - 1, 4))
     ts[1:] += rng.normal(0, trans, size=(B - 1, 3))
     return qs.astype(np.float32), ts.astype(np.float32)
+
+
+def record(name, **meas):
+    """Measured parity figures -> gpurun_out/parity_measured.jsonl (when that directory exists), quoted in DESIGN.md."""
+    import json
+
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: np.asarray(v, dtype=np.float64).tolist() for k, v in meas.items()}}) + "\n")
+
+
+def grad_rel_err(go, gg):
+    return float(np.abs(np.asarray(go) - np.asarray(gg)).max() / np.abs(np.asarray(go)).max())

@@ -13,18 +13,32 @@ pytestmark = pytest.mark.gpu
 
 
 def test_image_set_raw_on_the_device_equals_the_host_pipeline():
+    """`Image.set_raw` (one kernel, `ddope_image_from_raw`) against `Image.__post_init__` (cv2 on the host): full size and the
+    default config's img_resize = 0.5, with and without the flip, 3- and 4-channel colour, uint8 and uint16 depth."""
     import diffdope as dd
 
     sc = os.path.join(su.DATA, "scene")
     for name, depth in (("rgb.png", False), ("seg.png", False), ("depth.png", True)):
         path = os.path.join(sc, name)
-        host = dd.Image(img_path=path, depth=depth).img_tensor
         raw = cv2.imread(path, cv2.IMREAD_UNCHANGED if depth else cv2.IMREAD_COLOR)
         raw = raw.view(np.int16) if raw.dtype == np.uint16 else raw
         pinned = torch.from_numpy(np.ascontiguousarray(raw)).pin_memory()
-        dev = dd.Image(depth=depth).set_raw(pinned, device="cuda").img_tensor
-        assert dev.is_cuda and dev.dtype == torch.float32 and dev.is_contiguous()
-        assert torch.equal(dev.cpu(), host)
+        for resize in (1.0, 0.5):
+            host = dd.Image(img_path=path, depth=depth, img_resize=resize).img_tensor
+            dev = dd.Image(depth=depth, img_resize=resize).set_raw(pinned, device="cuda").img_tensor
+            assert dev.is_cuda and dev.dtype == torch.float32 and dev.is_contiguous()
+            assert torch.equal(dev.cpu(), host), (name, resize)
+        noflip = dd.Image(depth=depth, flip_img=False).set_raw(raw).img_tensor
+        assert torch.equal(noflip.cpu(), torch.flip(dd.Image(img_path=path, depth=depth).img_tensor, dims=[0]))
+    bgra = np.concatenate([cv2.imread(os.path.join(sc, "rgb.png")), np.full((1080, 1920, 1), 255, np.uint8)], -1)
+    assert torch.equal(dd.Image().set_raw(bgra).img_tensor.cpu(), dd.Image(img_path=os.path.join(sc, "rgb.png")).img_tensor)
+    d8 = (cv2.imread(os.path.join(sc, "depth.png"), cv2.IMREAD_UNCHANGED) >> 4).astype(np.uint8)
+    assert torch.equal(dd.Image(depth=True, img_resize=0.5).set_raw(d8).img_tensor.cpu(),
+                       torch.tensor(cv2.resize(cv2.flip(d8 / 100, 0), (960, 540), interpolation=cv2.INTER_NEAREST)).float())
+    with pytest.raises(ValueError):
+        dd.Image(img_resize=0.3).set_raw(cv2.imread(os.path.join(sc, "rgb.png")))
+    with pytest.raises(ValueError):
+        dd.Image(img_resize=0.5).set_raw(np.zeros((11, 10, 3), np.uint8))
 
 
 def test_empty_shard_enqueues_nothing():

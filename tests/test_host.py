@@ -283,27 +283,33 @@ def test_camera_and_image_loading_follow_reference():
     assert np.array_equal(d.img_tensor.numpy(), su.example_targets(0.5)["depth"])
 
 
-def test_image_set_raw_is_bit_equal_to_the_host_pipeline():
-    """Extension: integer samples converted through a k/255.0 (k/depth_scale) table equal the cv2 float64 pipeline bit for bit."""
+def test_device_image_arithmetic_equals_the_host_pipeline():
+    """`ddope_image_from_raw` (csrc/image.cu) is float64 arithmetic rounded once to float32: sample / divisor, and at
+    img_resize = 0.5 the 2x2 area mean (((a+b)+c)+d) * 0.25 for colour, pixel (2y, 2x) for depth. This restates that
+    arithmetic in numpy and checks it against the reference's cv2 pipeline (`Image.__post_init__`, diffdope.py:1122-1152)
+    on the example images and on random even-sized images (SURVEY.md Appendix D pins 6-7); the kernel itself is compared
+    with the host pipeline on the GPU (tests/test_gpu_wire.py)."""
     import cv2
-    import diffdope as dd
+
+    def kernel_arithmetic(raw, depth, divisor, half):
+        f = (raw[::-1].astype(np.float64) if depth else raw[::-1, :, 2::-1].astype(np.float64)) / divisor
+        if half:
+            f = f[0::2, 0::2] if depth else (((f[0::2, 0::2] + f[0::2, 1::2]) + f[1::2, 0::2]) + f[1::2, 1::2]) * 0.25
+        return f.astype(np.float32)
 
     sc = os.path.join(su.DATA, "scene")
     for name, depth in (("rgb.png", False), ("seg.png", False), ("depth.png", True)):
-        path = os.path.join(sc, name)
-        host = dd.Image(img_path=path, depth=depth)
-        raw = cv2.imread(path, cv2.IMREAD_UNCHANGED if depth else cv2.IMREAD_COLOR)
-        for src in (raw, torch.from_numpy(raw)):
-            im = dd.Image(depth=depth).set_raw(src)
-            assert im.img_tensor.dtype == torch.float32 and im.img_tensor.is_contiguous()
-            assert torch.equal(im.img_tensor, host.img_tensor)
-        assert torch.equal(dd.Image(depth=depth, flip_img=False).set_raw(raw).img_tensor, torch.flip(host.img_tensor, dims=[0]))
-    with pytest.raises(ValueError):
-        dd.Image(img_resize=0.5).set_raw(np.zeros((4, 4, 3), np.uint8))
-    with pytest.raises(ValueError):
-        dd.Image().set_raw(np.zeros((4, 4), np.uint8))
-    with pytest.raises(ValueError):
-        dd.Image(depth=True).set_raw(np.zeros((4, 4, 3), np.uint8))
+        raw = cv2.imread(os.path.join(sc, name), cv2.IMREAD_UNCHANGED if depth else cv2.IMREAD_COLOR)
+        for resize in (1.0, 0.5):
+            host = su.load_image(os.path.join(sc, name), resize, depth=depth)
+            assert np.array_equal(kernel_arithmetic(raw, depth, 100.0 if depth else 255.0, resize == 0.5), host), (name, resize)
+    rng = np.random.default_rng(0)
+    raw = rng.integers(0, 256, (54, 72, 3), dtype=np.uint8)
+    f = cv2.flip(cv2.cvtColor(raw, cv2.COLOR_BGR2RGB) / 255.0, 0)
+    assert np.array_equal(kernel_arithmetic(raw, False, 255.0, True), cv2.resize(f, (36, 27)).astype(np.float32))
+    rawd = rng.integers(0, 65536, (54, 72), dtype=np.uint16)
+    fd = cv2.flip(rawd / 100, 0)
+    assert np.array_equal(kernel_arithmetic(rawd, True, 100.0, True), cv2.resize(fd, (36, 27), interpolation=cv2.INTER_NEAREST).astype(np.float32))
 
 
 def test_mesh_and_object3d_follow_reference():
