@@ -188,10 +188,10 @@ extern "C" int ddope_image_from_raw(const void* raw, int sample_bytes, int src_h
     if (!raw || !out) return fail("ddope_image_from_raw: null pointer");
     if (sample_bytes != 1 && sample_bytes != 2) return fail("ddope_image_from_raw: samples must be uint8 or uint16");
     if (src_h <= 0 || src_w <= 0 || src_c <= 0 || !(divisor > 0.0)) return fail("ddope_image_from_raw: bad shape or divisor");
-    if (is_depth ? src_c != 1 : src_c < 3) return fail("ddope_image_from_raw: depth needs 1 channel, colour at least 3 (BGR)");
+    if (is_depth ? src_c != 1 : (src_c != 1 && src_c < 3)) return fail("ddope_image_from_raw: depth needs 1 channel, colour 1 (grey) or at least 3 (BGR)");
     if (resize_half && ((src_h & 1) || (src_w & 1))) return fail("ddope_image_from_raw: the 0.5x resize needs even image dimensions");
     const int oh = resize_half ? src_h / 2 : src_h, ow = resize_half ? src_w / 2 : src_w;
-    launch_image_from_raw(raw, sample_bytes, src_h, src_w, src_c, is_depth, divisor, flip, resize_half, out, oh, ow, is_depth ? 1 : 3,
+    launch_image_from_raw(raw, sample_bytes, src_h, src_w, src_c, is_depth, divisor, flip, resize_half, out, oh, ow, (is_depth || src_c == 1) ? 1 : 3,
                           (cudaStream_t)stream);
     CK(cudaGetLastError());
     return 0;

@@ -14,7 +14,7 @@ __device__ __forceinline__ double sample_at(const T* __restrict__ raw, int sw, i
 }
 
 // out [oh, ow, oc] float32. Colour (is_depth == 0): oc = 3, out channel c reads source channel 2 - c (BGR -> RGB) of the first three
-// channels. Depth: oc = 1. flip: output row y comes from source row (sh - 1 - y') -- the flip happens BEFORE the resize, as in the reference.
+// channels; a single-channel (grey) source gives oc = 1, the value all three channels of the reference's tensor would hold. Depth: oc = 1. flip: output row y comes from source row (sh - 1 - y') -- the flip happens BEFORE the resize, as in the reference.
 template <typename T>
 __global__ void image_from_raw_kernel(const T* __restrict__ raw, int sh, int sw, int sc, int is_depth, double divisor, int flip, int half,
                                       float* __restrict__ out, int oh, int ow, int oc) {
@@ -22,7 +22,7 @@ __global__ void image_from_raw_kernel(const T* __restrict__ raw, int sh, int sw,
     if (i >= (size_t)oh * ow * oc) return;
     const int c = (int)(i % oc);
     const int x = (int)((i / oc) % ow), y = (int)(i / ((size_t)oc * ow));
-    const int srcc = is_depth ? 0 : 2 - c;
+    const int srcc = (is_depth || sc == 1) ? 0 : 2 - c;
     double v;
     if (!half) {
         const int yy = flip ? sh - 1 - y : y;

@@ -152,7 +152,7 @@ def image_from_raw(raw, is_depth, divisor, flip=True, resize_half=False):
     H, W = int(raw.shape[0]), int(raw.shape[1])
     C = 1 if raw.dim() == 2 else int(raw.shape[2])
     oh, ow = (H // 2, W // 2) if resize_half else (H, W)
-    out = torch.empty((oh, ow) if is_depth else (oh, ow, 3), dtype=torch.float32, device=raw.device)
+    out = torch.empty((oh, ow) if (is_depth or C == 1) else (oh, ow, 3), dtype=torch.float32, device=raw.device)
     _check(lib().ddope_image_from_raw(_ptr(raw), nbytes, H, W, C, int(bool(is_depth)), float(divisor), int(bool(flip)), int(bool(resize_half)),
                                       _ptr(out), _stream()))
     return out
@@ -302,8 +302,9 @@ class NativeScene:
                                      ctypes.byref(cfg), _ptr(loss), _ptr(grad), _stream()))
         return loss, grad
 
-    def optimize(self, quat, trans, lr_mult, lr_sched, cfg, b_global=None, keep_history=True):
-        """In-place SGD on quat [B,4] / trans [B,3]. Returns (pose_hist [n,B,7], loss_hist [n,B,4]) or (None, None)."""
+    def optimize(self, quat, trans, lr_mult, lr_sched, cfg, b_global=None, keep_history=True, out=None):
+        """In-place SGD on quat [B,4] / trans [B,3]. Returns (pose_hist [n,B,7], loss_hist [n,B,4]) or (None, None).
+        out = (pose_hist, loss_hist): write the history into these preallocated contiguous cuda float32 tensors."""
         for t, n in ((quat, "quat"), (trans, "trans")):
             if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise RuntimeError("%s must be a contiguous cuda float32 tensor (updated in place)" % n)
@@ -312,7 +313,12 @@ class NativeScene:
         sched = np.ascontiguousarray(lr_sched, dtype=np.float32)
         n = sched.shape[0]
         pose_hist = loss_hist = None
-        if keep_history:
+        if out is not None:
+            pose_hist, loss_hist = out
+            if not (tuple(pose_hist.shape) == (n, B, 7) and tuple(loss_hist.shape) == (n, B, NUM_LOSSES) and pose_hist.is_contiguous()
+                    and loss_hist.is_contiguous() and pose_hist.dtype == torch.float32 and loss_hist.dtype == torch.float32 and pose_hist.is_cuda and loss_hist.is_cuda):
+                raise RuntimeError("optimize(out=...): need contiguous cuda float32 [n,B,7] and [n,B,%d]" % NUM_LOSSES)
+        elif keep_history:
             pose_hist = torch.empty(n, B, 7, device=quat.device)
             loss_hist = torch.empty(n, B, NUM_LOSSES, device=quat.device)
         if B == 0:  # an empty shard (more ranks than hypotheses): nothing to enqueue, empty tables

@@ -603,7 +603,8 @@ class Image:
 
     def set_raw(self, raw, device=None):
         """Extension (integer targets on the wire): take the file's samples as `cv2.imread` returns them -- uint8 [H,W,3|4] BGR
-        for colour / segmentation, uint8 or uint16 [H,W] for depth (`IMREAD_UNCHANGED`) -- as a numpy array or a (pinned) torch
+        for colour / segmentation ([H,W] uint8 for a grey file such as a binary mask read with IMREAD_GRAYSCALE: the three equal
+        channels are then a zero-stride view), uint8 or uint16 [H,W] for depth (`IMREAD_UNCHANGED`) -- as a numpy array or a (pinned) torch
         tensor, copy them to `device` in their integer type and build there, in one kernel (`ddope_image_from_raw`), the float32
         tensor `__post_init__` builds on the host (`diffdope/diffdope.py:1122-1152`): BGR -> RGB, / 255.0 (/ depth_scale),
         vertical flip, and the `img_resize` = 0.5 resize of the default config (2x2 area mean for colour, every second pixel for
@@ -619,15 +620,18 @@ class Image:
             if t.dim() != 2 or t.dtype not in (torch.uint8, torch.uint16, torch.int16):
                 raise ValueError("Image.set_raw: depth samples must be a [H,W] uint8 / uint16 array")
         else:
-            if t.dim() != 3 or t.shape[2] < 3 or t.dtype != torch.uint8:
-                raise ValueError("Image.set_raw: colour samples must be a [H,W,3|4] uint8 BGR array")
+            if not ((t.dim() == 3 and t.shape[2] >= 3) or t.dim() == 2) or t.dtype != torch.uint8:
+                raise ValueError("Image.set_raw: colour samples must be a [H,W,3|4] uint8 BGR array, or [H,W] uint8 for a grey file")
         if half and (t.shape[0] % 2 or t.shape[1] % 2):
             raise ValueError("Image.set_raw: img_resize 0.5 on the device needs even image dimensions")
         if t.dtype == torch.uint16:  # few torch ops take uint16: same bits as int16
             t = t.view(torch.int16)
         dev = torch.device(device) if device is not None else (t.device if t.is_cuda else torch.device("cuda"))
-        self.img_tensor = _native.image_from_raw(t.to(dev, non_blocking=True), self.depth, self.depth_scale if self.depth else 255.0,
-                                                 flip=bool(self.flip_img), resize_half=half)
+        im = _native.image_from_raw(t.to(dev, non_blocking=True), self.depth, self.depth_scale if self.depth else 255.0,
+                                    flip=bool(self.flip_img), resize_half=half)
+        if not self.depth and im.dim() == 2:  # grey file: the reference's [H,W,3] tensor with three equal channels, as a view
+            im = im.unsqueeze(-1).expand(-1, -1, 3)
+        self.img_tensor = im
         self._batchsize_set = False
         return self
 
@@ -828,7 +832,24 @@ class DiffDope:
         """[B, ...] target tensor -> entry 0 (all entries are the same image)."""
         if t is None:
             return None
-        return t[0].contiguous()
+        t = t[0]
+        return t if (t.dim() == 3 and t.stride(-1) == 0) else t.contiguous()
+
+    def _seg_for_kernel(self, seg):
+        """A [H,W,3] segmentation whose channels are equal is handed to the kernel as one channel (4 B/px instead of 12).
+        Zero-stride channel views (grey files through `Image.set_raw`) are recognised without touching the device; otherwise the
+        channels are compared once per image tensor (the verdict is cached on its address and version)."""
+        if seg is None or seg.dim() != 3 or seg.shape[2] != 3:
+            return seg
+        if seg.stride(-1) == 0:
+            return seg[..., 0].contiguous()
+        key = (seg.data_ptr(), tuple(seg.shape), seg._version)
+        hit = getattr(self, "_seg_single_cache", None)
+        if hit is None or hit[0] != key:
+            same = bool(torch.equal(seg[..., 0], seg[..., 1])) and bool(torch.equal(seg[..., 0], seg[..., 2]))
+            hit = (key, seg[..., 0].contiguous() if same else None, seg)  # holds `seg`: its address cannot be reused while cached
+            self._seg_single_cache = hit
+        return hit[1] if hit[1] is not None else seg
 
     def _prepare_native(self, slot=0):
         mesh = self.object3d.mesh
@@ -839,9 +860,7 @@ class DiffDope:
         rgb = self._single(self.gt_tensors.get("rgb"))
         depth = self._single(self.gt_tensors.get("depth"))
         seg = self._single(self.gt_tensors.get("segmentation"))
-        if seg is not None and seg.dim() == 3 and seg.shape[2] == 3:
-            if bool(torch.equal(seg[..., 0], seg[..., 1])) and bool(torch.equal(seg[..., 0], seg[..., 2])):
-                seg = seg[..., 0].contiguous()  # 4 B/px instead of 12
+        seg = self._seg_for_kernel(seg)
         sc.set_target(rgb, depth, seg)
         sc.set_texture_filter(self._texture_filter())
         if self.window is not None:
@@ -877,27 +896,43 @@ class DiffDope:
         B = q.shape[0]
         lr = self.learning_rates.float().contiguous()
         lo, hi = _dist.shard_range(B)
+        Bl, n, K = hi - lo, len(sched), _native.NUM_LOSSES
         ql, tl = q[lo:hi].contiguous(), t[lo:hi].contiguous()
-        pose_hist, loss_hist = sc.optimize(ql, tl, lr[lo:hi].contiguous(), sched, cfg, b_global=B)
-        final = torch.cat([ql, tl], dim=1)
-        return dict(sc=sc, kinds=kinds, B=B, pose_hist=pose_hist, loss_hist=loss_hist, final=final)
+        # one flat result buffer per rank: [pose history | loss history | final poses] -> one all-gather, one device-to-host copy
+        a, b, c = _dist.flat_sizes(n, Bl, K)
+        flat = torch.empty(max(c, 1), device=q.device, dtype=torch.float32)
+        sc.optimize(ql, tl, lr[lo:hi].contiguous(), sched, cfg, b_global=B, out=(flat[:a].view(n, Bl, 7), flat[a:b].view(n, Bl, K)))
+        if Bl > 0:
+            fin = flat[b:c].view(Bl, 7)
+            fin[:, :4].copy_(ql)
+            fin[:, 4:].copy_(tl)
+        return dict(sc=sc, kinds=kinds, B=B, n=n, flat=flat)
 
     def _fused_finish(self, st):
-        """Gather the shards, read the result tables back and publish them in the reference's attributes."""
+        """Gather the shards (one all-gather), read the result tables back (one copy into pinned memory) and publish them in
+        the reference's attributes."""
         from . import _dist
 
-        sc, kinds, B = st["sc"], st["kinds"], st["B"]
-        pose_hist, loss_hist, final = _dist.gather_hypotheses(B, st["pose_hist"], st["loss_hist"], st["final"])
-        self.object3d.load_pose_tensors(final[:, :4], final[:, 4:])
-        self._pose_hist = pose_hist  # [iters, B, 7] device
+        sc, kinds, B, n, K = st["sc"], st["kinds"], st["B"], st["n"], _native.NUM_LOSSES
+        rank, ws = _dist.world()
+        per = (B + ws - 1) // ws
+        allf = _dist.gather_flat(st["flat"], max(_dist.flat_sizes(n, per, K)[2], 1))
+        host = getattr(self, "_result_pin", None)
+        if host is None or tuple(host.shape) != tuple(allf.shape):
+            host = torch.empty(tuple(allf.shape), dtype=torch.float32, pin_memory=True)
+            self._result_pin = host
+        host.copy_(allf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        ph, lh, final = _dist.unpack_flat(host, B, n, K)
+        ph = ph.clone()  # the pinned buffer is reused by the next run
+        fin_dev = _dist.final_poses(allf, B, n, K)
+        self.object3d.load_pose_tensors(fin_dev[:, :4], fin_dev[:, 4:])
         self._native_scene = sc
-        ph = pose_hist.cpu()
-        lh = loss_hist.cpu()
         cols = {"rgb": 0, "depth": 1, "mask": 2, "edge": 3}
         keys = {"rgb": "rgb", "depth": "depth", "mask": "mask_selection", "edge": "edge"}
         for k in kinds:
             self.losses_values[keys[k]] = lh[:, :, cols[k]].contiguous()
-        self._pose_hist_host = ph  # [iters, B, 7] host copy: 'mtx' of an iteration is built from it on first access
+        self._pose_hist_host = ph  # [iters, B, 7]: 'mtx' of an iteration is built from it on first access, renders are re-made from it
         self.optimization_results = [_LazyResult(self, i) for i in range(ph.shape[0])]
         self.renders = self.optimization_results[-1]
 
@@ -905,9 +940,10 @@ class DiffDope:
         """Re-render iteration `index` (all hypotheses, or one) from the stored poses; CPU tensors in
         the reference's layout: rgb [B,H,W,3], depth [B,H,W], mask [B,H,W,3] over the full frame."""
         sc = self._native_scene
-        pose = self._pose_hist[index]
+        pose = self._pose_hist_host[index]
         if batch_index is not None:
             pose = pose[int(batch_index) : int(batch_index) + 1]
+        pose = pose.to(self.learning_rates.device)
         win = sc.window
         sc.set_window(0, 0, sc.H, sc.W)
         out = {"rgb": [], "depth": [], "mask": []}

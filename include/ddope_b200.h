@@ -160,7 +160,8 @@ int ddope_scene_set_optimizer(ddope_scene* s, const ddope_optim_cfg* cfg);
 
 /* Image.__post_init__ (diffdope.py:1122-1152) on the device, for targets that cross PCIe as the file's integer samples
  * (what cv2.imread returns) instead of float32: raw_dev [src_h, src_w, src_c] uint8 (sample_bytes 1) or uint16 (2).
- * Colour / segmentation (is_depth 0): src_c >= 3 in BGR order -> out [oh, ow, 3] RGB = sample / divisor (255.0).
+ * Colour / segmentation (is_depth 0): src_c >= 3 in BGR order -> out [oh, ow, 3] RGB = sample / divisor (255.0); src_c == 1 (a grey
+ * file, e.g. a binary mask read with IMREAD_GRAYSCALE) -> out [oh, ow], the value of each of the three equal channels.
  * Depth (is_depth 1): src_c == 1 -> out [oh, ow] = sample / divisor (depth_scale). flip != 0: vertical flip first, as the reference
  * does. resize_half != 0: the reference's cv2.resize at img_resize = 0.5 of an even-sized image (bilinear = 2x2 area mean for
  * colour, nearest = every second pixel for depth), oh = src_h / 2, ow = src_w / 2; else oh = src_h, ow = src_w.

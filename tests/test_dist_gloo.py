@@ -21,7 +21,9 @@ def _worker(rank, world, port, B, out_dir):
     pose = torch.arange(n * B * 7, dtype=torch.float32).reshape(n, B, 7)[:, lo:hi].contiguous()
     loss = torch.arange(n * B * 3, dtype=torch.float32).reshape(n, B, 3)[:, lo:hi].contiguous() * 0.5
     final = torch.arange(B * 7, dtype=torch.float32).reshape(B, 7)[lo:hi].contiguous() + 100
-    P, L, F = _dist.gather_hypotheses(B, pose, loss, final)
+    flat = torch.cat([pose.reshape(-1), loss.reshape(-1), final.reshape(-1)])  # a rank's flat result buffer (DiffDope._fused_enqueue)
+    assert flat.numel() == _dist.flat_sizes(n, hi - lo, 3)[2]
+    P, L, F = _dist.gather_hypotheses(B, n, 3, flat)
     lr = torch.full((B,), float(rank + 1))
     _dist.broadcast_from_rank0(lr)
     torch.save({"P": P, "L": L, "F": F, "lr": lr, "range": (lo, hi)}, os.path.join(out_dir, "r%d.pt" % rank))

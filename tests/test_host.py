@@ -425,3 +425,9 @@ def test_bench_byte_model_matches_survey():
     assert bench.B_PER_GPU == 64 and bench.WINDOW == 640 and bench.METRIC.startswith("pose-hypotheses")
     sched = bench.lr_schedule(200)
     assert abs(sched[0] - 2.0) < 1e-12 and abs(sched[-1] - 0.2) < 1e-12
+    # the other configurations' figures of SURVEY.md 8(d): 3.95 MB (config 1, default losses), 17.80 (3), 15.73 (4), 105.96 (5)
+    assert abs(bench.survey_bytes_per_hit(P=320 * 320, c=0.24, rgb=False, depth=False)["total"] / 1e6 - 3.95) < 0.01
+    assert abs(bench.survey_bytes_per_hit(P=640 * 480, c=0.05)["total"] / 1e6 - 17.80) < 0.03
+    assert abs(bench.survey_bytes_per_hit(V=5002, T=10000, P=720 * 540, c=0.05, rgb=False, textured=False)["total"] / 1e6 - 15.73) < 0.01
+    assert abs(bench.survey_bytes_per_hit(V=25002, T=50000, P=1024 * 1024, c=0.5)["total"] / 1e6 - 105.96) < 0.01
+    assert len(bench.source_sha()) == 16 and bench.workload_config(4, "strong")["hypotheses_per_gpu"] == 64
