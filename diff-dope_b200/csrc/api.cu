@@ -79,6 +79,13 @@ struct ddope_scene {
     cudaEvent_t part_done[MAX_PARTS] = {};
     cudaEvent_t fork_event = nullptr;
     std::atomic<int> busy{0};
+    // binned rasterisation: per-tile triangle-id bins instead of the global z-buffer, for the loss passes
+    int raster_mode = 0;          // 0 = global z-buffer (raster_kernel), 1 = binned (bin_kernel + tile CTAs)
+    int bin_cap = 2048;           // ids per bin (multiple of 4: TMA copies are 16-byte granular)
+    int* bin_count = nullptr;     // [tiles]; all zero between calls
+    int* bin_ids = nullptr;       // [tiles, bin_cap]
+    int* bin_overflow = nullptr;  // device counter of overflowed bins since scene creation
+    size_t bin_tiles_cap = 0;
 };
 
 SceneBusy::SceneBusy(ddope_scene* s_) : s(s_), ok(false) {
@@ -344,8 +351,37 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, dev_id);
+    if (const char* e = getenv("DDOPE_RASTER")) s->raster_mode = (strcmp(e, "binned") == 0) ? 1 : 0;
+    if (const char* e = getenv("DDOPE_BIN_CAP")) {
+        const int v = atoi(e);
+        if (v >= 4 && v <= (1 << 20)) s->bin_cap = (v + 3) & ~3;
+    }
+    CK(cudaMalloc(&s->bin_overflow, sizeof(int)));
+    CK(cudaMemset(s->bin_overflow, 0, sizeof(int)));
     guard.p = nullptr;
     *out = s;
+    return 0;
+}
+
+extern "C" int ddope_scene_set_raster_mode(ddope_scene* s, int mode) {
+    if (!s) return fail("ddope_scene_set_raster_mode: null scene");
+    if (mode != 0 && mode != 1) return fail("ddope_scene_set_raster_mode: mode must be 0 (global z-buffer) or 1 (binned)");
+    s->raster_mode = mode;
+    return 0;
+}
+extern "C" int ddope_scene_raster_mode(const ddope_scene* s) { return s ? s->raster_mode : 0; }
+extern "C" int ddope_scene_set_bin_capacity(ddope_scene* s, int cap) {
+    if (!s) return fail("ddope_scene_set_bin_capacity: null scene");
+    if (cap < 4 || cap > (1 << 20)) return fail("ddope_scene_set_bin_capacity: capacity must be in [4, 2^20]");
+    SCENE_GUARD("ddope_scene_set_bin_capacity");
+    cap = (cap + 3) & ~3;
+    if (cap != s->bin_cap) {  // the bins are re-allocated (and zeroed) by the next loss call
+        CK(cudaDeviceSynchronize());
+        if (s->bin_count) CK(cudaFree(s->bin_count));
+        if (s->bin_ids) CK(cudaFree(s->bin_ids));
+        s->bin_count = nullptr; s->bin_ids = nullptr; s->bin_tiles_cap = 0;
+        s->bin_cap = cap;
+    }
     return 0;
 }
 
@@ -354,6 +390,7 @@ extern "C" int ddope_scene_destroy(ddope_scene* s) {
     cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex4); cudaFree(s->vcol); cudaFree(s->gt_edge); cudaFree(s->adam_state); cudaFree(s->tripos); cudaFree(s->tricol);
     cudaFree(s->seg_bbox); cudaFree(s->total_tiles); cudaFree(s->hyp); cudaFree(s->zbuf); cudaFree(s->partials);
     cudaFree(s->arrive);
+    cudaFree(s->bin_count); cudaFree(s->bin_ids); cudaFree(s->bin_overflow);
     for (int p = 0; p < ddope_scene::MAX_PARTS; p++) {
         if (s->part_stream[p]) cudaStreamDestroy(s->part_stream[p]);
         if (s->part_done[p]) cudaEventDestroy(s->part_done[p]);
@@ -505,6 +542,15 @@ static int ensure_buffers(ddope_scene* s, int B, bool need_partials, cudaStream_
             CK(cudaMalloc(&s->partials, sizeof(float) * pneed));
             s->partials_cap = pneed;
         }
+        if (s->raster_mode == 1 && (size_t)B * tiles > s->bin_tiles_cap) {
+            if (s->bin_count) CK(cudaFree(s->bin_count));
+            if (s->bin_ids) CK(cudaFree(s->bin_ids));
+            s->bin_count = nullptr; s->bin_ids = nullptr; s->bin_tiles_cap = 0;
+            CK(cudaMalloc(&s->bin_count, sizeof(int) * (size_t)B * tiles));
+            CK(cudaMalloc(&s->bin_ids, sizeof(int) * (size_t)B * tiles * s->bin_cap));
+            CK(cudaMemsetAsync(s->bin_count, 0, sizeof(int) * (size_t)B * tiles, st));
+            s->bin_tiles_cap = (size_t)B * tiles;
+        }
     }
     return 0;
 }
@@ -564,7 +610,7 @@ static int render_common(ddope_scene* s, const float* quat, const float* trans, 
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, false, st)) return r;
     LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
-    launch_pose(s->dev, quat, trans, mtx_in, nullptr, B, B, cfg, 0, s->hyp, s->total_tiles, st);
+    launch_pose(s->dev, quat, trans, mtx_in, nullptr, B, B, cfg, 2, s->hyp, s->total_tiles, st);
     launch_raster(s->dev, s->hyp, B, s->zbuf, st);
     RenderOut out = {rgb, depth, mask, rast};
     launch_pixel_render(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), s->zbuf, out, s->num_sms, st);
@@ -652,6 +698,7 @@ struct Part {
     unsigned int* arrive;
     float* partials;         // this part's tile rows start at index 0 here
     unsigned long long* zbuf;
+    BinArgs bins;            // this part's bins (count == nullptr: global z-buffer path)
 };
 
 static size_t tiles_per_hyp(const ddope_scene* s) {
@@ -679,6 +726,11 @@ static int fork_parts(ddope_scene* s, int B, cudaStream_t st, Part* parts, int* 
         P.arrive = s->arrive + p;
         P.partials = s->partials + (size_t)P.b0 * tiles_per_hyp(s) * NACC;
         P.zbuf = s->zbuf + (size_t)P.b0 * s->dev.zh * s->dev.zw;
+        P.bins = {nullptr, nullptr, 0, nullptr};
+        if (s->raster_mode == 1) {
+            const size_t t0 = (size_t)P.b0 * tiles_per_hyp(s);
+            P.bins = {s->bin_count + t0, s->bin_ids + t0 * s->bin_cap, s->bin_cap, s->bin_overflow};
+        }
         P.st = st;
     }
     if (n > 1) {
@@ -728,13 +780,15 @@ static void enqueue_iteration(ddope_scene* s, const Part& P, float* quat, float*
     HypState* cur = s->hyp + (size_t)s->hyp_cur * s->hyp_cap + P.b0;
     s->dbg_hyp_half = s->hyp_cur;
     HypState* nxt = s->hyp + (size_t)(s->hyp_cur ^ 1) * s->hyp_cap + P.b0;
+    const bool binned = P.bins.count != nullptr;
     {
         ProfMark m(s, P.st, K_RASTER);
-        launch_raster(s->dev, cur, P.B, P.zbuf, P.st);
+        if (binned) launch_bin(s->dev, cur, P.B, P.bins.count, const_cast<int*>(P.bins.ids), P.bins.cap, P.st);
+        else launch_raster(s->dev, cur, P.B, P.zbuf, P.st);
     }
     {
         ProfMark m(s, P.st, K_PIXEL);
-        launch_pixel_loss(s->dev, cur, P.total_tiles, P.B, max_tiles_of(s, P.B), cfg, P.zbuf, P.partials, s->num_sms, P.st);
+        launch_pixel_loss(s->dev, cur, P.total_tiles, P.B, max_tiles_of(s, P.B), cfg, P.zbuf, P.partials, P.bins, s->num_sms, P.st);
     }
     {
         ProfMark m(s, P.st, K_ITER);
@@ -743,8 +797,8 @@ static void enqueue_iteration(ddope_scene* s, const Part& P, float* quat, float*
         launch_iter(s->dev, cur, nxt, P.partials, P.B, B_global, B_hist, cfg, o, quat + 4 * (size_t)P.b0, trans + 3 * (size_t)P.b0,
                     lr_mult ? lr_mult + P.b0 : nullptr, lr_t, it, 1, do_update, more,
                     loss_table ? loss_table + NLOSS * (size_t)P.b0 : nullptr, grad ? grad + 7 * (size_t)P.b0 : nullptr,
-                    pose_hist ? pose_hist + 7 * (size_t)P.b0 : nullptr, loss_hist ? loss_hist + NLOSS * (size_t)P.b0 : nullptr, P.zbuf,
-                    P.total_tiles, P.arrive, P.st);
+                    pose_hist ? pose_hist + 7 * (size_t)P.b0 : nullptr, loss_hist ? loss_hist + NLOSS * (size_t)P.b0 : nullptr,
+                    binned ? nullptr : P.zbuf, P.total_tiles, P.arrive, P.st);
     }
     s->launches += 3;
 }
@@ -860,6 +914,7 @@ extern "C" int64_t ddope_debug_read(ddope_scene* s, int what, void* dst, int64_t
     size_t avail = 0;
     if (what == 0) { src = s->partials; avail = s->partials_cap * sizeof(float); }
     else if (what == 1) { src = s->hyp ? s->hyp + (size_t)s->dbg_hyp_half * s->hyp_cap : nullptr; avail = (size_t)s->hyp_cap * sizeof(HypState); }
+    else if (what == 2) { src = s->bin_overflow; avail = sizeof(int); }
     else { fail("ddope_debug_read: unknown buffer"); return -1; }
     if (!src) return 0;
     const size_t n = (size_t)bytes < avail ? (size_t)bytes : avail;

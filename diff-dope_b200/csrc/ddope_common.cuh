@@ -61,12 +61,15 @@ struct __align__(16) HypState {
     float qhat[4];
     float qnorm;
     float k_rgb, k_depth, k_mask;  // d loss / d pixel value scale: w_k * lr_b / (B_global * P * C)
-    int rx0, ry0, rx1, ry1;        // loss ROI in frame pixels, [rx0,rx1) x [ry0,ry1)
+    int rx0, ry0, rx1, ry1;        // ROI in frame pixels, [rx0,rx1) x [ry0,ry1): where triangles are rasterised and ids are valid (grown by 1 px)
     int tiles_x, tiles_y, tile_base;
     float k_edge;
     int face;  // sign of the snapped window-space area of a front-facing triangle (0: rasterise both orientations)
+    int gx0, gy0, gx1, gy1;        // tile grid: 32x32 tiles from (gx0,gy0), pixels up to (gx1,gy1) exclusive. Loss / backward passes: the ROI.
+                                   // Image output (ddope_render*): the whole window, while the ROI stays the object's bounding box.
     int pad[3];
 };
+static_assert(sizeof(HypState) == 224, "HypState layout (scripts/dev_maskgrad_dump.py reads words 40..46)");
 
 struct LossCfgDev {
     int use_rgb, use_depth, use_mask;

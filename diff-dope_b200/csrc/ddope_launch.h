@@ -38,7 +38,7 @@ inline void launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 bl
 bool pdl_enabled();  // api.cu: on unless DDOPE_NO_PDL is set
 
 // pose.cu
-// quat/trans -> HypState (M, MVP, loss ROI, tile prefix). roi_mode: 0 = window (render), 1 = tight (loss).
+// quat/trans -> HypState (M, MVP, ROI, tile grid, tile prefix). roi_mode: 0 = window (external gradients), 1 = tight (loss), 2 = image output.
 // mtx_in != null: take M = mtx_in[b] instead of building it from quat/trans.
 void launch_pose(const SceneDev& S, const float* quat, const float* trans, const float* mtx_in, const float* lr_mult,
                  int B, int B_global, LossCfgDev cfg, int roi_mode, HypState* hyp, int* total_tiles, cudaStream_t st);
@@ -57,6 +57,7 @@ void launch_copy_mtx(const HypState* hyp, int B, float* mtx, cudaStream_t st);
 // raster.cu
 void launch_clear(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, cudaStream_t st);
 void launch_raster(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, cudaStream_t st);
+void launch_bin(const SceneDev& S, const HypState* hyp, int B, int* bin_count, int* bin_ids, int bin_cap, cudaStream_t st);
 
 // pixel.cu
 struct RenderOut {
@@ -70,10 +71,17 @@ struct ExtGrad {          // dL/d(render outputs), window-sized, any may be null
     const float* d_depth;  // [B,wh,ww]
     const float* d_mask;   // [B,wh,ww]
 };
+// Binned rasterisation (bin_kernel + the tile CTAs of pixel_kernel): count == nullptr selects the global z-buffer path.
+struct BinArgs {
+    int* count;       // [tiles] triangles appended to each tile's bin by bin_kernel (reset to 0 by the tile CTA that consumes it)
+    const int* ids;   // [tiles, cap]
+    int cap;
+    int* overflow;    // number of tiles whose bin overflowed (they fall back to scanning the whole mesh)
+};
 void launch_pixel_ext(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                       const unsigned long long* zbuf, ExtGrad ext, float* partials, int num_sms, cudaStream_t st);
 void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
-                       LossCfgDev cfg, const unsigned long long* zbuf, float* partials, int num_sms, cudaStream_t st);
+                       LossCfgDev cfg, const unsigned long long* zbuf, float* partials, BinArgs bins, int num_sms, cudaStream_t st);
 void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                          const unsigned long long* zbuf, RenderOut out, int num_sms, cudaStream_t st);
 

@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "ddope_launch.h"
+#include "raster_common.cuh"
 
 namespace ddope {
 
@@ -373,6 +374,37 @@ __device__ __forceinline__ float warp_reduce_nacc(const float* v, int lane, int&
     return r;
 }
 
+// ---- TMA (bulk async copy) + mbarrier, raw PTX: the binned path stages each tile's triangle-id bin into shared memory with
+// cp.async.bulk (SASS: UBLKCP) completing on an mbarrier, double-buffered against the rasterisation of the previous chunk.
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of the buffer are ordered before the async write
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr int BIN_CHUNK = TILE_THREADS;  // triangles rasterised per step by a tile CTA of the binned path
+
 constexpr int MODE_RENDER = 0;  // write rgb / depth / mask / rast images (ddope_render*)
 constexpr int MODE_LOSS = 1;    // fused reference losses + backward (ddope_loss_grad / ddope_optimize)
 constexpr int MODE_EXT = 2;     // backward of externally supplied image gradients (ddope_render_bwd)
@@ -383,14 +415,22 @@ constexpr int DI_NONE = 3;            // no pair here / analysis found no usable
 constexpr int GRAY_W = TILE_W + 4;  // grey image of the render: tile + 2 px halo (edge loss)
 constexpr int DG_W = TILE_W + 2;    // dL/d(Gx,Gy): tile + 1 px halo
 
-template <int MODE, bool EDGE, bool MIP>
-__global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(SceneDev S, const HypState* __restrict__ hyp,
+template <int MODE, bool EDGE, bool MIP, bool BINNED>
+__global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED : PIXEL_MIN_BLOCKS) pixel_kernel(SceneDev S, const HypState* __restrict__ hyp,
                                                              const int* __restrict__ total_tiles, int B,
                                                              LossCfgDev cfg,
                                                              const unsigned long long* __restrict__ zbuf,
-                                                             float* __restrict__ partials, RenderOut out, ExtGrad ext) {
+                                                             float* __restrict__ partials, RenderOut out, ExtGrad ext, BinArgs bins) {
     __shared__ int s_ids[NPAIR];
-    __shared__ float s_alpha[2][NPAIR];
+    // the antialias blend factors (phases 3-6) share their storage with the tile's z-buffer of the binned path (phase 0)
+    __shared__ __align__(16) union { float alpha[2][NPAIR]; unsigned long long z[NPAIR]; } s_u;
+    static_assert(sizeof(s_u) == sizeof(float) * 2 * NPAIR, "alpha / z alias");
+    float (*s_alpha)[NPAIR] = s_u.alpha;
+    extern __shared__ int s_rec[];                                      // binned path: BIN_CHUNK triangle records (dynamic: 25.6 KB)
+    __shared__ int s_off[BINNED ? BIN_CHUNK : 1];
+    __shared__ __align__(16) int s_binids[BINNED ? 2 * BIN_CHUNK : 4];  // two TMA landing buffers
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    __shared__ int s_nlarge, s_bincnt;
     __shared__ __align__(4) unsigned char s_di[2][NPAIR];
     __shared__ unsigned short s_queue[2 * NPAIR];
     __shared__ float s_maa[MAA_W * MAA_H];
@@ -409,6 +449,16 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
     // pixel centre -> NDC: fx = xs*px + xo (nvdiffrast's xs = 2/W, xo = 1/W - 1), hoisted out of the pixel loop
     const float ndc_xs = S.ndc_xs, ndc_xo = S.ndc_xo, ndc_ys = S.ndc_ys, ndc_yo = S.ndc_yo;
     const int lx = tid % TILE_W, ly0 = tid / TILE_W;  // this thread's pixels: (lx, ly0 + 8k), k = 0..3
+    unsigned int mbar_use[2] = {0u, 0u};  // completed phases of the two TMA barriers (uniform across the CTA)
+    if (BINNED) {
+        if (tid == 0) {
+            mbar_init(&s_mbar[0], 1);
+            mbar_init(&s_mbar[1], 1);
+            s_nlarge = 0;
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
 
 #if DYN_TILES
     // work items are handed out by an atomic counter: tiles differ a lot in cost (silhouette tiles,
@@ -434,14 +484,96 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
         if (tid < 16) s_mvp[tid] = h.mvp[tid];
         if (tid < 4) s_m2[tid] = h.m[8 + tid];
         const int rx0 = h.rx0, ry0 = h.ry0, rx1 = h.rx1, ry1 = h.ry1;
+        const int gx1 = h.gx1, gy1 = h.gy1;  // end of the tile grid (== the ROI except for image output)
         const int local = item - h.tile_base;
         const int tx = local % h.tiles_x, ty = local / h.tiles_x;
-        const int ox = rx0 + tx * TILE_W, oy = ry0 + ty * TILE_H;  // tile origin, frame pixels
+        const int ox = h.gx0 + tx * TILE_W, oy = h.gy0 + ty * TILE_H;  // tile origin, frame pixels
         const float k_rgb = h.k_rgb, k_depth = h.k_depth, k_mask = h.k_mask, k_edge = h.k_edge;
         // valid z-buffer region of this hypothesis
         const int vx0 = max(rx0 - 1, S.zx0), vx1 = min(rx1 + 1, S.zx0 + S.zw);
         const int vy0 = max(ry0 - 1, S.zy0), vy1 = min(ry1 + 1, S.zy0 + S.zh);
         const unsigned long long* zb = zbuf + (size_t)b * S.zh * S.zw;
+
+        if (MODE == MODE_RENDER) {
+            // image output: a tile whose ids region does not touch the object's ROI is pure background (rgb 0, depth -t_z, mask 0,
+            // rast 0): streamed out with 16-byte stores, no z-buffer reads, no barriers
+            const bool bg = rx1 <= rx0 || ox - 2 >= vx1 || ox + TILE_W + 2 <= vx0 || oy - 2 >= vy1 || oy + TILE_H + 2 <= vy0;
+            if (bg) {  // CTA-uniform
+                const float bgd = -h.m[11];
+                const int fy = tid >> 3, fx4 = (tid & 7) * 4;
+                const int x = ox + fx4, y = oy + fy;
+                if (y < gy1 && x < gx1) {
+                    const size_t wp = ((size_t)b * S.wh + (y - S.wy0)) * S.ww + (x - S.wx0);
+                    if ((S.ww & 3) == 0 && x + 3 < gx1) {
+                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (out.rgb) { float4* p = reinterpret_cast<float4*>(out.rgb + wp * 3); p[0] = z4; p[1] = z4; p[2] = z4; }
+                        if (out.depth) *reinterpret_cast<float4*>(out.depth + wp) = make_float4(bgd, bgd, bgd, bgd);
+                        if (out.mask) *reinterpret_cast<float4*>(out.mask + wp) = z4;
+                        if (out.rast) { float4* p = reinterpret_cast<float4*>(out.rast) + wp; p[0] = z4; p[1] = z4; p[2] = z4; p[3] = z4; }
+                    } else {
+                        for (int k = 0; k < 4 && x + k < gx1; k++) {
+                            if (out.rgb) { out.rgb[(wp + k) * 3] = 0.f; out.rgb[(wp + k) * 3 + 1] = 0.f; out.rgb[(wp + k) * 3 + 2] = 0.f; }
+                            if (out.depth) out.depth[wp + k] = bgd;
+                            if (out.mask) out.mask[wp + k] = 0.f;
+                            if (out.rast) reinterpret_cast<float4*>(out.rast)[wp + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
+                __syncthreads();  // s_b / s_item are rewritten at the top of the loop
+                continue;
+            }
+        }
+
+        if (BINNED) {
+            // 0. binned path: rasterise this tile's bin into the shared-memory z-buffer. The bin (triangle indices appended by
+            //    bin_kernel) is staged by TMA bulk copies, BIN_CHUNK ids at a time, the copy of chunk c+1 in flight while chunk c
+            //    is set up and rasterised (same per-triangle code as raster_kernel: bit-equal keys).
+            const int qx0 = max(ox - 2, vx0), qx1 = min(ox + TILE_W + 2, vx1) - 1;  // ids region inside the valid region, inclusive
+            const int qy0 = max(oy - 2, vy0), qy1 = min(oy + TILE_H + 2, vy1) - 1;
+            for (int i = tid; i < NPAIR; i += TILE_THREADS) s_u.z[i] = EMPTY_KEY;
+            if (tid == 0) {
+                s_bincnt = bins.count[item];
+                bins.count[item] = 0;  // invariant: every bin is empty between iterations and API calls
+            }
+            __syncthreads();
+            const int n = s_bincnt;
+            const ZShared zwrite = {s_u.z, ox - 2, oy - 2, IDS_W};
+            const int face = h.face;
+            if (qx0 <= qx1 && qy0 <= qy1 && n > 0) {
+                if (n <= bins.cap) {
+                    const int* src = bins.ids + (size_t)item * bins.cap;
+                    const int nchunks = (n + BIN_CHUNK - 1) / BIN_CHUNK;
+                    if (tid == 0) {
+                        const unsigned int bytes = (unsigned int)(((min(n, BIN_CHUNK) + 3) & ~3) * 4);
+                        mbar_expect_tx(&s_mbar[0], bytes);
+                        tma_load_1d(s_binids, src, bytes, &s_mbar[0]);
+                    }
+                    for (int c = 0; c < nchunks; c++) {
+                        const int buf = c & 1;
+                        if (tid == 0 && c + 1 < nchunks) {  // buffer buf^1 was last read before the barrier that ended chunk c-1
+                            const unsigned int bytes = (unsigned int)(((min(n - (c + 1) * BIN_CHUNK, BIN_CHUNK) + 3) & ~3) * 4);
+                            mbar_expect_tx(&s_mbar[buf ^ 1], bytes);
+                            tma_load_1d(s_binids + (buf ^ 1) * BIN_CHUNK, src + (size_t)(c + 1) * BIN_CHUNK, bytes, &s_mbar[buf ^ 1]);
+                        }
+                        mbar_wait(&s_mbar[buf], mbar_use[buf] & 1u);
+                        mbar_use[buf]++;
+                        const int k = c * BIN_CHUNK + tid;
+                        const int t = (k < n) ? s_binids[buf * BIN_CHUNK + tid] : -1;
+                        cta_raster_chunk<TILE_THREADS>(S, s_mvp, face, qx0, qx1, qy0, qy1, t, s_rec, s_off, &s_nlarge, zwrite);
+                        __syncthreads();
+                    }
+                } else {
+                    // the bin overflowed (more triangles touch this tile than a bin holds): scan the whole mesh instead
+                    if (tid == 0) atomicAdd(bins.overflow, 1);
+                    for (int t0 = 0; t0 < S.T; t0 += TILE_THREADS) {
+                        const int t = (t0 + tid < S.T) ? t0 + tid : -1;
+                        cta_raster_chunk<TILE_THREADS>(S, s_mvp, face, qx0, qx1, qy0, qy1, t, s_rec, s_off, &s_nlarge, zwrite);
+                        __syncthreads();
+                    }
+                }
+            }
+            __syncthreads();
+        }
 
         // 1. triangle ids of tile + 2 px halo, one warp per row (row loads coalesce; all of a warp's
         //    z-buffer loads are issued before any is consumed), plus per-row coverage / in-frame bitmasks
@@ -449,15 +581,15 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
             const int lane = tid & 31, warp = tid >> 5;
             constexpr int ROWS_PER_WARP = (IDS_H + 7) / 8;
             int idr[ROWS_PER_WARP][2];
-#pragma unroll
             const unsigned int vw = (unsigned int)(vx1 - vx0);
+#pragma unroll
             for (int k = 0; k < ROWS_PER_WARP; k++) {
                 const int iy = warp + 8 * k;
                 const int y = oy - 2 + iy;
                 // row tests are warp-uniform; the column tests use one unsigned compare per range
                 const bool row_in = iy < IDS_H && (unsigned int)y < (unsigned int)S.H;
                 const bool row_z = row_in && y >= vy0 && y < vy1;
-                const unsigned long long* zrow = zb + (size_t)(y - S.zy0) * S.zw - S.zx0;
+                const unsigned long long* zrow = BINNED ? (s_u.z + iy * IDS_W - (ox - 2)) : (zb + (size_t)(y - S.zy0) * S.zw - S.zx0);
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
                     const int ix = lane + 32 * half;
@@ -473,6 +605,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                     idr[k][half] = id;
                 }
             }
+            // (binned path: s_u.z is not touched again; s_alpha, the same storage, is first written in phase 3, two barriers from here)
 #pragma unroll
             for (int k = 0; k < ROWS_PER_WARP; k++) {
                 const int iy = warp + 8 * k;
@@ -631,7 +764,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
                         const float gy = ((tl - bl) + 2.f * (tc - bc)) + (tr - br);
                         const float e = sqrtf(gx * gx + gy * gy + 1e-12f);
                         const float diff = (e - S.gt_edge[gp]) * sg;
-                        const bool own = ix >= 1 && ix <= TILE_W && iy >= 1 && iy <= TILE_H && x < rx1 && y < ry1;
+                        const bool own = ix >= 1 && ix <= TILE_W && iy >= 1 && iy <= TILE_H && x < gx1 && y < gy1;
                         if (own) acc[19] += fabsf(diff);
                         const float de = k_edge * sgn(diff) * sg / e;
                         dgx = de * gx; dgy = de * gy;
@@ -646,7 +779,7 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
         for (int rep = 0; rep < TILE_H / 8; rep++) {
             const int ly = ly0 + 8 * rep;
             const int x = ox + lx, y = oy + ly;
-            if (!(x < rx1 && y < ry1)) continue;
+            if (!(x < gx1 && y < gy1)) continue;
             const int id = s_ids[(ly + 2) * IDS_W + (lx + 2)];
             const float maa = (nq > 0) ? s_maa[(ly + 1) * MAA_W + (lx + 1)] : ((id >= 0) ? 1.f : 0.f);
             const size_t gpix = (size_t)y * S.W + x;
@@ -664,7 +797,10 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
             float rgb[3] = {0.f, 0.f, 0.f};
             float depth = -s_m2[3];
             float gu = 0.f, gv = 0.f;  // dL/d(u,v)
-            if (id >= 0) {
+            // a covered pixel where the segmentation is zero in all channels contributes exactly nothing to the rgb / depth losses and
+            // their gradients (|(render - target) * 0|): it is not shaded. (The edge loss needs the render of every window pixel.)
+            const bool dead = MODE == MODE_LOSS && !EDGE && seg[0] == 0.f && seg[1] == 0.f && seg[2] == 0.f;
+            if (id >= 0 && !dead) {
                 gtouch = true;
                 Shade sh;
                 constexpr bool EX = (MODE == MODE_RENDER);
@@ -832,45 +968,69 @@ __global__ void __launch_bounds__(TILE_THREADS, PIXEL_MIN_BLOCKS) pixel_kernel(S
     }
 }
 
-static int pixel_grid(int max_tiles, int num_sms) {
-    static const int per_sm = [] { const char* e = getenv("DDOPE_PIXEL_CTAS_PER_SM"); int v = e ? atoi(e) : 4; return v >= 1 && v <= 8 ? v : 4; }();
-    int g = num_sms * per_sm;
+static int pixel_grid(int max_tiles, int num_sms, bool binned) {
+    static const int per_sm = [] { const char* e = getenv("DDOPE_PIXEL_CTAS_PER_SM"); int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 0; }();
+    int g = num_sms * (per_sm ? per_sm : (binned ? PIXEL_MIN_BLOCKS_BINNED : PIXEL_MIN_BLOCKS));
     if (g > max_tiles) g = max_tiles;
     return g < 1 ? 1 : g;
 }
 
-template <int MODE, bool EDGE>
+template <int MODE, bool EDGE, bool MIP, bool BINNED>
+static void launch_pixel_inst(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int grid, LossCfgDev cfg,
+                              const unsigned long long* zbuf, float* partials, RenderOut out, ExtGrad ext, BinArgs bins, cudaStream_t st) {
+    size_t dyn = 0;
+    if (BINNED) {
+        dyn = sizeof(int) * BIN_CHUNK * REC_WORDS;
+        static bool once = [] {  // static + dynamic shared memory of the binned variant exceeds the 48 KB default
+            note_launch(cudaFuncSetAttribute(pixel_kernel<MODE, EDGE, MIP, BINNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * BIN_CHUNK * REC_WORDS)));
+            return true;
+        }();
+        (void)once;
+    }
+    launch_kernel(pdl_enabled(), pixel_kernel<MODE, EDGE, MIP, BINNED>, dim3(grid), dim3(TILE_THREADS), dyn, st, S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext, bins);
+}
+
+template <int MODE, bool EDGE, bool BINNED>
 static void launch_pixel(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles, LossCfgDev cfg,
-                         const unsigned long long* zbuf, float* partials, RenderOut out, ExtGrad ext, int num_sms, cudaStream_t st) {
-    const int grid = pixel_grid(max_tiles, num_sms);
+                         const unsigned long long* zbuf, float* partials, RenderOut out, ExtGrad ext, BinArgs bins, int num_sms, cudaStream_t st) {
+    const int grid = pixel_grid(max_tiles, num_sms, BINNED);
     if (S.tex4 && S.tex_filter == 1)
-        launch_kernel(pdl_enabled(), pixel_kernel<MODE, EDGE, true>, dim3(grid), dim3(TILE_THREADS), 0, st, S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext);
+        launch_pixel_inst<MODE, EDGE, true, BINNED>(S, hyp, total_tiles, B, grid, cfg, zbuf, partials, out, ext, bins, st);
     else
-        launch_kernel(pdl_enabled(), pixel_kernel<MODE, EDGE, false>, dim3(grid), dim3(TILE_THREADS), 0, st, S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext);
+        launch_pixel_inst<MODE, EDGE, false, BINNED>(S, hyp, total_tiles, B, grid, cfg, zbuf, partials, out, ext, bins, st);
 }
 
 void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
-                       LossCfgDev cfg, const unsigned long long* zbuf, float* partials, int num_sms, cudaStream_t st) {
+                       LossCfgDev cfg, const unsigned long long* zbuf, float* partials, BinArgs bins, int num_sms, cudaStream_t st) {
     RenderOut none = {nullptr, nullptr, nullptr, nullptr};
     ExtGrad noext = {nullptr, nullptr, nullptr};
-    if (cfg.use_edge)
-        launch_pixel<MODE_LOSS, true>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, noext, num_sms, st);
-    else
-        launch_pixel<MODE_LOSS, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, noext, num_sms, st);
+    if (bins.count) {
+        if (cfg.use_edge)
+            launch_pixel<MODE_LOSS, true, true>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, noext, bins, num_sms, st);
+        else
+            launch_pixel<MODE_LOSS, false, true>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, noext, bins, num_sms, st);
+    } else {
+        if (cfg.use_edge)
+            launch_pixel<MODE_LOSS, true, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, noext, bins, num_sms, st);
+        else
+            launch_pixel<MODE_LOSS, false, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, noext, bins, num_sms, st);
+    }
 }
 
 void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                          const unsigned long long* zbuf, RenderOut out, int num_sms, cudaStream_t st) {
     LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
     ExtGrad noext = {nullptr, nullptr, nullptr};
-    launch_pixel<MODE_RENDER, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, nullptr, out, noext, num_sms, st);
+    BinArgs nobins = {nullptr, nullptr, 0, nullptr};
+    launch_pixel<MODE_RENDER, false, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, nullptr, out, noext, nobins, num_sms, st);
 }
 
 void launch_pixel_ext(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                       const unsigned long long* zbuf, ExtGrad ext, float* partials, int num_sms, cudaStream_t st) {
     LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
     RenderOut none = {nullptr, nullptr, nullptr, nullptr};
-    launch_pixel<MODE_EXT, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, ext, num_sms, st);
+    BinArgs nobins = {nullptr, nullptr, 0, nullptr};
+    launch_pixel<MODE_EXT, false, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, ext, nobins, num_sms, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -85,13 +85,16 @@ __device__ __forceinline__ bool roi_corner(const SceneDev& S, const float* mvp, 
     return (fabsf(sx) < 1e6f) && (fabsf(sy) < 1e6f);
 }
 
-// ROI = (screen bbox of the AABB corners, grown) U (bbox of seg != 0), clipped to the window; tile grid.
+// roi_mode 1 (losses): ROI = (screen bbox of the AABB corners, grown) U (bbox of seg != 0), clipped to the window; the tile grid covers it.
+// roi_mode 0 (external image gradients): ROI = tile grid = the whole window.
+// roi_mode 2 (image output): ROI = screen bbox of the object only (what is rasterised / cleared), tile grid = the whole window.
 __device__ void hyp_roi_part(const SceneDev& S, bool full, float mnx, float mny, float mxx, float mxy, int roi_mode, HypState& h) {
-    int x0 = S.wx0, y0 = S.wy0, x1 = S.wx0 + S.ww, y1 = S.wy0 + S.wh;  // window, exclusive end
-    if (roi_mode == 1 && !full) {
+    const int wx0 = S.wx0, wy0 = S.wy0, wx1 = S.wx0 + S.ww, wy1 = S.wy0 + S.wh;  // window, exclusive end
+    int x0 = wx0, y0 = wy0, x1 = wx1, y1 = wy1;
+    if (roi_mode != 0 && !full) {
         int ox0 = (int)floorf(mnx) - 2, ox1 = (int)ceilf(mxx) + 3;  // exclusive end
         int oy0 = (int)floorf(mny) - 2, oy1 = (int)ceilf(mxy) + 3;
-        if (S.gt_seg != nullptr) {
+        if (roi_mode == 1 && S.gt_seg != nullptr) {
             int sx0 = S.seg_bbox[0], sy0 = S.seg_bbox[1], sx1 = S.seg_bbox[2], sy1 = S.seg_bbox[3];
             if (sx0 <= sx1 && sy0 <= sy1) {
                 ox0 = min(ox0, sx0); oy0 = min(oy0, sy0);
@@ -103,8 +106,10 @@ __device__ void hyp_roi_part(const SceneDev& S, bool full, float mnx, float mny,
     }
     if (x1 <= x0 || y1 <= y0) { x0 = x1 = S.wx0; y0 = y1 = S.wy0; }
     h.rx0 = x0; h.ry0 = y0; h.rx1 = x1; h.ry1 = y1;
-    h.tiles_x = (x1 - x0 + TILE_W - 1) / TILE_W;
-    h.tiles_y = (y1 - y0 + TILE_H - 1) / TILE_H;
+    if (roi_mode == 2) { h.gx0 = wx0; h.gy0 = wy0; h.gx1 = wx1; h.gy1 = wy1; }
+    else { h.gx0 = x0; h.gy0 = y0; h.gx1 = x1; h.gy1 = y1; }
+    h.tiles_x = (h.gx1 - h.gx0 + TILE_W - 1) / TILE_W;
+    h.tiles_y = (h.gy1 - h.gy0 + TILE_H - 1) / TILE_H;
     h.tile_base = 0;
 }
 
@@ -122,7 +127,7 @@ __device__ void hyp_from_pose(const SceneDev& S, const float* qb, const float* t
     hyp_pose_part(S, qb, tb, mtx_b, h);
     bool full = false;
     float mnx = 1e30f, mny = 1e30f, mxx = -1e30f, mxy = -1e30f;
-    if (roi_mode == 1) {
+    if (roi_mode != 0) {
         for (int c = 0; c < 8; c++) {
             float sx, sy;
             if (!roi_corner(S, h.mvp, c, sx, sy)) { full = true; break; }
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
     pdl_wait();  // partial sums of the preceding pixel_kernel
     const int b = blockIdx.y;
     if (blockIdx.x > 0) {
-        if (!do_step) return;  // nothing was rasterised yet
+        if (!do_step || zbuf == nullptr) return;  // nothing was rasterised yet / binned path: no global z-buffer to restore
         const HypState& h = hyp_old[b];
         const int rx0 = h.rx0, ry0 = h.ry0, rx1 = h.rx1, ry1 = h.ry1;
         if (rx1 <= rx0) return;
@@ -456,7 +461,7 @@ void launch_iter(const SceneDev& S, const HypState* hyp_old, HypState* hyp_new, 
                  int B_hist, LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, float lr_t, int it,
                  int do_step, int do_update, int do_pose, float* loss_table, float* grad_out, float* pose_hist,
                  float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, cudaStream_t st) {
-    launch_kernel(pdl_enabled(), iter_kernel, dim3(do_step ? 1 + CLEAR_CTAS : 1, B), dim3(ITER_THREADS), 0, st, S, hyp_old, hyp_new, partials, B,
+    launch_kernel(pdl_enabled(), iter_kernel, dim3((do_step && zbuf) ? 1 + CLEAR_CTAS : 1, B), dim3(ITER_THREADS), 0, st, S, hyp_old, hyp_new, partials, B,
                   B_global, B_hist, cfg, opt, quat, trans, lr_mult, lr_t, it, do_step, do_update, do_pose, loss_table, grad_out, pose_hist,
                   loss_hist, zbuf, total_tiles, arrive);
 }

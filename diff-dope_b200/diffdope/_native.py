@@ -74,6 +74,10 @@ def lib():
     L.ddope_scene_set_window.argtypes = [vp, ci, ci, ci, ci]
     L.ddope_scene_set_texture_filter.argtypes = [vp, ci, ci]
     L.ddope_scene_set_culling.argtypes = [vp, ci]
+    L.ddope_scene_set_raster_mode.argtypes = [vp, ci]
+    L.ddope_scene_raster_mode.argtypes = [vp]
+    L.ddope_scene_raster_mode.restype = ci
+    L.ddope_scene_set_bin_capacity.argtypes = [vp, ci]
     L.ddope_scene_mesh_orientation.argtypes = [vp]
     L.ddope_scene_mesh_orientation.restype = ci
     L.ddope_scene_set_optimizer.argtypes = [vp, ctypes.POINTER(OptimCfg)]
@@ -93,7 +97,7 @@ def lib():
         "ddope_scene_destroy", "ddope_scene_set_camera", "ddope_scene_set_target", "ddope_scene_set_window",
         "ddope_render", "ddope_render_mtx", "ddope_render_bwd", "ddope_loss_grad", "ddope_optimize",
         "ddope_profile_begin", "ddope_profile_end", "ddope_scene_set_texture_filter", "ddope_scene_set_optimizer",
-        "ddope_scene_set_culling", "ddope_image_from_raw",
+        "ddope_scene_set_culling", "ddope_image_from_raw", "ddope_scene_set_raster_mode", "ddope_scene_set_bin_capacity",
     ):
         getattr(L, name).restype = ci
     if L.ddope_abi_version() != 2:
@@ -213,6 +217,23 @@ class NativeScene:
     def set_culling(self, auto=True):
         """Back-face culling of closed, consistently oriented meshes (default on); False rasterises every triangle."""
         _check(lib().ddope_scene_set_culling(self._h, 1 if auto else 0))
+
+    def set_raster_mode(self, mode, bin_capacity=None):
+        """'zbuffer' (one launch over all triangles, global 64-bit atomicMin z-buffer) or 'binned' (per-tile triangle bins staged by
+        TMA, shared-memory z-buffer inside the pixel pass). Same raster rule, bit-identical results."""
+        modes = {"zbuffer": 0, "binned": 1, 0: 0, 1: 1}
+        if mode not in modes:
+            raise RuntimeError("ddope_b200: unknown raster mode %r" % (mode,))
+        _check(lib().ddope_scene_set_raster_mode(self._h, modes[mode]))
+        if bin_capacity is not None:
+            _check(lib().ddope_scene_set_bin_capacity(self._h, int(bin_capacity)))
+
+    def raster_mode(self):
+        return ("zbuffer", "binned")[int(lib().ddope_scene_raster_mode(self._h))]
+
+    def bin_overflows(self):
+        """Tile bins that overflowed (and fell back to scanning the mesh) since the scene was created."""
+        return int(self.debug_read(2, 4).view(np.int32)[0])
 
     def mesh_orientation(self):
         """+1 / -1: closed mesh of positive / negative volume (culling applies); 0: open or inconsistent mesh."""

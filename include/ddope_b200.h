@@ -154,6 +154,19 @@ int ddope_scene_mesh_orientation(const ddope_scene* s);
 /* The same classification for host arrays (pos [V,3], tri [T,3]); pure host code, needs no GPU. */
 int ddope_mesh_orientation(const float* pos_host, int V, const int32_t* tri_host, int T);
 
+/* How ddope_loss_grad / ddope_optimize rasterise (same raster rule, bit-identical results; replaces dr.rasterize's GL draw,
+ * diffdope/diffdope.py:198-200). mode 0: one launch over every (hypothesis, triangle), winners through 64-bit atomicMin into a
+ * global z-buffer over the loss ROI. mode 1 ("binned"): a binning launch appends each visible triangle to the bins of the 32x32
+ * pixel tiles (+ 2 px halo) it touches; each tile CTA of the pixel pass stages its bin into shared memory with TMA bulk copies
+ * and rasterises it into a shared-memory z-buffer before shading -- no global z-buffer traffic, no restore pass. The default is the
+ * faster one on the benchmark workload; the environment variable DDOPE_RASTER=zbuffer|binned overrides it
+ * at scene creation. */
+int ddope_scene_set_raster_mode(ddope_scene* s, int mode);
+int ddope_scene_raster_mode(const ddope_scene* s);
+/* Triangle ids one tile bin can hold (default 2048, rounded up to a multiple of 4). A tile whose bin overflows is still
+ * rendered correctly: its CTA scans the whole mesh instead (slow path; counted, see ddope_debug_read). */
+int ddope_scene_set_bin_capacity(ddope_scene* s, int capacity);
+
 /* Extensions (defaults = reference behaviour). max_levels <= 0: the full chain down to 1x1. */
 int ddope_scene_set_texture_filter(ddope_scene* s, int mode, int max_levels);
 int ddope_scene_set_optimizer(ddope_scene* s, const ddope_optim_cfg* cfg);
@@ -234,7 +247,7 @@ int ddope_profile_end(ddope_scene* s, float* ms_out3, int* launches_out3);
 /* Debug hook (tests / parity investigations only): synchronise and copy internal work buffers of the last
  * ddope_loss_grad / ddope_optimize call to host memory. what 0 = per-tile partial rows [tiles,20] float32
  * (12 dL/dMVP rows x,y,w + 4 dL/dM row z + 4 loss sums), 1 = the HypState records [B] (208 bytes each) the
- * last iteration read. Copies min(bytes, available) and returns the number of bytes copied, negative on error. */
+ * last iteration read, 2 = int32 count of tile bins that overflowed since scene creation (binned rasterisation). Copies min(bytes, available) and returns the number of bytes copied, negative on error. */
 int64_t ddope_debug_read(ddope_scene* s, int what, void* dst_host, int64_t bytes);
 
 #ifdef __cplusplus

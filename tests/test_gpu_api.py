@@ -265,8 +265,8 @@ def test_extension_config_keys_through_the_api():
     c = dd.DiffDope(cfg=_cfg(**{"hyperparameters.batchsize": 2, "hyperparameters.nb_iterations": 3, "hyperparameters.optimizer": "adam",
                                 "hyperparameters.base_lr": 0.01, "render.texture_filter": "linear-mipmap-linear", "losses.l1_rgb_with_mask": True}))
     c.run_optimization()
-    q0, t0 = c._pose_hist[0, :, :4].cpu(), c._pose_hist[0, :, 4:].cpu()
-    q1, t1 = c._pose_hist[1, :, :4].cpu(), c._pose_hist[1, :, 4:].cpu()
+    q0, t0 = c._pose_hist_host[0, :, :4].cpu(), c._pose_hist_host[0, :, 4:].cpu()
+    q1, t1 = c._pose_hist_host[1, :, :4].cpu(), c._pose_hist_host[1, :, 4:].cpu()
     lr0 = 0.01 * 0.1 ** 1.0
     assert np.allclose((q1 - q0).abs().numpy(), lr0, rtol=5e-3) and np.allclose((t1 - t0).abs().numpy(), lr0, rtol=5e-3)
 
