@@ -86,6 +86,11 @@ struct ddope_scene {
     int* bin_ids = nullptr;       // [tiles, bin_cap]
     int* bin_overflow = nullptr;  // device counter of overflowed bins since scene creation
     size_t bin_tiles_cap = 0;
+    // small batches (one part): the 1 + 3n launches of a ddope_optimize call are captured into a CUDA graph on an internal stream
+    // (programmatic-dependent-launch edges kept) and replayed as one launch; the executable graph is updated in place from call to call
+    cudaGraphExec_t graph_exec = nullptr;
+    int use_graph = 1;            // DDOPE_GRAPH=0 / ddope_scene_set_graph(s, 0): launch directly
+    int64_t graph_calls = 0;      // calls served by a graph launch (tests / bench)
 };
 
 SceneBusy::SceneBusy(ddope_scene* s_) : s(s_), ok(false) {
@@ -351,6 +356,7 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, dev_id);
+    if (const char* e = getenv("DDOPE_GRAPH")) s->use_graph = atoi(e) != 0;
     if (const char* e = getenv("DDOPE_RASTER")) s->raster_mode = (strcmp(e, "binned") == 0) ? 1 : 0;
     if (const char* e = getenv("DDOPE_BIN_CAP")) {
         const int v = atoi(e);
@@ -391,6 +397,7 @@ extern "C" int ddope_scene_destroy(ddope_scene* s) {
     cudaFree(s->seg_bbox); cudaFree(s->total_tiles); cudaFree(s->hyp); cudaFree(s->zbuf); cudaFree(s->partials);
     cudaFree(s->arrive);
     cudaFree(s->bin_count); cudaFree(s->bin_ids); cudaFree(s->bin_overflow);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     for (int p = 0; p < ddope_scene::MAX_PARTS; p++) {
         if (s->part_stream[p]) cudaStreamDestroy(s->part_stream[p]);
         if (s->part_done[p]) cudaEventDestroy(s->part_done[p]);
@@ -858,6 +865,25 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     Part parts[ddope_scene::MAX_PARTS];
     int n_parts = 1;
     if (int r = fork_parts(s, B, st, parts, &n_parts)) return r;
+
+    // Small batch: the host cannot enqueue ~5 us kernels as fast as the GPU finishes them (3.8 us per launch measured), so the
+    // whole call is captured once and launched as a graph. Capture needs a real stream (the caller's may be the legacy default
+    // stream, which cannot be captured): the internal stream of part 0, forked from / joined into the caller's stream.
+    bool capturing = false;
+    cudaStream_t gs = nullptr;
+    if (s->use_graph && n_parts == 1 && !s->profiling && n_iters >= 2) {
+        if (!s->fork_event) CK(cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming));
+        if (!s->part_stream[0]) CK(cudaStreamCreateWithFlags(&s->part_stream[0], cudaStreamNonBlocking));
+        if (!s->part_done[0]) CK(cudaEventCreateWithFlags(&s->part_done[0], cudaEventDisableTiming));
+        gs = s->part_stream[0];
+        if (cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            capturing = true;
+            parts[0].st = gs;
+        } else {
+            cudaGetLastError();
+        }
+    }
+
     s->hyp_cur = 0;
     for (int p = 0; p < n_parts; p++) enqueue_prologue(s, parts[p], quat, trans, lr_mult, B_global, c, opt);
     cudaError_t lerr = cudaSuccess;
@@ -870,8 +896,45 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
         lerr = take_launch_error();  // checked after every iteration's launches, not once at the end
         if (lerr != cudaSuccess) break;
     }
+    if (capturing) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+        if (ce == cudaSuccess && lerr == cudaSuccess) {
+            if (s->graph_exec) {
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(s->graph_exec, graph, &info) != cudaSuccess) {  // other topology (n_iters, raster mode, ...): rebuild
+                    cudaGetLastError();
+                    cudaGraphExecDestroy(s->graph_exec);
+                    s->graph_exec = nullptr;
+                }
+            }
+            if (!s->graph_exec) ce = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+            if (ce == cudaSuccess) {
+                CK(cudaEventRecord(s->fork_event, st));
+                CK(cudaStreamWaitEvent(gs, s->fork_event, 0));
+                CK(cudaGraphLaunch(s->graph_exec, gs));
+                CK(cudaEventRecord(s->part_done[0], gs));
+                CK(cudaStreamWaitEvent(st, s->part_done[0], 0));
+                s->graph_calls++;
+            }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (ce != cudaSuccess || lerr != cudaSuccess) {
+            cudaGetLastError();
+            if (lerr != cudaSuccess) return fail(std::string("ddope_optimize: kernel launch failed during graph capture: ") + cudaGetErrorString(lerr));
+            return fail(std::string("ddope_optimize: CUDA graph capture / instantiation failed: ") + cudaGetErrorString(ce) + " (set DDOPE_GRAPH=0 to launch directly)");
+        }
+        return 0;
+    }
     if (int r = join_parts(s, st, parts, n_parts)) return r;  // joined on the error path too
     if (lerr != cudaSuccess) return fail(std::string("ddope_optimize: kernel launch failed: ") + cudaGetErrorString(lerr));
+    return 0;
+}
+
+extern "C" int64_t ddope_graph_launch_count(const ddope_scene* s) { return s ? s->graph_calls : 0; }
+extern "C" int ddope_scene_set_graph(ddope_scene* s, int on) {
+    if (!s) return fail("ddope_scene_set_graph: null scene");
+    s->use_graph = on != 0;
     return 0;
 }
 

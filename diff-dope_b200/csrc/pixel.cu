@@ -416,7 +416,7 @@ constexpr int GRAY_W = TILE_W + 4;  // grey image of the render: tile + 2 px hal
 constexpr int DG_W = TILE_W + 2;    // dL/d(Gx,Gy): tile + 1 px halo
 
 template <int MODE, bool EDGE, bool MIP, bool BINNED>
-__global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED : PIXEL_MIN_BLOCKS) pixel_kernel(SceneDev S, const HypState* __restrict__ hyp,
+__global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED : (EDGE ? PIXEL_MIN_BLOCKS_EDGE : PIXEL_MIN_BLOCKS)) pixel_kernel(SceneDev S, const HypState* __restrict__ hyp,
                                                              const int* __restrict__ total_tiles, int B,
                                                              LossCfgDev cfg,
                                                              const unsigned long long* __restrict__ zbuf,
@@ -443,7 +443,11 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
     __shared__ float s_dgx[EDGE ? DG_W * DG_W : 1], s_dgy[EDGE ? DG_W * DG_W : 1];
 
     pdl_trigger();
-    pdl_wait();  // z-buffer of the preceding raster_kernel
+    // Loss / backward passes need the z-buffer (or the bins) of the preceding launch at once. Image output does not for its
+    // background tiles (90 % of a window): those are streamed out while the rasteriser is still running, and a CTA waits only
+    // before its first tile that touches the object's ROI. (hyp / total_tiles come from pose_kernel, complete before either started.)
+    bool waited = MODE != MODE_RENDER;
+    if (waited) pdl_wait();
     const int total = *total_tiles;
     const int tid = threadIdx.x;
     // pixel centre -> NDC: fx = xs*px + xo (nvdiffrast's xs = 2/W, xo = 1/W - 1), hoisted out of the pixel loop
@@ -521,6 +525,10 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
                 }
                 __syncthreads();  // s_b / s_item are rewritten at the top of the loop
                 continue;
+            }
+            if (!waited) {
+                pdl_wait();
+                waited = true;
             }
         }
 
@@ -729,21 +737,108 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
         bool gtouch = false;  // this thread added to a gradient accumulator (acc[0..15])
 
         if (EDGE) {
-            // E1. grey image of the render over tile + 2 px halo (0 for background and outside the loss window:
-            //     the Sobel stencil is zero-padded at the window)
-            for (int i = tid; i < GRAY_W * GRAY_W; i += TILE_THREADS) {
-                const int ix = i % GRAY_W, iy = i / GRAY_W;
+            // Edge loss (EDGE implies MODE_LOSS). The Sobel stencil couples neighbouring pixels, so the shading is split around it
+            // instead of being done twice:
+            //   A   forward shading of this thread's four tile pixels: L1 rgb / depth / mask terms, the direct depth gradient, the
+            //       grey value -> shared memory, and -- in registers -- what the backward will need: dL/d(u,v) so far and
+            //       d grey / d(u,v). Spare iterations shade the 272 pixels of the 2 px halo ring for their grey value only.
+            //   E2  Sobel magnitude of the render, the edge loss against the precomputed target edges, dL/d(Gx, Gy)
+            //   B   backward: dL/d(u,v) += dL/d grey * d grey/d(u,v), barycentric setup again (no texture fetch), dL/dMVP.
+            float st_gu[TILE_H / 8], st_gv[TILE_H / 8], st_G0[TILE_H / 8], st_G1[TILE_H / 8];
+            const int wx1 = S.wx0 + S.ww, wy1 = S.wy0 + S.wh;
+            for (int i = tid; i < GRAY_W * GRAY_W - TILE_W * TILE_H; i += TILE_THREADS) {  // halo ring: rows 0,1 | rows 34,35 | columns 0,1,34,35
+                int ix, iy;
+                if (i < 2 * GRAY_W) { iy = i / GRAY_W; ix = i - iy * GRAY_W; }
+                else if (i < 4 * GRAY_W) { const int j = i - 2 * GRAY_W; iy = j / GRAY_W; ix = j - iy * GRAY_W; iy += TILE_H + 2; }
+                else { const int j = i - 4 * GRAY_W; iy = 2 + (j >> 2); const int cc = j & 3; ix = cc < 2 ? cc : TILE_W + cc; }
                 const int x = ox - 2 + ix, y = oy - 2 + iy;
                 const int id = s_ids[iy * IDS_W + ix];
                 float gray = 0.f;
-                if (id >= 0 && x >= S.wx0 && x < S.wx0 + S.ww && y >= S.wy0 && y < S.wy0 + S.wh) {
+                if (id >= 0 && x >= S.wx0 && x < wx1 && y >= S.wy0 && y < wy1) {
                     Shade sh;
                     shade_setup<true>(S, s_mvp, id, x, y, ndc_xs, ndc_xo, ndc_ys, ndc_yo, sh);
                     float rgb[3];
                     shade_color<false, false, MIP>(S, sh, id, sh.u, sh.v, (1.f - sh.u) - sh.v, ndc_xs, ndc_ys, rgb, nullptr, nullptr);
                     gray = ((rgb[0] + rgb[1]) + rgb[2]) * (1.f / 3.f);
                 }
-                s_gray[i] = gray;
+                s_gray[iy * GRAY_W + ix] = gray;
+            }
+#pragma unroll
+            for (int rep = 0; rep < TILE_H / 8; rep++) {  // A
+                const int ly = ly0 + 8 * rep;
+                const int x = ox + lx, y = oy + ly;
+                st_gu[rep] = st_gv[rep] = st_G0[rep] = st_G1[rep] = 0.f;
+                float gray = 0.f;
+                if (x < gx1 && y < gy1) {
+                    const int id = s_ids[(ly + 2) * IDS_W + (lx + 2)];
+                    const float maa = (nq > 0) ? s_maa[(ly + 1) * MAA_W + (lx + 1)] : ((id >= 0) ? 1.f : 0.f);
+                    const size_t gpix = (size_t)y * S.W + x;
+                    float seg[3];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) seg[c] = S.gt_seg[gpix * S.seg_pix_stride + c * S.seg_ch_stride];
+                    float gt_rgb[3] = {0.f, 0.f, 0.f}, gt_d = 0.f;
+                    if (cfg.use_rgb) { gt_rgb[0] = S.gt_rgb[gpix * 3]; gt_rgb[1] = S.gt_rgb[gpix * 3 + 1]; gt_rgb[2] = S.gt_rgb[gpix * 3 + 2]; }
+                    if (cfg.use_depth) gt_d = S.gt_depth[gpix];
+                    float depth = -s_m2[3];
+                    if (id >= 0) {
+                        gtouch = true;
+                        Shade sh;
+                        shade_setup<true>(S, s_mvp, id, x, y, ndc_xs, ndc_xo, ndc_ys, ndc_yo, sh);
+                        const float b0 = sh.u, b1 = sh.v, b2 = (1.f - sh.u) - sh.v;
+                        const float p0[3] = {sh.v0.x, sh.v0.y, sh.v0.z}, p1[3] = {sh.v1.x, sh.v1.y, sh.v1.z}, p2[3] = {sh.v2.x, sh.v2.y, sh.v2.z};
+                        float g[3];
+#pragma unroll
+                        for (int k = 0; k < 3; k++) g[k] = b0 * p0[k] + b1 * p1[k] + b2 * p2[k];
+                        depth = -(s_m2[0] * g[0] + s_m2[1] * g[1] + s_m2[2] * g[2] + s_m2[3]);
+                        float gu = 0.f, gv = 0.f;
+                        if (cfg.use_depth) {
+                            const float diff = (depth - gt_d) * seg[0];
+                            acc[17] += fabsf(diff);
+                            const float gd = ksgn(k_depth, diff) * seg[0];
+                            if (gd != 0.f) {
+                                acc[12] -= gd * g[0]; acc[13] -= gd * g[1]; acc[14] -= gd * g[2]; acc[15] -= gd;
+#pragma unroll
+                                for (int k = 0; k < 3; k++) {  // through g = sum b_i p_i
+                                    const float dg = -gd * s_m2[k];
+                                    gu += dg * (p0[k] - p2[k]);
+                                    gv += dg * (p1[k] - p2[k]);
+                                }
+                            }
+                        }
+                        float rgb[3], g0[3], g1[3];
+                        shade_color<false, true, MIP>(S, sh, id, b0, b1, b2, ndc_xs, ndc_ys, rgb, g0, g1);
+                        gray = ((rgb[0] + rgb[1]) + rgb[2]) * (1.f / 3.f);
+                        if (cfg.use_rgb) {
+#pragma unroll
+                            for (int c = 0; c < 3; c++) {
+                                const float diff = (rgb[c] - gt_rgb[c]) * seg[c];
+                                acc[16] += fabsf(diff);
+                                const float dy = ksgn(k_rgb, diff) * seg[c];
+                                gu += dy * g0[c];
+                                gv += dy * g1[c];
+                            }
+                        }
+                        st_gu[rep] = gu; st_gv[rep] = gv;
+                        st_G0[rep] = (g0[0] + g0[1]) + g0[2]; st_G1[rep] = (g1[0] + g1[1]) + g1[2];
+                    } else {
+                        // background: rgb = 0, depth = -t_z (interpolate yields 0 where tri_id == 0)
+                        if (cfg.use_depth) {
+                            const float diff = (depth - gt_d) * seg[0];
+                            acc[17] += fabsf(diff);
+                            acc[15] -= ksgn(k_depth, diff) * seg[0];
+                            gtouch = true;
+                        }
+                        if (cfg.use_rgb) {
+#pragma unroll
+                            for (int c = 0; c < 3; c++) acc[16] += fabsf((0.f - gt_rgb[c]) * seg[c]);
+                        }
+                    }
+                    if (cfg.use_mask) {
+#pragma unroll
+                        for (int c = 0; c < 3; c++) acc[18] += fabsf(maa - seg[c]);
+                    }
+                }
+                s_gray[(ly + 2) * GRAY_W + (lx + 2)] = gray;
             }
             __syncthreads();
             // E2. Sobel magnitude of the render, the edge loss against the precomputed target edges and
@@ -752,7 +847,7 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
                 const int ix = i % DG_W, iy = i / DG_W;
                 const int x = ox - 1 + ix, y = oy - 1 + iy;
                 float dgx = 0.f, dgy = 0.f;
-                if (x >= S.wx0 && x < S.wx0 + S.ww && y >= S.wy0 && y < S.wy0 + S.wh) {
+                if (x >= S.wx0 && x < wx1 && y >= S.wy0 && y < wy1) {
                     const size_t gp = (size_t)y * S.W + x;
                     const float sg = S.gt_seg[gp * S.seg_pix_stride];
                     if (sg != 0.f) {
@@ -773,8 +868,27 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
                 s_dgx[i] = dgx; s_dgy[i] = dgy;
             }
             __syncthreads();
-        }
-
+#pragma unroll
+            for (int rep = 0; rep < TILE_H / 8; rep++) {  // B
+                const int ly = ly0 + 8 * rep;
+                const int x = ox + lx, y = oy + ly;
+                if (!(x < gx1 && y < gy1)) continue;
+                const int id = s_ids[(ly + 2) * IDS_W + (lx + 2)];
+                if (id < 0) continue;
+                // transpose of the Sobel stencils: grey(q) enters G(p) for the 8 neighbours p of q
+                const float* dx = s_dgx + (ly + 1) * DG_W + (lx + 1);
+                const float* dy = s_dgy + (ly + 1) * DG_W + (lx + 1);
+                const float sx = ((dx[-DG_W - 1] - dx[-DG_W + 1]) + 2.f * (dx[-1] - dx[1])) + (dx[DG_W - 1] - dx[DG_W + 1]);
+                const float sy = ((dy[-DG_W - 1] - dy[DG_W - 1]) + 2.f * (dy[-DG_W] - dy[DG_W])) + (dy[-DG_W + 1] - dy[DG_W + 1]);
+                const float dgray3 = (sx + sy) * (1.f / 3.f);  // dL/d rgb_c of the edge loss: dL/d grey / 3
+                const float gu = st_gu[rep] + dgray3 * st_G0[rep], gv = st_gv[rep] + dgray3 * st_G1[rep];
+                if (gu != 0.f || gv != 0.f) {
+                    Shade sh;
+                    shade_setup<true>(S, s_mvp, id, x, y, ndc_xs, ndc_xo, ndc_ys, ndc_yo, sh);
+                    raster_grad_accum(S, sh, gu, gv, acc);
+                }
+            }
+        } else {
         // 5. shading, losses and their backward, 4 pixels per thread
         for (int rep = 0; rep < TILE_H / 8; rep++) {
             const int ly = ly0 + 8 * rep;
@@ -894,6 +1008,8 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
             }
         }
 
+        }  // !EDGE
+
         // 6. silhouette gradients, one pair per thread. A pair is owned by the tile holding its first
         //    pixel, or its second pixel when the first lies outside the loss ROI.
         if ((MODE == MODE_LOSS && cfg.use_mask) || (MODE == MODE_EXT && ext.d_mask)) {
@@ -968,9 +1084,9 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
     }
 }
 
-static int pixel_grid(int max_tiles, int num_sms, bool binned) {
+static int pixel_grid(int max_tiles, int num_sms, bool binned, bool edge) {
     static const int per_sm = [] { const char* e = getenv("DDOPE_PIXEL_CTAS_PER_SM"); int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 0; }();
-    int g = num_sms * (per_sm ? per_sm : (binned ? PIXEL_MIN_BLOCKS_BINNED : PIXEL_MIN_BLOCKS));
+    int g = num_sms * (per_sm ? per_sm : (binned ? PIXEL_MIN_BLOCKS_BINNED : (edge ? PIXEL_MIN_BLOCKS_EDGE : PIXEL_MIN_BLOCKS)));
     if (g > max_tiles) g = max_tiles;
     return g < 1 ? 1 : g;
 }
@@ -993,7 +1109,7 @@ static void launch_pixel_inst(const SceneDev& S, const HypState* hyp, const int*
 template <int MODE, bool EDGE, bool BINNED>
 static void launch_pixel(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles, LossCfgDev cfg,
                          const unsigned long long* zbuf, float* partials, RenderOut out, ExtGrad ext, BinArgs bins, int num_sms, cudaStream_t st) {
-    const int grid = pixel_grid(max_tiles, num_sms, BINNED);
+    const int grid = pixel_grid(max_tiles, num_sms, BINNED, EDGE);
     if (S.tex4 && S.tex_filter == 1)
         launch_pixel_inst<MODE, EDGE, true, BINNED>(S, hyp, total_tiles, B, grid, cfg, zbuf, partials, out, ext, bins, st);
     else

@@ -63,6 +63,9 @@ def lib():
     L.ddope_last_error.restype = ctypes.c_char_p
     L.ddope_last_launch_count.restype = ctypes.c_int64
     L.ddope_last_launch_count.argtypes = [vp]
+    L.ddope_graph_launch_count.restype = ctypes.c_int64
+    L.ddope_graph_launch_count.argtypes = [vp]
+    L.ddope_scene_set_graph.argtypes = [vp, ci]
     L.ddope_xfm_fwd.argtypes = [vp, ci, ci, vp, ci, ci, vp, vp]
     L.ddope_xfm_bwd.argtypes = [vp, ci, ci, vp, ci, vp, vp]
     L.ddope_xfm_bwd_mtx.argtypes = [vp, ci, ci, vp, ci, ci, vp, vp]
@@ -97,7 +100,7 @@ def lib():
         "ddope_scene_destroy", "ddope_scene_set_camera", "ddope_scene_set_target", "ddope_scene_set_window",
         "ddope_render", "ddope_render_mtx", "ddope_render_bwd", "ddope_loss_grad", "ddope_optimize",
         "ddope_profile_begin", "ddope_profile_end", "ddope_scene_set_texture_filter", "ddope_scene_set_optimizer",
-        "ddope_scene_set_culling", "ddope_image_from_raw", "ddope_scene_set_raster_mode", "ddope_scene_set_bin_capacity",
+        "ddope_scene_set_culling", "ddope_image_from_raw", "ddope_scene_set_raster_mode", "ddope_scene_set_bin_capacity", "ddope_scene_set_graph",
     ):
         getattr(L, name).restype = ci
     if L.ddope_abi_version() != 2:
@@ -367,6 +370,14 @@ class NativeScene:
         if n < 0:
             _check(-1)
         return buf[:n]
+
+    def set_graph(self, on=True):
+        """Small-batch CUDA-graph replay of ddope_optimize (default on)."""
+        _check(lib().ddope_scene_set_graph(self._h, 1 if on else 0))
+
+    def graph_launch_count(self):
+        """ddope_optimize calls served by a CUDA-graph launch so far (small batches)."""
+        return int(lib().ddope_graph_launch_count(self._h))
 
     def last_launch_count(self):
         return int(lib().ddope_last_launch_count(self._h))

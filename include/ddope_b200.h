@@ -232,6 +232,12 @@ int ddope_optimize(ddope_scene* s, float* quat_dev, float* trans_dev, const floa
  * issue-bound raster kernel of one part overlaps the latency-bound pixel kernel of another -- and join them back
  * into `stream` before returning; the caller sees ordinary stream semantics and bit-identical results. */
 
+/* Small batches (fewer than 8 hypotheses, one part): ddope_optimize captures its 1 + 3 n_iters launches into a CUDA graph on an
+ * internal stream and launches that instead (the host cannot enqueue ~5 us kernels as fast as the GPU retires them); the executable
+ * graph is kept and updated in place by later calls. DDOPE_GRAPH=0 disables it. Number of calls served that way so far: */
+int64_t ddope_graph_launch_count(const ddope_scene* s);
+int ddope_scene_set_graph(ddope_scene* s, int on);
+
 /* Number of kernels the last ddope_optimize / ddope_loss_grad / ddope_render call on this
  * scene launched (for bench.py's gpu_launches). */
 int64_t ddope_last_launch_count(const ddope_scene* s);

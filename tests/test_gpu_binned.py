@@ -107,3 +107,46 @@ def test_binned_equals_zbuffer_on_the_stress_workload():
     ref, outs = _both_modes(sc, run)
     _assert_same(ref, outs)
     assert sc.bin_overflows() == 0
+
+
+def test_small_batch_graph_replay_is_bit_identical():
+    """Fewer than 8 hypotheses: ddope_optimize replays its launches as one CUDA graph (updated in place from call to call, rebuilt when
+    the iteration count changes); same tables as the direct launches, in both raster modes, from the legacy default stream and from
+    a side stream."""
+    n = _nat()
+    arr = su.example_mesh_arrays()
+    q, t = su.example_pose()
+    gt = su.example_targets(0.5)
+    H, W = gt["rgb"].shape[:2]
+    sc = n.NativeScene(arr["pos"], arr["tri"], arr["uv"], arr["tex"])
+    sc.set_camera(su.projection(), H, W)
+    g = {k: torch.from_numpy(v).cuda() for k, v in gt.items()}
+    sc.set_target(g["rgb"], g["depth"], g["segmentation"])
+    cfg = _cfg(n, ALL)
+    for mode in ("zbuffer", "binned"):
+        sc.set_raster_mode(mode)
+        for B, iters in ((1, 12), (3, 12), (3, 7), (1, 12)):
+            qs, ts = su.perturbed_poses(q, t, B, seed=B, rot_deg=2.0, trans=0.02)
+            lr = torch.from_numpy(su.lr_multipliers(B, 0.01, 1.0)).cuda()
+            sched = [2.0 * 0.9 ** i for i in range(iters)]
+
+            def run():
+                qd, td = torch.from_numpy(qs).cuda().contiguous(), torch.from_numpy(ts).cuda().contiguous()
+                ph, lh = sc.optimize(qd, td, lr, sched, cfg)
+                torch.cuda.synchronize()
+                return ph, lh, qd, td
+
+            sc.set_graph(False)
+            ref = run()
+            sc.set_graph(True)
+            before = sc.graph_launch_count()
+            got = run()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                got2 = run()
+            torch.cuda.current_stream().wait_stream(side)
+            assert sc.graph_launch_count() == before + 2, "both calls were served by a graph launch"
+            for a, b, c in zip(ref, got, got2):
+                assert torch.equal(a, b) and torch.equal(a, c)
+    sc.set_raster_mode("zbuffer")
