@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -88,8 +89,14 @@ struct ddope_scene {
     size_t bin_tiles_cap = 0;
     // small batches (one part): the 1 + 3n launches of a ddope_optimize call are captured into a CUDA graph on an internal stream
     // (programmatic-dependent-launch edges kept) and replayed as one launch; the executable graph is updated in place from call to call
+    // multi-object calls (this scene as the leader): device table of the scenes' SceneDev + per-hypothesis (scene, B_global)
+    SceneDev* multi_scenes = nullptr;
+    int multi_scenes_cap = 0;
+    int2* multi_meta = nullptr;
+    int multi_meta_cap = 0;
+    bool multi_active = false;
     cudaGraphExec_t graph_exec = nullptr;
-    int use_graph = 1;            // DDOPE_GRAPH=0 / ddope_scene_set_graph(s, 0): launch directly
+    int use_graph = 0;            // DDOPE_GRAPH=1 / ddope_scene_set_graph(s, 1): replay small batches as a CUDA graph (measured: no gain, off)
     int64_t graph_calls = 0;      // calls served by a graph launch (tests / bench)
 };
 
@@ -398,6 +405,7 @@ extern "C" int ddope_scene_destroy(ddope_scene* s) {
     cudaFree(s->arrive);
     cudaFree(s->bin_count); cudaFree(s->bin_ids); cudaFree(s->bin_overflow);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    cudaFree(s->multi_scenes); cudaFree(s->multi_meta);
     for (int p = 0; p < ddope_scene::MAX_PARTS; p++) {
         if (s->part_stream[p]) cudaStreamDestroy(s->part_stream[p]);
         if (s->part_done[p]) cudaEventDestroy(s->part_done[p]);
@@ -617,12 +625,22 @@ static int render_common(ddope_scene* s, const float* quat, const float* trans, 
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, false, st)) return r;
     LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
-    launch_pose(s->dev, quat, trans, mtx_in, nullptr, B, B, cfg, 2, s->hyp, s->total_tiles, st);
-    launch_raster(s->dev, s->hyp, B, s->zbuf, st);
     RenderOut out = {rgb, depth, mask, rast};
+    // the background of every output image is streamed out on an internal stream while pose + raster run on the caller's; the
+    // pixel pass (tiles that can contain the object only) starts when both are done
+    if (!s->fork_event) CK(cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming));
+    if (!s->part_stream[1]) CK(cudaStreamCreateWithFlags(&s->part_stream[1], cudaStreamNonBlocking));
+    if (!s->part_done[1]) CK(cudaEventCreateWithFlags(&s->part_done[1], cudaEventDisableTiming));
+    CK(cudaEventRecord(s->fork_event, st));
+    CK(cudaStreamWaitEvent(s->part_stream[1], s->fork_event, 0));
+    launch_render_fill(out, trans, mtx_in, B, s->dev.wh, s->dev.ww, s->num_sms, s->part_stream[1]);
+    CK(cudaEventRecord(s->part_done[1], s->part_stream[1]));
+    launch_pose(s->dev, quat, trans, mtx_in, nullptr, B, B, cfg, 2, s->hyp, s->total_tiles, st);
+    launch_raster(s->dev, s->hyp, B, s->zbuf, MultiArgs{nullptr, nullptr, 0, 0}, st);
+    CK(cudaStreamWaitEvent(st, s->part_done[1], 0));
     launch_pixel_render(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), s->zbuf, out, s->num_sms, st);
     launch_clear(s->dev, s->hyp, B, s->zbuf, st);  // restore the z-buffer invariant
-    s->launches = 4;
+    s->launches = 5;
     if (mtx) {
         launch_copy_mtx(s->hyp, B, mtx, st);
         s->launches++;
@@ -651,7 +669,7 @@ extern "C" int ddope_render_bwd(ddope_scene* s, const float* mtx_in, int B, cons
     if (int r = ensure_buffers(s, B, true, st)) return r;
     LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
     launch_pose(s->dev, nullptr, nullptr, mtx_in, nullptr, B, B, cfg, 0, s->hyp, s->total_tiles, st);
-    launch_raster(s->dev, s->hyp, B, s->zbuf, st);
+    launch_raster(s->dev, s->hyp, B, s->zbuf, MultiArgs{nullptr, nullptr, 0, 0}, st);
     ExtGrad ext = {d_rgb, d_depth, d_mask};
     launch_pixel_ext(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), s->zbuf, ext, s->partials, s->num_sms, st);
     launch_step(s->dev, s->hyp, s->partials, B, cfg, d_mtx, st);
@@ -706,6 +724,7 @@ struct Part {
     float* partials;         // this part's tile rows start at index 0 here
     unsigned long long* zbuf;
     BinArgs bins;            // this part's bins (count == nullptr: global z-buffer path)
+    MultiArgs multi;         // multi-object call: scene table + this part's slice of the per-hypothesis table
 };
 
 static size_t tiles_per_hyp(const ddope_scene* s) {
@@ -734,7 +753,8 @@ static int fork_parts(ddope_scene* s, int B, cudaStream_t st, Part* parts, int* 
         P.partials = s->partials + (size_t)P.b0 * tiles_per_hyp(s) * NACC;
         P.zbuf = s->zbuf + (size_t)P.b0 * s->dev.zh * s->dev.zw;
         P.bins = {nullptr, nullptr, 0, nullptr};
-        if (s->raster_mode == 1) {
+        P.multi = {nullptr, nullptr, 0, 0};
+        if (s->raster_mode == 1 && !s->multi_active) {
             const size_t t0 = (size_t)P.b0 * tiles_per_hyp(s);
             P.bins = {s->bin_count + t0, s->bin_ids + t0 * s->bin_cap, s->bin_cap, s->bin_overflow};
         }
@@ -775,7 +795,7 @@ static void enqueue_prologue(ddope_scene* s, const Part& P, float* quat, float* 
     HypState* h = s->hyp + P.b0;
     launch_iter(s->dev, h, h, P.partials, P.B, B_global, P.B, cfg, opt, quat + 4 * (size_t)P.b0, trans + 3 * (size_t)P.b0,
                 lr_mult ? lr_mult + P.b0 : nullptr, 0.f, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr, P.zbuf, P.total_tiles,
-                P.arrive, P.st);
+                P.arrive, P.multi, P.st);
     s->launches += 1;
 }
 
@@ -791,11 +811,11 @@ static void enqueue_iteration(ddope_scene* s, const Part& P, float* quat, float*
     {
         ProfMark m(s, P.st, K_RASTER);
         if (binned) launch_bin(s->dev, cur, P.B, P.bins.count, const_cast<int*>(P.bins.ids), P.bins.cap, P.st);
-        else launch_raster(s->dev, cur, P.B, P.zbuf, P.st);
+        else launch_raster(s->dev, cur, P.B, P.zbuf, P.multi, P.st);
     }
     {
         ProfMark m(s, P.st, K_PIXEL);
-        launch_pixel_loss(s->dev, cur, P.total_tiles, P.B, max_tiles_of(s, P.B), cfg, P.zbuf, P.partials, P.bins, s->num_sms, P.st);
+        launch_pixel_loss(s->dev, cur, P.total_tiles, P.B, max_tiles_of(s, P.B), cfg, P.zbuf, P.partials, P.bins, P.multi, s->num_sms, P.st);
     }
     {
         ProfMark m(s, P.st, K_ITER);
@@ -805,7 +825,7 @@ static void enqueue_iteration(ddope_scene* s, const Part& P, float* quat, float*
                     lr_mult ? lr_mult + P.b0 : nullptr, lr_t, it, 1, do_update, more,
                     loss_table ? loss_table + NLOSS * (size_t)P.b0 : nullptr, grad ? grad + 7 * (size_t)P.b0 : nullptr,
                     pose_hist ? pose_hist + 7 * (size_t)P.b0 : nullptr, loss_hist ? loss_hist + NLOSS * (size_t)P.b0 : nullptr,
-                    binned ? nullptr : P.zbuf, P.total_tiles, P.arrive, P.st);
+                    binned ? nullptr : P.zbuf, P.total_tiles, P.arrive, P.multi, P.st);
     }
     s->launches += 3;
 }
@@ -935,6 +955,105 @@ extern "C" int64_t ddope_graph_launch_count(const ddope_scene* s) { return s ? s
 extern "C" int ddope_scene_set_graph(ddope_scene* s, int on) {
     if (!s) return fail("ddope_scene_set_graph: null scene");
     s->use_graph = on != 0;
+    return 0;
+}
+
+// All objects of a frame in ONE sequence of launches (reference: the sequential per-object loop of examples/run_bop_scene.py:48-93).
+// Hypothesis b of the call belongs to scenes[hyp_scene[b]] and its loss mean divides by hyp_bglobal[b]; quat / trans / lr_mult /
+// histories are the objects' arrays concatenated in call order. Every kernel picks the hypothesis's mesh, texture and targets from a
+// device table of the scenes. Results are bit-identical to one ddope_optimize call per object. The work buffers of scenes[0] serve.
+extern "C" int ddope_optimize_multi(ddope_scene* const* scenes, int n_scenes, const int32_t* hyp_scene, const int32_t* hyp_bglobal, float* quat,
+                                    float* trans, const float* lr_mult, int B, const float* lr_sched, int n_iters, const ddope_loss_cfg* cfg,
+                                    float* pose_hist, float* loss_hist, void* stream) {
+    if (!scenes || n_scenes <= 0 || !hyp_scene || !hyp_bglobal || !quat || !trans || !lr_sched) return fail("ddope_optimize_multi: null pointer");
+    if (B <= 0 || B > 65535) return fail("ddope_optimize_multi: need 1 <= B <= 65535");
+    if (n_iters <= 0) return fail("ddope_optimize_multi: n_iters must be positive");
+    ddope_scene* s = scenes[0];
+    if (!s) return fail("ddope_optimize_multi: null scene");
+    int max_T = 0, mip = -1;
+    for (int k = 0; k < n_scenes; k++) {
+        ddope_scene* sk = scenes[k];
+        if (!sk) return fail("ddope_optimize_multi: null scene");
+        for (int j = 0; j < k; j++)
+            if (scenes[j] == sk) return fail("ddope_optimize_multi: a scene may appear only once (objects sharing a mesh need their own scene: targets differ)");
+        if (int r = check_loss_inputs(sk, cfg, "ddope_optimize_multi")) return r;
+        const SceneDev &a = s->dev, &b = sk->dev;
+        if (a.H != b.H || a.W != b.W || a.wy0 != b.wy0 || a.wx0 != b.wx0 || a.wh != b.wh || a.ww != b.ww || memcmp(a.proj, b.proj, sizeof(a.proj)) != 0)
+            return fail("ddope_optimize_multi: every scene must have the same camera, frame size and loss window");
+        if (b.tex4) {
+            if (mip >= 0 && mip != b.tex_filter) return fail("ddope_optimize_multi: textured scenes must use the same texture filter");
+            mip = b.tex_filter;
+        }
+        if (sk->optim.kind != s->optim.kind) return fail("ddope_optimize_multi: scenes must use the same optimizer");
+        max_T = b.T > max_T ? b.T : max_T;
+    }
+    for (int b = 0; b < B; b++) {
+        if (hyp_scene[b] < 0 || hyp_scene[b] >= n_scenes) return fail("ddope_optimize_multi: hyp_scene out of range");
+        if (hyp_bglobal[b] < 1) return fail("ddope_optimize_multi: hyp_bglobal must be positive");
+    }
+    std::vector<std::unique_ptr<SceneBusy>> guards;
+    for (int k = 0; k < n_scenes; k++) {
+        guards.emplace_back(new SceneBusy(scenes[k]));
+        if (!guards.back()->ok) return fail("ddope_optimize_multi: a scene is in use by another call");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    s->multi_active = true;
+    struct Reset { ddope_scene* s; ~Reset() { s->multi_active = false; } } reset{s};
+    if (int r = ensure_buffers(s, B, true, st)) return r;
+    for (int k = 0; k < n_scenes; k++)
+        if (int r = prepare_edge(scenes[k], cfg, st)) return r;
+    if (n_scenes > s->multi_scenes_cap) {
+        if (s->multi_scenes) CK(cudaFree(s->multi_scenes));
+        s->multi_scenes = nullptr; s->multi_scenes_cap = 0;
+        CK(cudaMalloc(&s->multi_scenes, sizeof(SceneDev) * n_scenes));
+        s->multi_scenes_cap = n_scenes;
+    }
+    if (B > s->multi_meta_cap) {
+        if (s->multi_meta) CK(cudaFree(s->multi_meta));
+        s->multi_meta = nullptr; s->multi_meta_cap = 0;
+        CK(cudaMalloc(&s->multi_meta, sizeof(int2) * B));
+        s->multi_meta_cap = B;
+    }
+    {   // stream-ordered uploads from pageable host memory (staged by the runtime before the call returns)
+        std::vector<SceneDev> tab(n_scenes);
+        for (int k = 0; k < n_scenes; k++) tab[k] = scenes[k]->dev;
+        std::vector<int2> meta(B);
+        for (int b = 0; b < B; b++) meta[b] = make_int2(hyp_scene[b], hyp_bglobal[b]);
+        CK(cudaMemcpyAsync(s->multi_scenes, tab.data(), sizeof(SceneDev) * n_scenes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s->multi_meta, meta.data(), sizeof(int2) * B, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));  // the host vectors go out of scope here
+    }
+    if (s->optim.kind == DDOPE_OPT_ADAM) {
+        bool fresh = s->optim.step0 == 0;
+        if (B > s->adam_cap) {
+            if (s->optim.step0 > 0 && s->adam_state) return fail("ddope_optimize_multi: Adam continuation (step0 > 0) with a larger batch than the stored moments");
+            if (s->adam_state) CK(cudaFree(s->adam_state));
+            CK(cudaMalloc(&s->adam_state, sizeof(float) * 14 * (size_t)B));
+            s->adam_cap = B;
+            fresh = true;
+        }
+        if (fresh) CK(cudaMemsetAsync(s->adam_state, 0, sizeof(float) * 14 * (size_t)B, st));
+    }
+    LossCfgDev c = to_dev(cfg);
+    OptimDev opt = optim_dev(s, 0.f, 0);
+    s->launches = 0;
+    Part parts[ddope_scene::MAX_PARTS];
+    int n_parts = 1;
+    if (int r = fork_parts(s, B, st, parts, &n_parts)) return r;
+    for (int p = 0; p < n_parts; p++) parts[p].multi = {s->multi_scenes, s->multi_meta + parts[p].b0, max_T, mip > 0 ? 1 : 0};
+    s->hyp_cur = 0;
+    for (int p = 0; p < n_parts; p++) enqueue_prologue(s, parts[p], quat, trans, lr_mult, B, c, opt);
+    cudaError_t lerr = cudaSuccess;
+    for (int it = 0; it < n_iters; it++) {
+        opt = optim_dev(s, lr_sched[it], it);
+        for (int p = 0; p < n_parts; p++)
+            enqueue_iteration(s, parts[p], quat, trans, lr_mult, B, B, c, opt, lr_sched[it], it, 1, it + 1 < n_iters, nullptr, nullptr, pose_hist, loss_hist);
+        s->hyp_cur ^= 1;
+        lerr = take_launch_error();
+        if (lerr != cudaSuccess) break;
+    }
+    if (int r = join_parts(s, st, parts, n_parts)) return r;
+    if (lerr != cudaSuccess) return fail(std::string("ddope_optimize_multi: kernel launch failed: ") + cudaGetErrorString(lerr));
     return 0;
 }
 

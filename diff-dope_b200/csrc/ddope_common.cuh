@@ -67,9 +67,19 @@ struct __align__(16) HypState {
     int face;  // sign of the snapped window-space area of a front-facing triangle (0: rasterise both orientations)
     int gx0, gy0, gx1, gy1;        // tile grid: 32x32 tiles from (gx0,gy0), pixels up to (gx1,gy1) exclusive. Loss / backward passes: the ROI.
                                    // Image output (ddope_render*): the whole window, while the ROI stays the object's bounding box.
-    int pad[3];
+    int obj;                       // index into the scene table of a multi-object call (0 otherwise)
+    int pad[2];
 };
 static_assert(sizeof(HypState) == 224, "HypState layout (scripts/dev_maskgrad_dump.py reads words 40..46)");
+
+// Multi-object calls (ddope_optimize_multi): one launch covers the hypotheses of several objects. scenes = device table of the
+// objects' SceneDev, meta[b] = (scene index, divisor of the hypothesis mean) of hypothesis b. scenes == nullptr: single object.
+struct MultiArgs {
+    const SceneDev* scenes;
+    const int2* meta;
+    int max_T;  // largest triangle count among the scenes (grid of the raster launch)
+    int mip;    // the textured scenes of the call use the mipmapped filter (all of them, or none)
+};
 
 struct LossCfgDev {
     int use_rgb, use_depth, use_mask;

@@ -50,13 +50,13 @@ void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, 
 void launch_iter(const SceneDev& S, const HypState* hyp_old, HypState* hyp_new, const float* partials, int B, int B_global,
                  int B_hist, LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, float lr_t, int it,
                  int do_step, int do_update, int do_pose, float* loss_table, float* grad_out, float* pose_hist,
-                 float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, cudaStream_t st);
+                 float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, MultiArgs multi, cudaStream_t st);
 void launch_seg_bbox(const float* seg, int H, int W, int seg_c, int* bbox4, cudaStream_t st);
 void launch_copy_mtx(const HypState* hyp, int B, float* mtx, cudaStream_t st);
 
 // raster.cu
 void launch_clear(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, cudaStream_t st);
-void launch_raster(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, cudaStream_t st);
+void launch_raster(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, MultiArgs multi, cudaStream_t st);
 void launch_bin(const SceneDev& S, const HypState* hyp, int B, int* bin_count, int* bin_ids, int bin_cap, cudaStream_t st);
 
 // pixel.cu
@@ -81,10 +81,11 @@ struct BinArgs {
 void launch_pixel_ext(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                       const unsigned long long* zbuf, ExtGrad ext, float* partials, int num_sms, cudaStream_t st);
 void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
-                       LossCfgDev cfg, const unsigned long long* zbuf, float* partials, BinArgs bins, int num_sms, cudaStream_t st);
+                       LossCfgDev cfg, const unsigned long long* zbuf, float* partials, BinArgs bins, MultiArgs multi, int num_sms, cudaStream_t st);
 void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                          const unsigned long long* zbuf, RenderOut out, int num_sms, cudaStream_t st);
 
+void launch_render_fill(RenderOut out, const float* trans, const float* mtx, int B, int wh, int ww, int num_sms, cudaStream_t st);
 void launch_gt_edge(const SceneDev& S, float* out, cudaStream_t st);
 void launch_tex_pack(const float* tex3, size_t n, float4* out, cudaStream_t st);
 void launch_tex_mip(const float4* src, int sw, int sh, float4* dst, int dw, int dh, cudaStream_t st);

@@ -415,12 +415,16 @@ constexpr int DI_NONE = 3;            // no pair here / analysis found no usable
 constexpr int GRAY_W = TILE_W + 4;  // grey image of the render: tile + 2 px halo (edge loss)
 constexpr int DG_W = TILE_W + 2;    // dL/d(Gx,Gy): tile + 1 px halo
 
-template <int MODE, bool EDGE, bool MIP, bool BINNED>
-__global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED : (EDGE ? PIXEL_MIN_BLOCKS_EDGE : PIXEL_MIN_BLOCKS)) pixel_kernel(SceneDev S, const HypState* __restrict__ hyp,
+template <int MODE, bool EDGE, bool MIP, bool BINNED, bool MULTI>
+__global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED : (EDGE ? PIXEL_MIN_BLOCKS_EDGE : PIXEL_MIN_BLOCKS)) pixel_kernel(SceneDev Sp, const HypState* __restrict__ hyp,
                                                              const int* __restrict__ total_tiles, int B,
                                                              LossCfgDev cfg,
                                                              const unsigned long long* __restrict__ zbuf,
-                                                             float* __restrict__ partials, RenderOut out, ExtGrad ext, BinArgs bins) {
+                                                             float* __restrict__ partials, RenderOut out, ExtGrad ext, BinArgs bins, MultiArgs multi) {
+    // multi-object call: the SceneDev of the object the current tile's hypothesis belongs to, copied from the scene table
+    __shared__ __align__(16) unsigned int s_scene[MULTI ? sizeof(SceneDev) / 4 : 4];
+    const SceneDev& S = MULTI ? *reinterpret_cast<const SceneDev*>(s_scene) : Sp;
+    int cur_obj = -1;
     __shared__ int s_ids[NPAIR];
     // the antialias blend factors (phases 3-6) share their storage with the tile's z-buffer of the binned path (phase 0)
     __shared__ __align__(16) union { float alpha[2][NPAIR]; unsigned long long z[NPAIR]; } s_u;
@@ -443,15 +447,13 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
     __shared__ float s_dgx[EDGE ? DG_W * DG_W : 1], s_dgy[EDGE ? DG_W * DG_W : 1];
 
     pdl_trigger();
-    // Loss / backward passes need the z-buffer (or the bins) of the preceding launch at once. Image output does not for its
-    // background tiles (90 % of a window): those are streamed out while the rasteriser is still running, and a CTA waits only
-    // before its first tile that touches the object's ROI. (hyp / total_tiles come from pose_kernel, complete before either started.)
-    bool waited = MODE != MODE_RENDER;
-    if (waited) pdl_wait();
+    bool waited = true;
+    pdl_wait();  // z-buffer (or bins) of the preceding launch
     const int total = *total_tiles;
     const int tid = threadIdx.x;
     // pixel centre -> NDC: fx = xs*px + xo (nvdiffrast's xs = 2/W, xo = 1/W - 1), hoisted out of the pixel loop
-    const float ndc_xs = S.ndc_xs, ndc_xo = S.ndc_xo, ndc_ys = S.ndc_ys, ndc_yo = S.ndc_yo;
+    // (a multi-object call shares camera, frame and window between its scenes, checked by the API: the leader's values serve all)
+    const float ndc_xs = Sp.ndc_xs, ndc_xo = Sp.ndc_xo, ndc_ys = Sp.ndc_ys, ndc_yo = Sp.ndc_yo;
     const int lx = tid % TILE_W, ly0 = tid / TILE_W;  // this thread's pixels: (lx, ly0 + 8k), k = 0..3
     unsigned int mbar_use[2] = {0u, 0u};  // completed phases of the two TMA barriers (uniform across the CTA)
     if (BINNED) {
@@ -485,6 +487,15 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
         __syncthreads();
         const int b = s_b;
         const HypState& h = hyp[b];
+        if (MULTI) {
+            const int obj = h.obj;  // CTA-uniform
+            if (obj != cur_obj) {
+                const unsigned int* src = reinterpret_cast<const unsigned int*>(multi.scenes + obj);
+                for (int i = tid; i < (int)(sizeof(SceneDev) / 4); i += TILE_THREADS) s_scene[i] = src[i];
+                cur_obj = obj;
+                __syncthreads();
+            }
+        }
         if (tid < 16) s_mvp[tid] = h.mvp[tid];
         if (tid < 4) s_m2[tid] = h.m[8 + tid];
         const int rx0 = h.rx0, ry0 = h.ry0, rx1 = h.rx1, ry1 = h.ry1;
@@ -500,29 +511,10 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
 
         if (MODE == MODE_RENDER) {
             // image output: a tile whose ids region does not touch the object's ROI is pure background (rgb 0, depth -t_z, mask 0,
-            // rast 0): streamed out with 16-byte stores, no z-buffer reads, no barriers
+            // rast 0): the whole output was pre-filled with that by render_fill_kernel (a streaming kernel on a second stream,
+            // concurrent with pose_kernel + raster_kernel); only tiles that can contain the object are visited here
             const bool bg = rx1 <= rx0 || ox - 2 >= vx1 || ox + TILE_W + 2 <= vx0 || oy - 2 >= vy1 || oy + TILE_H + 2 <= vy0;
-            if (bg) {  // CTA-uniform
-                const float bgd = -h.m[11];
-                const int fy = tid >> 3, fx4 = (tid & 7) * 4;
-                const int x = ox + fx4, y = oy + fy;
-                if (y < gy1 && x < gx1) {
-                    const size_t wp = ((size_t)b * S.wh + (y - S.wy0)) * S.ww + (x - S.wx0);
-                    if ((S.ww & 3) == 0 && x + 3 < gx1) {
-                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (out.rgb) { float4* p = reinterpret_cast<float4*>(out.rgb + wp * 3); p[0] = z4; p[1] = z4; p[2] = z4; }
-                        if (out.depth) *reinterpret_cast<float4*>(out.depth + wp) = make_float4(bgd, bgd, bgd, bgd);
-                        if (out.mask) *reinterpret_cast<float4*>(out.mask + wp) = z4;
-                        if (out.rast) { float4* p = reinterpret_cast<float4*>(out.rast) + wp; p[0] = z4; p[1] = z4; p[2] = z4; p[3] = z4; }
-                    } else {
-                        for (int k = 0; k < 4 && x + k < gx1; k++) {
-                            if (out.rgb) { out.rgb[(wp + k) * 3] = 0.f; out.rgb[(wp + k) * 3 + 1] = 0.f; out.rgb[(wp + k) * 3 + 2] = 0.f; }
-                            if (out.depth) out.depth[wp + k] = bgd;
-                            if (out.mask) out.mask[wp + k] = 0.f;
-                            if (out.rast) reinterpret_cast<float4*>(out.rast)[wp + k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
-                }
+            if (bg) {  // CTA-uniform: render_fill_kernel has written these pixels
                 __syncthreads();  // s_b / s_item are rewritten at the top of the loop
                 continue;
             }
@@ -1091,19 +1083,20 @@ static int pixel_grid(int max_tiles, int num_sms, bool binned, bool edge) {
     return g < 1 ? 1 : g;
 }
 
-template <int MODE, bool EDGE, bool MIP, bool BINNED>
+template <int MODE, bool EDGE, bool MIP, bool BINNED, bool MULTI = false>
 static void launch_pixel_inst(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int grid, LossCfgDev cfg,
-                              const unsigned long long* zbuf, float* partials, RenderOut out, ExtGrad ext, BinArgs bins, cudaStream_t st) {
+                              const unsigned long long* zbuf, float* partials, RenderOut out, ExtGrad ext, BinArgs bins, cudaStream_t st,
+                              MultiArgs multi = {nullptr, nullptr, 0, 0}) {
     size_t dyn = 0;
     if (BINNED) {
         dyn = sizeof(int) * BIN_CHUNK * REC_WORDS;
         static bool once = [] {  // static + dynamic shared memory of the binned variant exceeds the 48 KB default
-            note_launch(cudaFuncSetAttribute(pixel_kernel<MODE, EDGE, MIP, BINNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * BIN_CHUNK * REC_WORDS)));
+            note_launch(cudaFuncSetAttribute(pixel_kernel<MODE, EDGE, MIP, BINNED, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * BIN_CHUNK * REC_WORDS)));
             return true;
         }();
         (void)once;
     }
-    launch_kernel(pdl_enabled(), pixel_kernel<MODE, EDGE, MIP, BINNED>, dim3(grid), dim3(TILE_THREADS), dyn, st, S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext, bins);
+    launch_kernel(pdl_enabled(), pixel_kernel<MODE, EDGE, MIP, BINNED, MULTI>, dim3(grid), dim3(TILE_THREADS), dyn, st, S, hyp, total_tiles, B, cfg, zbuf, partials, out, ext, bins, multi);
 }
 
 template <int MODE, bool EDGE, bool BINNED>
@@ -1117,9 +1110,21 @@ static void launch_pixel(const SceneDev& S, const HypState* hyp, const int* tota
 }
 
 void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
-                       LossCfgDev cfg, const unsigned long long* zbuf, float* partials, BinArgs bins, int num_sms, cudaStream_t st) {
+                       LossCfgDev cfg, const unsigned long long* zbuf, float* partials, BinArgs bins, MultiArgs multi, int num_sms, cudaStream_t st) {
     RenderOut none = {nullptr, nullptr, nullptr, nullptr};
     ExtGrad noext = {nullptr, nullptr, nullptr};
+    if (multi.scenes) {  // multi-object launch (global z-buffer path): the filter is the same for every scene of the call
+        const bool mip = multi.mip != 0;
+        const int grid = pixel_grid(max_tiles, num_sms, false, cfg.use_edge);
+        if (cfg.use_edge) {
+            if (mip) launch_pixel_inst<MODE_LOSS, true, true, false, true>(S, hyp, total_tiles, B, grid, cfg, zbuf, partials, none, noext, bins, st, multi);
+            else launch_pixel_inst<MODE_LOSS, true, false, false, true>(S, hyp, total_tiles, B, grid, cfg, zbuf, partials, none, noext, bins, st, multi);
+        } else {
+            if (mip) launch_pixel_inst<MODE_LOSS, false, true, false, true>(S, hyp, total_tiles, B, grid, cfg, zbuf, partials, none, noext, bins, st, multi);
+            else launch_pixel_inst<MODE_LOSS, false, false, false, true>(S, hyp, total_tiles, B, grid, cfg, zbuf, partials, none, noext, bins, st, multi);
+        }
+        return;
+    }
     if (bins.count) {
         if (cfg.use_edge)
             launch_pixel<MODE_LOSS, true, true>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, noext, bins, num_sms, st);
@@ -1131,6 +1136,39 @@ void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_
         else
             launch_pixel<MODE_LOSS, false, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, noext, bins, num_sms, st);
     }
+}
+
+// Background of the image outputs for all hypotheses: rgb 0, depth -t_z (interpolate yields 0 where nothing is covered, so the
+// depth transform leaves -t_z: diffdope/diffdope.py:203-209,228), mask 0, rast 0. Pure streaming stores, 16 bytes per thread and step.
+__global__ void __launch_bounds__(256) render_fill_kernel(RenderOut out, const float* __restrict__ trans, const float* __restrict__ mtx, int B,
+                                                          unsigned int px_per_hyp) {
+    const size_t n = (size_t)B * px_per_hyp;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((px_per_hyp & 3u) == 0) {
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n / 4; q += stride) {
+            const size_t wp = q * 4;
+            const int b = (int)(wp / px_per_hyp);
+            const float bgd = mtx ? -mtx[16 * b + 11] : -trans[3 * b + 2];
+            if (out.rgb) { float4* p = reinterpret_cast<float4*>(out.rgb + wp * 3); p[0] = z4; p[1] = z4; p[2] = z4; }
+            if (out.depth) *reinterpret_cast<float4*>(out.depth + wp) = make_float4(bgd, bgd, bgd, bgd);
+            if (out.mask) *reinterpret_cast<float4*>(out.mask + wp) = z4;
+            if (out.rast) { float4* p = reinterpret_cast<float4*>(out.rast) + wp; p[0] = z4; p[1] = z4; p[2] = z4; p[3] = z4; }
+        }
+    } else {
+        for (size_t wp = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wp < n; wp += stride) {
+            const int b = (int)(wp / px_per_hyp);
+            const float bgd = mtx ? -mtx[16 * b + 11] : -trans[3 * b + 2];
+            if (out.rgb) { out.rgb[wp * 3] = 0.f; out.rgb[wp * 3 + 1] = 0.f; out.rgb[wp * 3 + 2] = 0.f; }
+            if (out.depth) out.depth[wp] = bgd;
+            if (out.mask) out.mask[wp] = 0.f;
+            if (out.rast) reinterpret_cast<float4*>(out.rast)[wp] = z4;
+        }
+    }
+}
+
+void launch_render_fill(RenderOut out, const float* trans, const float* mtx, int B, int wh, int ww, int num_sms, cudaStream_t st) {
+    render_fill_kernel<<<num_sms * 8, 256, 0, st>>>(out, trans, mtx, B, (unsigned int)(wh * ww));
 }
 
 void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,

@@ -67,7 +67,8 @@ __device__ void hyp_pose_part(const SceneDev& S, const float* qb, const float* t
         const bool outside = cx < S.bbmin[0] || cx > S.bbmax[0] || cy < S.bbmin[1] || cy > S.bbmax[1] || cz < S.bbmin[2] || cz > S.bbmax[2];
         if (!outside) h.face = 0;  // also taken when the position is NaN
     }
-    h.pad[0] = h.pad[1] = h.pad[2] = 0;
+    h.obj = 0;
+    h.pad[0] = h.pad[1] = 0;
 }
 
 // Screen position of corner c of the object-space AABB; false if it is behind the camera / absurdly far out
@@ -335,7 +336,8 @@ constexpr int CLEAR_CTAS = 3;  // CTAs per hypothesis that restore the z-buffer 
 //              k-1, k-1+CLEAR_CTAS, ... -- independent of the step, so it overlaps CTA 0's serial math.
 // Replaces step_kernel + pose_kernel + clear_kernel (3 launches) inside ddope_optimize. The z-buffer
 // invariant is "all EMPTY between iterations"; hyp_old / hyp_new alternate so nothing is read after it is rewritten.
-__global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const HypState* __restrict__ hyp_old,
+template <bool MULTI>
+__global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev Sp, const HypState* __restrict__ hyp_old,
                                                    HypState* __restrict__ hyp_new,
                                                    const float* __restrict__ partials, int B, int B_global, int B_hist,
                                                    LossCfgDev cfg, OptimDev opt, float* __restrict__ quat,
@@ -344,10 +346,14 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
                                                    int do_pose, float* __restrict__ loss_table, float* __restrict__ grad_out,
                                                    float* __restrict__ pose_hist, float* __restrict__ loss_hist,
                                                    unsigned long long* __restrict__ zbuf, int* __restrict__ total_tiles,
-                                                   unsigned int* __restrict__ arrive) {
+                                                   unsigned int* __restrict__ arrive, MultiArgs multi) {
     pdl_trigger();
     pdl_wait();  // partial sums of the preceding pixel_kernel
     const int b = blockIdx.y;
+    // multi-object call: this hypothesis's object and the divisor of its hypothesis mean come from the per-hypothesis table
+    const int obj = MULTI ? multi.meta[b].x : 0;
+    if (MULTI) B_global = multi.meta[b].y;
+    const SceneDev& S = MULTI ? multi.scenes[obj] : Sp;
     if (blockIdx.x > 0) {
         if (!do_step || zbuf == nullptr) return;  // nothing was rasterised yet / binned path: no global z-buffer to restore
         const HypState& h = hyp_old[b];
@@ -395,6 +401,7 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
     __shared__ __align__(16) HypState s_n;
     if (threadIdx.x == 0) {
         hyp_pose_part(S, s_theta, s_theta + 4, nullptr, s_n);
+        s_n.obj = obj;
         if (do_step) { s_n.k_rgb = s_h.k_rgb; s_n.k_depth = s_h.k_depth; s_n.k_mask = s_h.k_mask; s_n.k_edge = s_h.k_edge; }
         else hyp_scales(S, lr_mult ? lr_mult[b] : 1.f, B_global, cfg, s_n);
     }
@@ -460,10 +467,14 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev S, const Hy
 void launch_iter(const SceneDev& S, const HypState* hyp_old, HypState* hyp_new, const float* partials, int B, int B_global,
                  int B_hist, LossCfgDev cfg, OptimDev opt, float* quat, float* trans, const float* lr_mult, float lr_t, int it,
                  int do_step, int do_update, int do_pose, float* loss_table, float* grad_out, float* pose_hist,
-                 float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, cudaStream_t st) {
-    launch_kernel(pdl_enabled(), iter_kernel, dim3((do_step && zbuf) ? 1 + CLEAR_CTAS : 1, B), dim3(ITER_THREADS), 0, st, S, hyp_old, hyp_new, partials, B,
-                  B_global, B_hist, cfg, opt, quat, trans, lr_mult, lr_t, it, do_step, do_update, do_pose, loss_table, grad_out, pose_hist,
-                  loss_hist, zbuf, total_tiles, arrive);
+                 float* loss_hist, unsigned long long* zbuf, int* total_tiles, unsigned int* arrive, MultiArgs multi, cudaStream_t st) {
+    const dim3 grid((do_step && zbuf) ? 1 + CLEAR_CTAS : 1, B);
+    if (multi.scenes)
+        launch_kernel(pdl_enabled(), iter_kernel<true>, grid, dim3(ITER_THREADS), 0, st, S, hyp_old, hyp_new, partials, B, B_global, B_hist, cfg, opt, quat,
+                      trans, lr_mult, lr_t, it, do_step, do_update, do_pose, loss_table, grad_out, pose_hist, loss_hist, zbuf, total_tiles, arrive, multi);
+    else
+        launch_kernel(pdl_enabled(), iter_kernel<false>, grid, dim3(ITER_THREADS), 0, st, S, hyp_old, hyp_new, partials, B, B_global, B_hist, cfg, opt, quat,
+                      trans, lr_mult, lr_t, it, do_step, do_update, do_pose, loss_table, grad_out, pose_hist, loss_hist, zbuf, total_tiles, arrive, multi);
 }
 
 void launch_step(const SceneDev& S, const HypState* hyp, const float* partials, int B, LossCfgDev cfg, float* dmtx_out,

@@ -32,11 +32,19 @@ void launch_clear(const SceneDev& S, const HypState* hyp, int B, unsigned long l
 #endif
 constexpr int RASTER_THREADS = RASTER_THREADS_N;
 
-__global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, const HypState* __restrict__ hyp,
-                                                                unsigned long long* __restrict__ zbuf) {
+template <bool MULTI>
+__global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev Sp, const HypState* __restrict__ hyp,
+                                                                unsigned long long* __restrict__ zbuf, MultiArgs multi) {
     pdl_trigger();
     pdl_wait();  // hyp / z-buffer state of the preceding iter_kernel
     const int b = blockIdx.y;
+    __shared__ __align__(16) unsigned int s_scene[MULTI ? sizeof(SceneDev) / 4 : 4];
+    if (MULTI) {  // this hypothesis's object: its SceneDev from the table into shared memory
+        const unsigned int* src = reinterpret_cast<const unsigned int*>(multi.scenes + hyp[b].obj);
+        for (int i = threadIdx.x; i < (int)(sizeof(SceneDev) / 4); i += blockDim.x) s_scene[i] = src[i];
+        __syncthreads();
+    }
+    const SceneDev& S = MULTI ? *reinterpret_cast<const SceneDev*>(s_scene) : Sp;
     __shared__ float s_mvp[16];
     __shared__ int s_reg[5];
     __shared__ int s_rec[RASTER_THREADS * REC_WORDS];
@@ -60,8 +68,11 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev S, cons
     cta_raster_chunk<RASTER_THREADS>(S, s_mvp, s_reg[4], s_reg[0], s_reg[1], s_reg[2], s_reg[3], t < S.T ? t : -1, s_rec, s_off, &s_nlarge, zwrite);
 }
 
-void launch_raster(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, cudaStream_t st) {
-    launch_kernel(pdl_enabled(), raster_kernel, dim3((S.T + RASTER_THREADS - 1) / RASTER_THREADS, B), dim3(RASTER_THREADS), 0, st, S, hyp, zbuf);
+void launch_raster(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, MultiArgs multi, cudaStream_t st) {
+    const int T = multi.scenes ? multi.max_T : S.T;
+    const dim3 grid((T + RASTER_THREADS - 1) / RASTER_THREADS, B);
+    if (multi.scenes) launch_kernel(pdl_enabled(), raster_kernel<true>, grid, dim3(RASTER_THREADS), 0, st, S, hyp, zbuf, multi);
+    else launch_kernel(pdl_enabled(), raster_kernel<false>, grid, dim3(RASTER_THREADS), 0, st, S, hyp, zbuf, multi);
 }
 
 // Binned path, pass 1: one thread per (hypothesis, triangle) runs the same clip / snap / cull / bounding-box code as the

@@ -95,12 +95,13 @@ def lib():
     L.ddope_profile_end.argtypes = [vp, vp, vp]
     L.ddope_loss_grad.argtypes = [vp, vp, vp, vp, ci, ci, ctypes.POINTER(LossCfg), vp, vp, vp]
     L.ddope_optimize.argtypes = [vp, vp, vp, vp, ci, ci, vp, ci, ctypes.POINTER(LossCfg), vp, vp, vp]
+    L.ddope_optimize_multi.argtypes = [vp, ci, vp, vp, vp, vp, vp, ci, vp, ci, ctypes.POINTER(LossCfg), vp, vp, vp]
     for name in (
         "ddope_xfm_fwd", "ddope_xfm_bwd", "ddope_xfm_bwd_mtx", "ddope_xfm_bwd_full", "ddope_scene_create",
         "ddope_scene_destroy", "ddope_scene_set_camera", "ddope_scene_set_target", "ddope_scene_set_window",
         "ddope_render", "ddope_render_mtx", "ddope_render_bwd", "ddope_loss_grad", "ddope_optimize",
         "ddope_profile_begin", "ddope_profile_end", "ddope_scene_set_texture_filter", "ddope_scene_set_optimizer",
-        "ddope_scene_set_culling", "ddope_image_from_raw", "ddope_scene_set_raster_mode", "ddope_scene_set_bin_capacity", "ddope_scene_set_graph",
+        "ddope_scene_set_culling", "ddope_image_from_raw", "ddope_scene_set_raster_mode", "ddope_scene_set_bin_capacity", "ddope_scene_set_graph", "ddope_optimize_multi",
     ):
         getattr(L, name).restype = ci
     if L.ddope_abi_version() != 2:
@@ -163,6 +164,34 @@ def image_from_raw(raw, is_depth, divisor, flip=True, resize_half=False):
     _check(lib().ddope_image_from_raw(_ptr(raw), nbytes, H, W, C, int(bool(is_depth)), float(divisor), int(bool(flip)), int(bool(resize_half)),
                                       _ptr(out), _stream()))
     return out
+
+
+def optimize_multi(scenes, counts, b_globals, quat, trans, lr_mult, lr_sched, cfg, out=None):
+    """`ddope_optimize_multi`: the hypotheses of several objects (scenes[k] has counts[k] of them, concatenated in that order in
+    quat [B,4] / trans [B,3] / lr_mult [B]; b_globals[k] = divisor of object k's hypothesis mean) refined by one sequence of
+    launches. In place on quat / trans; returns (pose_hist [n,B,7], loss_hist [n,B,4])."""
+    for t, n in ((quat, "quat"), (trans, "trans")):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError("%s must be a contiguous cuda float32 tensor (updated in place)" % n)
+    lr_mult = _dev_f32(lr_mult, "lr_mult")
+    B = int(quat.shape[0])
+    if B != sum(int(c) for c in counts) or len(counts) != len(scenes) or len(b_globals) != len(scenes):
+        raise RuntimeError("optimize_multi: counts / b_globals do not match the scenes and the hypothesis arrays")
+    sched = np.ascontiguousarray(lr_sched, dtype=np.float32)
+    n = sched.shape[0]
+    if out is not None:
+        pose_hist, loss_hist = out
+    else:
+        pose_hist = torch.empty(n, B, 7, device=quat.device)
+        loss_hist = torch.empty(n, B, NUM_LOSSES, device=quat.device)
+    if B == 0:
+        return pose_hist, loss_hist
+    hyp_scene = np.ascontiguousarray(np.repeat(np.arange(len(scenes), dtype=np.int32), np.asarray(counts, dtype=np.int64)))
+    hyp_bg = np.ascontiguousarray(np.repeat(np.asarray(b_globals, dtype=np.int32), np.asarray(counts, dtype=np.int64)))
+    handles = (ctypes.c_void_p * len(scenes))(*[sc._h for sc in scenes])
+    _check(lib().ddope_optimize_multi(ctypes.cast(handles, ctypes.c_void_p), len(scenes), _hptr(hyp_scene), _hptr(hyp_bg), _ptr(quat), _ptr(trans),
+                                      _ptr(lr_mult), B, _hptr(sched), n, ctypes.byref(cfg), _ptr(pose_hist), _ptr(loss_hist), _stream()))
+    return pose_hist, loss_hist
 
 
 class NativeScene:

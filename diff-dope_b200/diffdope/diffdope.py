@@ -881,8 +881,9 @@ class DiffDope:
     def _run_fused(self):
         self._fused_finish(self._fused_enqueue())
 
-    def _fused_enqueue(self, slot=0):
-        """Enqueue the whole optimisation on the current stream (no synchronisation, no host reads)."""
+    def _fused_prepare(self, slot=0):
+        """Everything one fused optimisation needs, nothing enqueued yet: native scene with camera / target / window set, loss
+        config, schedule, this rank's shard of the start poses and multipliers, and the flat result buffer."""
         from . import _dist
 
         L = self.cfg.losses
@@ -897,16 +898,29 @@ class DiffDope:
         lr = self.learning_rates.float().contiguous()
         lo, hi = _dist.shard_range(B)
         Bl, n, K = hi - lo, len(sched), _native.NUM_LOSSES
-        ql, tl = q[lo:hi].contiguous(), t[lo:hi].contiguous()
         # one flat result buffer per rank: [pose history | loss history | final poses] -> one all-gather, one device-to-host copy
         a, b, c = _dist.flat_sizes(n, Bl, K)
         flat = torch.empty(max(c, 1), device=q.device, dtype=torch.float32)
-        sc.optimize(ql, tl, lr[lo:hi].contiguous(), sched, cfg, b_global=B, out=(flat[:a].view(n, Bl, 7), flat[a:b].view(n, Bl, K)))
-        if Bl > 0:
-            fin = flat[b:c].view(Bl, 7)
+        return dict(sc=sc, kinds=kinds, cfg=cfg, sched=sched, B=B, Bl=Bl, n=n, flat=flat, offs=(a, b, c), ql=q[lo:hi].contiguous(),
+                    tl=t[lo:hi].contiguous(), lr=lr[lo:hi].contiguous())
+
+    @staticmethod
+    def _store_final(st, ql, tl):
+        if st["Bl"] > 0:
+            b, c = st["offs"][1], st["offs"][2]
+            fin = st["flat"][b:c].view(st["Bl"], 7)
             fin[:, :4].copy_(ql)
             fin[:, 4:].copy_(tl)
-        return dict(sc=sc, kinds=kinds, B=B, n=n, flat=flat)
+
+    def _fused_enqueue(self, slot=0):
+        """Enqueue the whole optimisation on the current stream (no synchronisation, no host reads)."""
+        st = self._fused_prepare(slot)
+        a, b, _ = st["offs"]
+        n, Bl, K = st["n"], st["Bl"], _native.NUM_LOSSES
+        st["sc"].optimize(st["ql"], st["tl"], st["lr"], st["sched"], st["cfg"], b_global=st["B"],
+                          out=(st["flat"][:a].view(n, Bl, 7), st["flat"][a:b].view(n, Bl, K)))
+        self._store_final(st, st["ql"], st["tl"])
+        return st
 
     def _fused_finish(self, st):
         """Gather the shards (one all-gather), read the result tables back (one copy into pinned memory) and publish them in
@@ -1083,17 +1097,19 @@ class DiffDope:
         return img
 
 
-def run_optimization_batched(ddopes):
-    """Refine several objects of one frame concurrently: every `DiffDope` in `ddopes` (one per object, sharing
-    camera / rgb / depth, each with its own Object3D and segmentation) enqueues its whole optimisation on its
-    own CUDA stream, then all are joined and the result tables are read back once.
+def run_optimization_batched(ddopes, one_launch=True):
+    """Refine several objects of one frame together: every `DiffDope` in `ddopes` (one per object, sharing camera / rgb / depth,
+    each with its own Object3D and segmentation). Replaces the sequential per-object loop of the reference's
+    `examples/run_bop_scene.py:48-93`; each object's result is bit-identical to what `ddope.run_optimization()` gives on its own
+    (same kernels, same fixed reduction order).
 
-    Replaces the sequential per-object loop of the reference's `examples/run_bop_scene.py:48-93`; each
-    object's result is bit-identical to what `ddope.run_optimization()` gives on its own (same kernels, same
-    fixed reduction order). Objects with user-written loss functions fall back to the sequential autograd path."""
+    one_launch=True (default): the hypotheses of all objects form ONE batch -- one sequence of launches whose kernels pick each
+    hypothesis's mesh, texture and targets from a device table of the objects (`ddope_optimize_multi`). Needs the same camera,
+    frame, window, loss configuration, schedule and optimizer for every object; otherwise (or with one_launch=False) every object
+    enqueues its optimisation on its own CUDA stream. Objects with user-written loss functions run the sequential autograd path."""
     ddopes = list(ddopes)
     cur = torch.cuda.current_stream()
-    pending, slots = [], {}
+    fused, slots = [], {}
     for d in ddopes:
         d.losses_values = {}
         d.optimization_results = []
@@ -1105,13 +1121,46 @@ def run_optimization_batched(ddopes):
         mesh_key = id(d.object3d.mesh)
         slot = slots.get(mesh_key, 0)
         slots[mesh_key] = slot + 1
-        stream = torch.cuda.Stream()
-        stream.wait_stream(cur)
-        with torch.cuda.stream(stream):
-            st = d._fused_enqueue(slot)
-        pending.append((d, st, stream))
-    for _, _, stream in pending:
-        cur.wait_stream(stream)
+        fused.append((d, slot))
+    if not fused:
+        return ddopes
+    pending = []
+    preps = [d._fused_prepare(slot) for d, slot in fused] if one_launch and len(fused) > 1 else None
+    if preps is not None:
+        p0 = preps[0]
+        same = all(p["kinds"] == p0["kinds"] and p["sched"] == p0["sched"] and p["n"] == p0["n"] and bytes(p["cfg"]) == bytes(p0["cfg"])
+                   and p["sc"].window == p0["sc"].window and (p["sc"].H, p["sc"].W) == (p0["sc"].H, p0["sc"].W) for p in preps)
+        same = same and len({d._optimizer_kind() for d, _ in fused}) == 1 and len({d._texture_filter() for d, _ in fused}) == 1
+        same = same and all(torch.equal(d.camera.cam_proj.reshape(-1, 16)[0], fused[0][0].camera.cam_proj.reshape(-1, 16)[0]) for d, _ in fused)
+        if not same:
+            preps = None
+    if preps is not None:
+        n, K = preps[0]["n"], _native.NUM_LOSSES
+        counts = [p["Bl"] for p in preps]
+        Bt = sum(counts)
+        q = torch.cat([p["ql"] for p in preps], 0).contiguous()
+        t = torch.cat([p["tl"] for p in preps], 0).contiguous()
+        lr = torch.cat([p["lr"] for p in preps], 0).contiguous()
+        ph, lh = _native.optimize_multi([p["sc"] for p in preps], counts, [p["B"] for p in preps], q, t, lr, preps[0]["sched"], preps[0]["cfg"])
+        o = 0
+        for (d, _), p in zip(fused, preps):
+            a, b, _c = p["offs"]
+            Bl = p["Bl"]
+            p["flat"][:a].view(n, Bl, 7).copy_(ph[:, o:o + Bl])
+            p["flat"][a:b].view(n, Bl, K).copy_(lh[:, o:o + Bl])
+            DiffDope._store_final(p, q[o:o + Bl, :], t[o:o + Bl, :])
+            o += Bl
+            pending.append((d, p, None))
+        assert o == Bt
+    else:
+        for d, slot in fused:
+            stream = torch.cuda.Stream()
+            stream.wait_stream(cur)
+            with torch.cuda.stream(stream):
+                st = d._fused_enqueue(slot)
+            pending.append((d, st, stream))
+        for _, _, stream in pending:
+            cur.wait_stream(stream)
     for d, st, _ in pending:
         d._fused_finish(st)
     return ddopes

@@ -194,7 +194,7 @@ def test_reference_example_runs_unchanged(tmp_path):
 
 
 def test_batched_objects_equal_sequential_loop():
-    """dd.run_optimization_batched (every object on its own CUDA stream) gives each object
+    """dd.run_optimization_batched (all objects of a frame as one batch of launches) gives each object
     bit for bit what the reference-style sequential loop gives; two of the objects share one Mesh."""
     import diffdope as dd
 
@@ -219,15 +219,18 @@ def test_batched_objects_equal_sequential_loop():
     seq = [make(k) for k in range(3)]
     for d in seq:
         d.run_optimization()
-    par = dd.run_optimization_batched([make(k) for k in range(3)])
-    for a, b in zip(seq, par):
-        assert list(a.losses_values.keys()) == list(b.losses_values.keys()) == ["rgb", "depth", "mask_selection"]
-        for k in a.losses_values:
-            assert torch.equal(a.losses_values[k], b.losses_values[k])
-        qa, ta = a.object3d.pose_tensors()
-        qb, tb = b.object3d.pose_tensors()
-        assert torch.equal(qa, qb) and torch.equal(ta, tb)
-        assert np.array_equal(a.get_pose(), b.get_pose())
+    # one launch over (object, hypothesis) with per-object mesh / target tables (ddope_optimize_multi), and one stream per object
+    for one_launch in (True, False):
+        par = dd.run_optimization_batched([make(k) for k in range(3)], one_launch=one_launch)
+        for a, b in zip(seq, par):
+            assert list(a.losses_values.keys()) == list(b.losses_values.keys()) == ["rgb", "depth", "mask_selection"]
+            for k in a.losses_values:
+                assert torch.equal(a.losses_values[k], b.losses_values[k]), (one_launch, k)
+            qa, ta = a.object3d.pose_tensors()
+            qb, tb = b.object3d.pose_tensors()
+            assert torch.equal(qa, qb) and torch.equal(ta, tb)
+            assert np.array_equal(a.get_pose(), b.get_pose())
+            assert torch.equal(a._pose_hist_host, b._pose_hist_host)
     assert not torch.equal(seq[0].losses_values["rgb"], seq[1].losses_values["rgb"])
 
 
