@@ -679,6 +679,58 @@ extern "C" int ddope_render_bwd(ddope_scene* s, const float* mtx_in, int B, cons
     return 0;
 }
 
+// Gradient of dL/d rgb w.r.t. the texture texels or the vertex colours (Mesh.enable_gradients_texture, diffdope.py:909-920).
+extern "C" int ddope_render_bwd_attr(ddope_scene* s, const float* mtx_in, int B, const float* d_rgb, float* d_tex, float* d_vcol, void* stream) {
+    if (!s || !mtx_in || !d_rgb || (!d_tex && !d_vcol)) return fail("ddope_render_bwd_attr: null pointer");
+    if (B <= 0 || B > 65535) return fail("ddope_render_bwd_attr: B must be in [1, 65535]");
+    if (!s->have_camera) return fail("ddope_render_bwd_attr: set the camera first");
+    const SceneDev& d = s->dev;
+    if (d_tex && !d.tex4) return fail("ddope_render_bwd_attr: the mesh has no texture");
+    if (d_vcol && !d.tricol) return fail("ddope_render_bwd_attr: the mesh has no vertex colours");
+    if (d_tex && d.tex_filter != DDOPE_TEX_LINEAR) return fail("ddope_render_bwd_attr: texture gradients are built for the reference's bilinear filter only");
+    SCENE_GUARD("ddope_render_bwd_attr");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = ensure_buffers(s, B, false, st)) return r;
+    LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
+    if (d_tex) CK(cudaMemsetAsync(d_tex, 0, sizeof(float) * 3 * (size_t)d.tex_h * d.tex_w, st));
+    if (d_vcol) CK(cudaMemsetAsync(d_vcol, 0, sizeof(float) * 3 * (size_t)d.V, st));
+    launch_pose(s->dev, nullptr, nullptr, mtx_in, nullptr, B, B, cfg, 2, s->hyp, s->total_tiles, st);
+    launch_raster(s->dev, s->hyp, B, s->zbuf, MultiArgs{nullptr, nullptr, 0, 0}, st);
+    launch_attr_grad(s->dev, s->hyp, B, s->zbuf, d_rgb, d_tex, d_vcol, st);
+    launch_clear(s->dev, s->hyp, B, s->zbuf, st);  // restore the z-buffer invariant
+    s->launches = 4;
+    CK_LAUNCH("ddope_render_bwd_attr");
+    return 0;
+}
+
+// The colour attributes changed (an optimizer stepped them): refresh the scene's copies. tex_dev [tex_h, tex_w, 3], vcol_dev [V, 3].
+extern "C" int ddope_scene_update_texture(ddope_scene* s, const float* tex_dev, void* stream) {
+    if (!s || !tex_dev) return fail("ddope_scene_update_texture: null pointer");
+    SceneDev& d = s->dev;
+    if (!d.tex4) return fail("ddope_scene_update_texture: the mesh has no texture");
+    SCENE_GUARD("ddope_scene_update_texture");
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_tex_pack(tex_dev, (size_t)d.tex_h * d.tex_w, s->tex4, st);
+    for (int l = 1, w = d.tex_w, h = d.tex_h; l < d.tex_levels; l++) {  // rebuild the mip chain, if one exists
+        const int nw = w > 1 ? w >> 1 : 1, nh = h > 1 ? h >> 1 : 1;
+        launch_tex_mip(s->tex4 + d.tex_off[l - 1], w, h, s->tex4 + d.tex_off[l], nw, nh, st);
+        w = nw; h = nh;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ddope_scene_update_vertex_colors(ddope_scene* s, const float* vcol_dev, void* stream) {
+    if (!s || !vcol_dev) return fail("ddope_scene_update_vertex_colors: null pointer");
+    SceneDev& d = s->dev;
+    if (!d.tricol) return fail("ddope_scene_update_vertex_colors: the mesh has no vertex colours");
+    SCENE_GUARD("ddope_scene_update_vertex_colors");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(s->vcol, vcol_dev, sizeof(float) * 3 * (size_t)d.V, cudaMemcpyDeviceToDevice, st));
+    launch_tricol(s->vcol, s->tri, d.T, s->tricol, st);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // kernel classes for the profiling hook
 enum { K_ITER = 0, K_RASTER = 1, K_PIXEL = 2 };
 

@@ -86,6 +86,9 @@ void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* tota
                          const unsigned long long* zbuf, RenderOut out, int num_sms, cudaStream_t st);
 
 void launch_render_fill(RenderOut out, const float* trans, const float* mtx, int B, int wh, int ww, int num_sms, cudaStream_t st);
+void launch_attr_grad(const SceneDev& S, const HypState* hyp, int B, const unsigned long long* zbuf, const float* d_rgb, float* d_tex, float* d_vcol,
+                      cudaStream_t st);
+void launch_tricol(const float* vcol, const int* tri, int T, float4* tricol, cudaStream_t st);
 void launch_gt_edge(const SceneDev& S, float* out, cudaStream_t st);
 void launch_tex_pack(const float* tex3, size_t n, float4* out, cudaStream_t st);
 void launch_tex_mip(const float4* src, int sw, int sh, float4* dst, int dw, int dh, cudaStream_t st);

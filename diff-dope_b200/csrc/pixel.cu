@@ -577,6 +577,7 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
 
         // 1. triangle ids of tile + 2 px halo, one warp per row (row loads coalesce; all of a warp's
         //    z-buffer loads are issued before any is consumed), plus per-row coverage / in-frame bitmasks
+        bool tile_cov = false;
         {
             const int lane = tid & 31, warp = tid >> 5;
             constexpr int ROWS_PER_WARP = (IDS_H + 7) / 8;
@@ -620,9 +621,15 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
                     s_cov[iy] = ((unsigned long long)c1 << 32) | c0;
                     s_inf[iy] = ((unsigned long long)f1 << 32) | f0;
                 }
+                tile_cov |= (c0 | c1) != 0u;
             }
         }
-        __syncthreads();
+        if (MODE == MODE_RENDER) {
+            // image output: nothing of the object in this tile or its halo -> background, already written by render_fill_kernel
+            if (!__syncthreads_or(tile_cov ? 1 : 0)) continue;  // (the barrier also orders s_b / s_item against the next item)
+        } else {
+            __syncthreads();
+        }
 
         // 2. silhouette pairs (exactly one pixel covered, both in the frame, at least one within the
         //    1 px halo) -> queue, from the row bitmasks. Equal-coverage pairs blend alpha*(1-1) or
@@ -1185,6 +1192,78 @@ void launch_pixel_ext(const SceneDev& S, const HypState* hyp, const int* total_t
     RenderOut none = {nullptr, nullptr, nullptr, nullptr};
     BinArgs nobins = {nullptr, nullptr, 0, nullptr};
     launch_pixel<MODE_EXT, false, false>(S, hyp, total_tiles, B, max_tiles, cfg, zbuf, partials, none, ext, nobins, num_sms, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gradient of the rendered colour w.r.t. the colour ATTRIBUTES (texture texels or vertex colours): what autograd sends into
+// `tex` / `vtx_color` once Mesh.enable_gradients_texture() made them parameters (diffdope/diffdope.py:909-920) -- the tex part of
+// nvdiffrast's TextureGradKernelLinear (bilinear weights scattered to the four taps) or the attribute part of InterpolateGradKernel
+// (barycentrics scattered to the three vertices). One thread per window pixel and hypothesis, ids from the z-buffer; float atomics,
+// summed over the batch (the reference's B stacked copies of the texture are one texture here). Bilinear level-0 lookups only.
+__global__ void __launch_bounds__(256) attr_grad_kernel(SceneDev S, const HypState* __restrict__ hyp, const unsigned long long* __restrict__ zbuf,
+                                                        const float* __restrict__ d_rgb, float* __restrict__ d_tex, float* __restrict__ d_vcol) {
+    const int b = blockIdx.y;
+    const HypState& h = hyp[b];
+    const int rw = h.rx1 - h.rx0, rh = h.ry1 - h.ry0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rw <= 0 || i >= rw * rh) return;
+    const int x = h.rx0 + i % rw, y = h.ry0 + i / rw;
+    const unsigned long long key = zbuf[(size_t)b * S.zh * S.zw + (size_t)(y - S.zy0) * S.zw + (x - S.zx0)];
+    if (key == EMPTY_KEY) return;
+    const int id = (int)(unsigned int)(key & 0xFFFFFFFFull);
+    const size_t wp = ((size_t)b * S.wh + (y - S.wy0)) * S.ww + (x - S.wx0);
+    const float dy[3] = {d_rgb[wp * 3], d_rgb[wp * 3 + 1], d_rgb[wp * 3 + 2]};
+    if (dy[0] == 0.f && dy[1] == 0.f && dy[2] == 0.f) return;
+    Shade sh;
+    shade_setup<true>(S, h.mvp, id, x, y, S.ndc_xs, S.ndc_xo, S.ndc_ys, S.ndc_yo, sh);
+    const float b0 = sh.u, b1 = sh.v, b2 = xsub(xsub(1.f, sh.u), sh.v);
+    if (d_tex && S.tex4) {
+        const float u = xadd(xadd(xmul(b0, sh.v0.w), xmul(b1, sh.v1.w)), xmul(b2, sh.v2.w));
+        const float v = xadd(xadd(xmul(b0, sh.vv.x), xmul(b1, sh.vv.y)), xmul(b2, sh.vv.z));
+        const int tw = S.tex_w, th = S.tex_h;
+        float tu = xsub(u, floorf(u)), tv = xsub(v, floorf(v));
+        tu = xsub(xmul(tu, (float)tw), 0.5f); tv = xsub(xmul(tv, (float)th), 0.5f);
+        int iu0 = (int)floorf(tu), iv0 = (int)floorf(tv);
+        const float fu = xsub(tu, (float)iu0), fv = xsub(tv, (float)iv0);
+        int iu1 = iu0 + 1, iv1 = iv0 + 1;
+        if (iu0 < 0) iu0 += tw;
+        if (iv0 < 0) iv0 += th;
+        if (iu1 >= tw) iu1 -= tw;
+        if (iv1 >= th) iv1 -= th;
+        const float w00 = (1.f - fu) * (1.f - fv), w10 = fu * (1.f - fv), w01 = (1.f - fu) * fv, w11 = fu * fv;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            atomicAdd(d_tex + ((size_t)iv0 * tw + iu0) * 3 + c, w00 * dy[c]);
+            atomicAdd(d_tex + ((size_t)iv0 * tw + iu1) * 3 + c, w10 * dy[c]);
+            atomicAdd(d_tex + ((size_t)iv1 * tw + iu0) * 3 + c, w01 * dy[c]);
+            atomicAdd(d_tex + ((size_t)iv1 * tw + iu1) * 3 + c, w11 * dy[c]);
+        }
+    } else if (d_vcol && S.tricol) {
+        const int v0 = S.tri[3 * id], v1 = S.tri[3 * id + 1], v2 = S.tri[3 * id + 2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            atomicAdd(d_vcol + 3 * (size_t)v0 + c, b0 * dy[c]);
+            atomicAdd(d_vcol + 3 * (size_t)v1 + c, b1 * dy[c]);
+            atomicAdd(d_vcol + 3 * (size_t)v2 + c, b2 * dy[c]);
+        }
+    }
+}
+
+void launch_attr_grad(const SceneDev& S, const HypState* hyp, int B, const unsigned long long* zbuf, const float* d_rgb, float* d_tex, float* d_vcol,
+                      cudaStream_t st) {
+    const int n = S.wh * S.ww;  // upper bound of a hypothesis's ROI
+    attr_grad_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(S, hyp, zbuf, d_rgb, d_tex, d_vcol);
+}
+
+// per-triangle vertex colours from the per-vertex table (after the colours changed: ddope_scene_update_vertex_colors)
+__global__ void tricol_kernel(const float* __restrict__ vcol, const int* __restrict__ tri, int T, float4* __restrict__ tricol) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * T) return;
+    const int v = tri[i];
+    tricol[i] = make_float4(vcol[3 * v], vcol[3 * v + 1], vcol[3 * v + 2], 0.f);
+}
+void launch_tricol(const float* vcol, const int* tri, int T, float4* tricol, cudaStream_t st) {
+    tricol_kernel<<<(3 * T + 255) / 256, 256, 0, st>>>(vcol, tri, T, tricol);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -87,6 +87,9 @@ def lib():
     L.ddope_render.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
     L.ddope_render_mtx.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
     L.ddope_render_bwd.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp]
+    L.ddope_render_bwd_attr.argtypes = [vp, vp, ci, vp, vp, vp, vp]
+    L.ddope_scene_update_texture.argtypes = [vp, vp, vp]
+    L.ddope_scene_update_vertex_colors.argtypes = [vp, vp, vp]
     L.ddope_image_from_raw.argtypes = [vp, ci, ci, ci, ci, ci, ctypes.c_double, ci, ci, vp, vp]
     L.ddope_image_from_raw.restype = ci
     L.ddope_debug_read.argtypes = [vp, ci, vp, ctypes.c_int64]
@@ -101,7 +104,8 @@ def lib():
         "ddope_scene_destroy", "ddope_scene_set_camera", "ddope_scene_set_target", "ddope_scene_set_window",
         "ddope_render", "ddope_render_mtx", "ddope_render_bwd", "ddope_loss_grad", "ddope_optimize",
         "ddope_profile_begin", "ddope_profile_end", "ddope_scene_set_texture_filter", "ddope_scene_set_optimizer",
-        "ddope_scene_set_culling", "ddope_image_from_raw", "ddope_scene_set_raster_mode", "ddope_scene_set_bin_capacity", "ddope_scene_set_graph", "ddope_optimize_multi",
+        "ddope_scene_set_culling", "ddope_image_from_raw", "ddope_scene_set_raster_mode", "ddope_scene_set_bin_capacity", "ddope_scene_set_graph", "ddope_optimize_multi", "ddope_render_bwd_attr",
+        "ddope_scene_update_texture", "ddope_scene_update_vertex_colors",
     ):
         getattr(L, name).restype = ci
     if L.ddope_abi_version() != 2:
@@ -217,6 +221,7 @@ class NativeScene:
                                     _hptr(None if self.textured else vc)))
         self._h = h
         self._keep = {}
+        self.tex_shape = tuple(tex.shape[:2]) if self.textured else None
         self.H = self.W = None
         self.window = None
 
@@ -344,6 +349,28 @@ class NativeScene:
         d_mtx = torch.empty(B, 4, 4, device=mtx.device)
         _check(lib().ddope_render_bwd(self._h, _ptr(mtx), B, _ptr(d_rgb), _ptr(d_depth), _ptr(d_mask), _ptr(d_mtx), _stream()))
         return d_mtx
+
+    def render_attr_grad(self, mtx, d_rgb):
+        """dL/d rgb [B,h,w,3] -> dL/d tex [Ht,Wt,3] (textured mesh) or dL/d vtx_color [V,3], summed over the batch."""
+        mtx, d_rgb = _dev_f32(mtx, "mtx"), _dev_f32(d_rgb, "d_rgb")
+        B = mtx.shape[0]
+        if self.textured:
+            g = torch.empty(self.tex_shape[0], self.tex_shape[1], 3, device=mtx.device)
+            _check(lib().ddope_render_bwd_attr(self._h, _ptr(mtx), B, _ptr(d_rgb), _ptr(g), None, _stream()))
+        else:
+            g = torch.empty(self.V, 3, device=mtx.device)
+            _check(lib().ddope_render_bwd_attr(self._h, _ptr(mtx), B, _ptr(d_rgb), None, _ptr(g), _stream()))
+        return g
+
+    def update_colors(self, attr):
+        """The texture [Ht,Wt,3] / vertex colours [V,3] changed (an optimizer step): refresh the scene's device copy."""
+        attr = _dev_f32(attr.detach(), "attr")
+        if self.textured:
+            assert tuple(attr.shape) == (self.tex_shape[0], self.tex_shape[1], 3)
+            _check(lib().ddope_scene_update_texture(self._h, _ptr(attr), _stream()))
+        else:
+            assert tuple(attr.shape) == (self.V, 3)
+            _check(lib().ddope_scene_update_vertex_colors(self._h, _ptr(attr), _stream()))
 
     def loss_grad(self, quat, trans, lr_mult, cfg, b_global=None):
         quat, trans = _dev_f32(quat, "quat"), _dev_f32(trans, "trans")

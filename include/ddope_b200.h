@@ -208,6 +208,15 @@ int ddope_render_mtx(ddope_scene* s, const float* mtx_dev, int B, float* rgb_dev
 int ddope_render_bwd(ddope_scene* s, const float* mtx_dev, int B, const float* d_rgb_dev,
                      const float* d_depth_dev, const float* d_mask_dev, float* d_mtx_dev, void* stream);
 
+/* The colour-attribute part of the same backward: dL/d rgb [B,h,w,3] -> dL/d tex [tex_h,tex_w,3] (textured mesh, bilinear filter) or
+ * dL/d vtx_color [V,3], summed over the B hypotheses (the reference stacks B copies of the texture; here there is one). This is what
+ * autograd delivers into `tex` / `vtx_color` once Mesh.enable_gradients_texture() made them parameters (diffdope.py:909-920: dr.texture's
+ * and dr.interpolate's attribute gradients). The output is zeroed first; float atomics (summation order not fixed, like nvdiffrast's).
+ * ddope_scene_update_texture / _vertex_colors refresh the scene's copy after an optimizer changed the attribute (device pointers). */
+int ddope_render_bwd_attr(ddope_scene* s, const float* mtx_dev, int B, const float* d_rgb_dev, float* d_tex_dev, float* d_vcol_dev, void* stream);
+int ddope_scene_update_texture(ddope_scene* s, const float* tex_dev, void* stream);
+int ddope_scene_update_vertex_colors(ddope_scene* s, const float* vcol_dev, void* stream);
+
 /* One forward + loss + backward without a parameter update: the gradient autograd
  * produces at diffdope.py:1713 for loss = sum_k w_k * mean_b(lr_b * mean_px |.|)
  * (diffdope.py:534-613). B_global is the divisor of mean_b (the whole job's hypothesis

@@ -485,6 +485,20 @@ def texture_linear_grad_uv(tex, uv, d_out):
     return np.stack([gu, gv], -1).astype(F)
 
 
+def texture_linear_grad_tex(tex_shape, uv, d_out):
+    """`TextureGradKernelLinear`, texture part: the bilinear weights of every lookup scattered to its four taps (what autograd
+    sends into `tex` once `Mesh.enable_gradients_texture()` made it a parameter, `diffdope/diffdope.py:909-920`). One texture
+    shared by the batch: the gradient is summed over it. Accumulated in float64, returned as float32."""
+    Ht, Wt, C = tex_shape
+    iu0, iv0, iu1, iv1, fu, fv = _tex_taps(uv, Ht, Wt)
+    g = np.zeros((Ht * Wt, C), dtype=np.float64)
+    dy = d_out.reshape(-1, C).astype(np.float64)
+    fu, fv = fu.reshape(-1, 1).astype(np.float64), fv.reshape(-1, 1).astype(np.float64)
+    for iv, iu, w in ((iv0, iu0, (1 - fu) * (1 - fv)), (iv0, iu1, fu * (1 - fv)), (iv1, iu0, (1 - fu) * fv), (iv1, iu1, fu * fv)):
+        np.add.at(g, (iv * Wt + iu).reshape(-1), w * dy)
+    return g.reshape(Ht, Wt, C).astype(F)
+
+
 # ----------------------------------------------------------------------------
 # texture, "linear-mipmap-linear" -- EXTENSION with no reference counterpart (the reference calls
 # dr.texture with filter_mode="linear" only, `diffdope/diffdope.py:221-226`; BASELINE.json's

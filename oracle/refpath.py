@@ -99,12 +99,15 @@ class _TextureLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tex, uv):
         ctx.save_for_backward(tex, uv)
-        return torch.from_numpy(nvdr.texture_linear(tex.numpy(), uv.detach().numpy()))
+        return torch.from_numpy(nvdr.texture_linear(tex.detach().numpy(), uv.detach().numpy()))
 
     @staticmethod
     def backward(ctx, d_out):
         tex, uv = ctx.saved_tensors
-        return None, torch.from_numpy(nvdr.texture_linear_grad_uv(tex.numpy(), uv.detach().numpy(), d_out.numpy()))
+        g_tex = None
+        if ctx.needs_input_grad[0]:  # Mesh.enable_gradients_texture (diffdope.py:909-920)
+            g_tex = torch.from_numpy(nvdr.texture_linear_grad_tex(tuple(tex.shape), uv.detach().numpy(), d_out.numpy()))
+        return g_tex, torch.from_numpy(nvdr.texture_linear_grad_uv(tex.detach().numpy(), uv.detach().numpy(), d_out.numpy()))
 
 
 class _TextureMipmap(torch.autograd.Function):
@@ -195,11 +198,12 @@ class Mesh:
         return self.tex is not None
 
 
-def render(mesh, proj, quat_raw, trans, H, W):
+def render(mesh, proj, quat_raw, trans, H, W, tex=None, vtx_color=None):
     """`Object3D.forward` + `matrix_batch_44_from_position_quat` + `render_texture_batch`
     (`diffdope/diffdope.py:1085-1098,46-89,156-234`). quat_raw/trans are torch leaf
     (or any) tensors [B,4]/[B,3]. Returns dict rgb [B,H,W,3], depth [B,H,W],
-    mask [B,H,W,3], rast_out, mtx."""
+    mask [B,H,W,3], rast_out, mtx. `tex` / `vtx_color`: torch tensors to use instead of the mesh's arrays (so that they can
+    require grad: `Mesh.enable_gradients_texture`, diffdope.py:909-920)."""
     B = quat_raw.shape[0]
     q = quat_raw / torch.norm(quat_raw, dim=1).reshape(-1, 1)
     mtx = matrix_batch_44_from_position_quat(q, trans)
@@ -231,9 +235,9 @@ def render(mesh, proj, quat_raw, trans, H, W):
             lod = nvdr.texture_lod(pos_clip.detach().numpy(), mesh.tri, mesh.uv, rast.detach().numpy(), mesh.tex.shape[:2], len(levels))
             color = _TextureMipmap.apply(texc, torch.from_numpy(lod), levels)
         else:
-            color = _TextureLinear.apply(torch.from_numpy(mesh.tex), texc)
+            color = _TextureLinear.apply(torch.from_numpy(mesh.tex) if tex is None else tex, texc)
     else:
-        color = _Interpolate.apply(torch.from_numpy(mesh.vtx_color), rast, mesh.tri)
+        color = _Interpolate.apply(torch.from_numpy(mesh.vtx_color) if vtx_color is None else vtx_color, rast, mesh.tri)
     color = color * torch.clamp(rast[..., -1:], 0, 1)
     return {"rgb": color, "depth": depth, "mask": mask, "rast_out": rast, "mtx": mtx}
 

@@ -193,6 +193,47 @@ def test_reference_example_runs_unchanged(tmp_path):
         os.remove(p)
 
 
+def test_reference_bop_example_runs_unchanged(tmp_path):
+    """The reference's own `examples/run_bop_scene.py` (byte-for-byte copy under tests/golden/reference_examples/) against this
+    package. Its BOP paths are hard-coded to its author's home directory (run_bop_scene.py:19-25), so the script runs under
+    tests/run_with_path_map.py, which serves those prefixes from a BOP-layout directory built here: the reference's own perturbed-pose
+    file for HOPE val/000001 (18 objects in frame "0"; copy under tests/golden/), the example rgb / depth images, the example
+    segmentation as every object's mask_visib, and the example mesh under every obj_id. The script itself is not touched."""
+    import json
+    import shutil
+
+    scene = tmp_path / "hope" / "val" / "000001"
+    models = tmp_path / "hope" / "models"
+    for d in (scene / "rgb", scene / "depth", scene / "mask_visib", models, tmp_path / "data" / "hope" / "val" / "000001", tmp_path / "out"):
+        d.mkdir(parents=True)
+    ex = os.path.join(ROOT, "data", "example")
+    shutil.copy(os.path.join(ex, "scene", "rgb.png"), scene / "rgb" / "000000.png")
+    shutil.copy(os.path.join(ex, "scene", "depth.png"), scene / "depth" / "000000.png")
+    poses = os.path.join(ROOT, "tests", "golden", "hope_val_000001_scene_error_deg_040_trans_016.json")
+    shutil.copy(poses, tmp_path / "data" / "hope" / "val" / "000001" / "scene_error_deg_040_trans_016.json")
+    frame0 = json.load(open(poses))["0"]
+    assert len(frame0) == 18
+    for k, obj in enumerate(frame0):
+        os.symlink(os.path.join(ex, "scene", "seg.png"), scene / "mask_visib" / ("000000_%06d.png" % k))
+        ply = models / ("obj_%06d.ply" % obj["obj_id"])
+        if not ply.exists():
+            os.symlink(os.path.join(ex, "mesh", "AlphabetSoup.ply"), ply)
+    for f in os.listdir(os.path.join(ex, "mesh")):  # the PLY names its texture file: it must sit next to the model
+        if not f.endswith(".ply"):
+            os.symlink(os.path.join(ex, "mesh", f), models / f)
+    path_map = [["/home/jtremblay/code/camera2robot/hope", str(tmp_path / "hope")], ["/home/jtremblay/code/diff-dope/data", str(tmp_path / "data")]]
+    env = dict(os.environ, PATH_MAP=json.dumps(path_map),
+               PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "diff-dope_b200"), os.path.join(ROOT, "diff-dope_b200", "compat")]))
+    script = os.path.join(ROOT, "tests", "golden", "reference_examples", "run_bop_scene.py")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_with_path_map.py"), script, "hyperparameters.nb_iterations=6",
+                          "hyperparameters.batchsize=4", "hydra.run.dir=%s" % (tmp_path / "out")], capture_output=True, text=True, cwd=ROOT, env=env, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    text = out.stdout + out.stderr
+    assert "object 17" in text, "all 18 objects of the frame were refined"
+    for k in range(18):
+        assert os.path.getsize(tmp_path / "out" / ("%02d.png" % k)) > 1000
+
+
 def test_batched_objects_equal_sequential_loop():
     """dd.run_optimization_batched (all objects of a frame as one batch of launches) gives each object
     bit for bit what the reference-style sequential loop gives; two of the objects share one Mesh."""

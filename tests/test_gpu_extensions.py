@@ -1,6 +1,8 @@
 """GPU parity of the north_star extensions that have no reference counterpart:
 Sobel-edge loss, linear-mipmap-linear texture filter, Adam pose step. Each is checked through the C ABI
 against its own oracle (oracle/refpath.py, oracle/nvdr.py); defaults stay the reference's behaviour."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -181,3 +183,70 @@ def test_parts_and_shards_are_bit_identical_with_extensions(ex_q):
     finally:
         ex.sc.set_optimizer("sgd")
         ex.sc.set_texture_filter("linear")
+
+
+def test_colour_attribute_gradients_match_oracle(ex_q, tmp_path):
+    """`Mesh.enable_gradients_texture` (`diffdope/diffdope.py:909-920`, dead code in the reference): gradient of a loss on the
+    rendered colour w.r.t. the texture texels (`ddope_render_bwd_attr`) against the oracle's dr.texture attribute backward, and
+    w.r.t. the vertex colours of an untextured mesh against dr.interpolate's; then through the public API (`render_texture_batch`
+    + autograd + an optimizer step that changes the texture)."""
+    from oracle import refpath
+    from test_gpu_parity import _cube_scene
+
+    ex = ex_q
+    B = 2
+    qs, ts = su.perturbed_poses(ex.q, ex.t, B, seed=4, rot_deg=2.0, trans=0.02)
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal((B, ex.H, ex.W, 3)).astype(np.float32)
+    qn = qs / np.linalg.norm(qs, axis=1, keepdims=True)
+    from diffdope import matrix_batch_44_from_position_quat
+
+    mtx = matrix_batch_44_from_position_quat(torch.from_numpy(qn), torch.from_numpy(ts)).cuda().contiguous()
+    g = ex.sc.render_attr_grad(mtx, torch.from_numpy(w).cuda())
+    tex = torch.tensor(ex.arr["tex"], requires_grad=True)
+    r = refpath.render(ex.oracle_mesh(), ex.P, torch.from_numpy(qs), torch.from_numpy(ts), ex.H, ex.W, tex=tex)
+    (r["rgb"] * torch.from_numpy(w)).sum().backward()
+    go, gg = tex.grad.numpy(), g.cpu().numpy()
+    assert np.count_nonzero(go) > 1000 and np.array_equal(go != 0, gg != 0), "the same texels receive gradient"
+    assert np.abs(go - gg).max() <= 1e-5 * np.abs(go).max()
+
+    # vertex colours (cube)
+    n, sc, mesh, P, gt, H, W = _cube_scene()
+    qc = np.array([[0.3, 0.2, 0.1, 0.9], [0.0, 0.7, 0.1, 0.6]], dtype=np.float32)
+    tc = np.array([[0.1, -0.05, -4.0], [-0.3, 0.2, -3.0]], dtype=np.float32)
+    wc = rng.standard_normal((2, H, W, 3)).astype(np.float32)
+    qcn = qc / np.linalg.norm(qc, axis=1, keepdims=True)
+    mc = matrix_batch_44_from_position_quat(torch.from_numpy(qcn), torch.from_numpy(tc)).cuda().contiguous()
+    gv = sc.render_attr_grad(mc, torch.from_numpy(wc).cuda()).cpu().numpy()
+    vcol = torch.tensor(mesh.vtx_color, requires_grad=True)
+    rc = refpath.render(mesh, P, torch.from_numpy(qc), torch.from_numpy(tc), H, W, vtx_color=vcol)
+    (rc["rgb"] * torch.from_numpy(wc)).sum().backward()
+    assert np.abs(vcol.grad.numpy() - gv).max() <= 1e-5 * np.abs(vcol.grad.numpy()).max()
+
+    # public API: the texture is a parameter of the mesh, a custom loss reaches it, the optimizer changes it, the render follows
+    import diffdope as dd
+
+    m = dd.Mesh(os.path.join(su.DATA, "mesh", "AlphabetSoup.ply"), scale=su.SCALE)
+    m.cuda()
+    m.set_batchsize(B)
+    m.enable_gradients_texture()
+    assert [k for k, _ in m.named_parameters()] == ["_tex"] and m.tex.requires_grad and tuple(m.tex.shape) == (B, 2048, 2048, 3)
+    proj = torch.from_numpy(ex.P.astype(np.float32)).cuda()
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+
+    def render():
+        out = m()
+        return dd.render_texture_batch(None, proj, mtx, out["pos"], out["pos_idx"], [ex.H, ex.W], uv=out["uv"], uv_idx=out["uv_idx"], tex=out["tex"])
+
+    wt = torch.from_numpy(w).cuda()
+    r0 = render()
+    loss0 = (r0["rgb"] * wt).sum()
+    loss0.backward()
+    assert tuple(m._tex.grad.shape) == (2048, 2048, 3)
+    assert np.abs(m._tex.grad.cpu().numpy() - go).max() <= 1e-5 * np.abs(go).max(), "same gradient through render_texture_batch + autograd"
+    opt.step()
+    r1 = render()
+    loss1 = (r1["rgb"] * wt).sum()
+    assert float(loss1) < float(loss0), "a gradient step on the texture lowers the loss, and the scene's copy followed the parameter"
+    exp = float(loss0) - 0.5 * float((m._tex.grad ** 2).sum())  # the render is linear in the texels
+    assert abs(float(loss1) - exp) <= 1e-3 * abs(float(loss0) - exp) + 1e-3 * abs(exp)

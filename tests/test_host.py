@@ -217,9 +217,33 @@ def test_reference_example_reaches_the_device_under_the_shims(tmp_path):
     assert "__post_init__" in out.stderr
 
 
+def test_find_crop_centred_extension():
+    """The better crop finder (extension; readme.md:30): centred, whole tiles, inside the image, contains the grown bounding box."""
+    import diffdope as dd
+
+    seg = torch.from_numpy(su.example_targets(0.5)["segmentation"])
+    y0, x0, h, w = dd.find_crop_centred(seg)
+    rows, cols = torch.nonzero(seg[..., 0] > 0).T
+    top, bottom, left, right = int(rows.min()), int(rows.max()), int(cols.min()), int(cols.max())
+    assert h == w and h % 32 == 0 and 0 <= y0 and y0 + h <= 540 and 0 <= x0 and x0 + w <= 960
+    assert y0 <= top and x0 <= left and y0 + h > bottom and x0 + w > right
+    assert abs((x0 + w / 2) - (left + right + 1) / 2) <= 1, "centred where the image allows it"
+    old = dd.find_crop(seg)  # the reference's: top-left anchored, side = max extent of the grown box
+    assert old[2] < h + 32
+    # elongated region near a corner: shifted inside, not cut; empty mask: the whole image
+    m = torch.zeros(100, 200)
+    m[2:10, 150:199] = 1
+    y0, x0, h, w = dd.find_crop_centred(m, percentage=0.1, multiple=32, min_size=32)
+    assert (h, w) == (64, 64) and y0 == 0 and x0 + w <= 200 and x0 <= 150 and x0 + w >= 199
+    assert dd.find_crop_centred(torch.zeros(50, 60)) == (0, 0, 50, 60)
+    assert dd.find_crop_centred(torch.ones(40, 300), multiple=32) == (0, 0, 40, 300), "larger than the image: the image"
+
+
 def test_shipped_reference_inputs_are_verbatim():
     """tests/golden/reference_examples/simple_scene.py and tests/golden/configs/diffdope.yaml are the reference's files, byte for byte."""
     pairs = [("tests/golden/reference_examples/simple_scene.py", "/root/reference/examples/simple_scene.py"),
+             ("tests/golden/reference_examples/run_bop_scene.py", "/root/reference/examples/run_bop_scene.py"),
+             ("tests/golden/hope_val_000001_scene_error_deg_040_trans_016.json", "/root/reference/data/hope/val/000001/scene_error_deg_040_trans_016.json"),
              ("tests/golden/configs/diffdope.yaml", "/root/reference/configs/diffdope.yaml")]
     if not os.path.exists(pairs[0][1]):
         pytest.skip("reference tree not on this box")
