@@ -88,7 +88,7 @@ __device__ __forceinline__ bool roi_corner(const SceneDev& S, const float* mvp, 
 
 // roi_mode 1 (losses): ROI = (screen bbox of the AABB corners, grown) U (bbox of seg != 0), clipped to the window; the tile grid covers it.
 // roi_mode 0 (external image gradients): ROI = tile grid = the whole window.
-// roi_mode 2 (image output): ROI = screen bbox of the object only (what is rasterised / cleared), tile grid = the whole window.
+// roi_mode 2 (image output): ROI = tile grid = screen bbox of the object only (the rest of the window is filled as background).
 __device__ void hyp_roi_part(const SceneDev& S, bool full, float mnx, float mny, float mxx, float mxy, int roi_mode, HypState& h) {
     const int wx0 = S.wx0, wy0 = S.wy0, wx1 = S.wx0 + S.ww, wy1 = S.wy0 + S.wh;  // window, exclusive end
     int x0 = wx0, y0 = wy0, x1 = wx1, y1 = wy1;
@@ -107,8 +107,9 @@ __device__ void hyp_roi_part(const SceneDev& S, bool full, float mnx, float mny,
     }
     if (x1 <= x0 || y1 <= y0) { x0 = x1 = S.wx0; y0 = y1 = S.wy0; }
     h.rx0 = x0; h.ry0 = y0; h.rx1 = x1; h.ry1 = y1;
-    if (roi_mode == 2) { h.gx0 = wx0; h.gy0 = wy0; h.gx1 = wx1; h.gy1 = wy1; }
-    else { h.gx0 = x0; h.gy0 = y0; h.gx1 = x1; h.gy1 = y1; }
+    // the tile grid covers the ROI in every mode: for image output everything outside it is background, which render_fill_kernel
+    // streams out (enumerating the window's other ~350 tiles per hypothesis just to skip them cost 65 us per call)
+    h.gx0 = x0; h.gy0 = y0; h.gx1 = x1; h.gy1 = y1;
     h.tiles_x = (h.gx1 - h.gx0 + TILE_W - 1) / TILE_W;
     h.tiles_y = (h.gy1 - h.gy0 + TILE_H - 1) / TILE_H;
     h.tile_base = 0;

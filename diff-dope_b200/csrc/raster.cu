@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) bin_kernel(SceneDev S, const H
     if (t >= S.T) return;
     float c0[4], c1[4], c2[4];
     int X[3], Y[3], xmin, xmax, ymin, ymax, pxmin, pxmax, pymin, pymax;
-    if (!tri_clip_snap_bbox(S, s_mvp, s_reg[4], t, s_reg[0], s_reg[1], s_reg[2], s_reg[3], c0, c1, c2, X, Y, xmin, xmax, ymin, ymax, pxmin, pxmax, pymin, pymax))
+    if (tri_clip_snap_bbox(S, s_mvp, s_reg[4], t, s_reg[0], s_reg[1], s_reg[2], s_reg[3], c0, c1, c2, X, Y, xmin, xmax, ymin, ymax, pxmin, pxmax, pymin, pymax) == 0)
         return;
     // tile tx needs ids of x in [gx0 + 32 tx - 2, gx0 + 32 tx + 33]
     const int gx0 = s_reg[5], gy0 = s_reg[6], tiles_x = s_reg[7], tiles_y = s_reg[8], base = s_reg[9];

@@ -60,6 +60,35 @@ __device__ __forceinline__ void depth_test_write(const float* c0, const float* c
     zwrite(((unsigned long long)float_orderable(zw) << 32) | (unsigned int)tri, px, py);
 }
 
+// Triangles that cross the camera plane (a vertex with w <= 0) or whose window coordinates leave the fixed-point range cannot be
+// snapped; GL / nvdiffrast clip them against the frustum. Here they are rasterised WITHOUT clipping, in homogeneous coordinates
+// (Olano & Greer): the fragment formula's edge functions a0, a1, a2 at the pixel centre decide coverage -- inside iff none of them
+// has the opposite sign of their sum -- and the fragment must lie in front of the camera (interpolated w > 0) between the near and
+// far planes (z/w in [-1, 1], which is what clipping against the near plane achieves). Same arithmetic as oracle/nvdr.py.
+template <class ZW>
+__device__ __forceinline__ void depth_test_write_homog(const float* c0, const float* c1, const float* c2, int tri, int face, int px, int py, float xs,
+                                                       float xo, float ys, float yo, const ZW& zwrite) {
+    const float fx = xadd(xmul(xs, (float)px), xo);
+    const float fy = xadd(xmul(ys, (float)py), yo);
+    const float p0x = xsub(c0[0], xmul(fx, c0[3])), p0y = xsub(c0[1], xmul(fy, c0[3]));
+    const float p1x = xsub(c1[0], xmul(fx, c1[3])), p1y = xsub(c1[1], xmul(fy, c1[3]));
+    const float p2x = xsub(c2[0], xmul(fx, c2[3])), p2y = xsub(c2[1], xmul(fy, c2[3]));
+    const float a0 = xsub(xmul(p1x, p2y), xmul(p1y, p2x));
+    const float a1 = xsub(xmul(p2x, p0y), xmul(p2y, p0x));
+    const float a2 = xsub(xmul(p0x, p1y), xmul(p0y, p1x));
+    const float sum = xadd(xadd(a0, a1), a2);
+    const bool pos = sum > 0.f && a0 >= 0.f && a1 >= 0.f && a2 >= 0.f;
+    const bool neg = sum < 0.f && a0 <= 0.f && a1 <= 0.f && a2 <= 0.f;
+    if (!(pos || neg)) return;  // outside, degenerate, or NaN
+    if (face != 0 && (pos != (face > 0))) return;  // back face of a closed mesh
+    const float z = xadd(xadd(xmul(c0[2], a0), xmul(c1[2], a1)), xmul(c2[2], a2));
+    const float w = xadd(xadd(xmul(c0[3], a0), xmul(c1[3], a1)), xmul(c2[3], a2));
+    if (!((w > 0.f) == pos) || w == 0.f) return;  // interpolated w = w / sum must be positive: in front of the camera
+    const float zw = xdiv(z, w);
+    if (!(zw >= -1.f && zw <= 1.f)) return;
+    zwrite(((unsigned long long)float_orderable(zw) << 32) | (unsigned int)tri, px, py);
+}
+
 __device__ __forceinline__ bool edge_inside64(int ax, int ay, int bx, int by, int px, int py) {
     const long long dx = (long long)bx - ax, dy = (long long)by - ay;
     const long long e = dx * ((long long)py - ay) - dy * ((long long)px - ax);
@@ -77,12 +106,53 @@ __device__ __forceinline__ void edge_setup32(int ax, int ay, int bx, int by, int
     b = dx * SUBPIX;
 }
 
+// Conservative pixel bounding box of the part of a triangle in front of the near plane (z + w >= 0, w > 0): its vertices there plus
+// the points where its edges cross the plane, projected, grown by 2 px, clipped to the region. Plain float math (only has to contain
+// every pixel the homogeneous coverage test can accept); anything not finite gives the whole region.
+__device__ __forceinline__ bool homog_bbox(const SceneDev& S, const float* c0, const float* c1, const float* c2, int rx0, int rx1, int ry0, int ry1,
+                                           int& pxmin, int& pxmax, int& pymin, int& pymax) {
+    const float* c[3] = {c0, c1, c2};
+    const float hw = 0.5f * (float)S.W, hh = 0.5f * (float)S.H;
+    float mnx = 3e38f, mny = 3e38f, mxx = -3e38f, mxy = -3e38f;
+    bool any = false, bad = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float* a = c[i];
+        const float* b = c[(i + 1) % 3];
+        const float da = a[2] + a[3], db = b[2] + b[3];
+        if (da > 0.f && a[3] > 0.f) {
+            const float sx = a[0] / a[3] * hw + hw, sy = a[1] / a[3] * hh + hh;
+            if (!(fabsf(sx) < 1e9f && fabsf(sy) < 1e9f)) bad = true;
+            mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx); mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
+            any = true;
+        }
+        if ((da > 0.f) != (db > 0.f)) {
+            const float t = da / (da - db);
+            const float x = a[0] + t * (b[0] - a[0]), y = a[1] + t * (b[1] - a[1]), w = a[3] + t * (b[3] - a[3]);
+            if (w > 0.f) {
+                const float sx = x / w * hw + hw, sy = y / w * hh + hh;
+                if (!(fabsf(sx) < 1e9f && fabsf(sy) < 1e9f)) bad = true;
+                mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx); mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
+                any = true;
+            } else {
+                bad = true;
+            }
+        }
+    }
+    if (!any) return false;  // nothing of it in front of the near plane
+    if (bad || !(mnx <= mxx) || !(mny <= mxy)) { pxmin = rx0; pxmax = rx1; pymin = ry0; pymax = ry1; return rx0 <= rx1 && ry0 <= ry1; }
+    pxmin = max((int)floorf(fmaxf(mnx, -1e9f)) - 3, rx0); pxmax = min((int)ceilf(fminf(mxx, 1e9f)) + 2, rx1);
+    pymin = max((int)floorf(fmaxf(mny, -1e9f)) - 3, ry0); pymax = min((int)ceilf(fminf(mxy, 1e9f)) + 2, ry1);
+    return pxmin <= pxmax && pymin <= pymax;
+}
+
 // Clip transform, snap to 1/256 px, degenerate / back-face rejection, pixel bounding box clipped to [rx0,rx1] x [ry0,ry1] (inclusive).
-// Returns false if nothing of the triangle can be visible there. X/Y: snapped window coordinates, orientation-normalised
-// (v1 <-> v2 swapped when the area is negative: coverage only); c0..c2: clip vertices in mesh order.
-__device__ __forceinline__ bool tri_clip_snap_bbox(const SceneDev& S, const float* mvp, int face, int t, int rx0, int rx1, int ry0, int ry1,
-                                                   float* c0, float* c1, float* c2, int* X, int* Y, int& xmin, int& xmax, int& ymin, int& ymax,
-                                                   int& pxmin, int& pxmax, int& pymin, int& pymax) {
+// Returns 0 if nothing of the triangle can be visible there, 1 for an ordinary triangle (X/Y: snapped window coordinates,
+// orientation-normalised -- v1 <-> v2 swapped when the area is negative: coverage only), 2 for a triangle that has to be rasterised in
+// homogeneous coordinates (a vertex behind the camera plane or outside the fixed-point range; X/Y unused). c0..c2: clip vertices in mesh order.
+__device__ __forceinline__ int tri_clip_snap_bbox(const SceneDev& S, const float* mvp, int face, int t, int rx0, int rx1, int ry0, int ry1,
+                                                  float* c0, float* c1, float* c2, int* X, int* Y, int& xmin, int& xmax, int& ymin, int& ymax,
+                                                  int& pxmin, int& pxmax, int& pymin, int& pymax) {
     const float4 v0 = S.tripos[4 * (size_t)t], v1 = S.tripos[4 * (size_t)t + 1], v2 = S.tripos[4 * (size_t)t + 2];
     xfm_exact(mvp, v0.x, v0.y, v0.z, c0);
     xfm_exact(mvp, v1.x, v1.y, v1.z, c1);
@@ -94,13 +164,16 @@ __device__ __forceinline__ bool tri_clip_snap_bbox(const SceneDev& S, const floa
     const bool ok = (c0[3] > 0.f) && (c1[3] > 0.f) && (c2[3] > 0.f) && (fabsf(sx0) < COORD_LIMIT) &&
                     (fabsf(sy0) < COORD_LIMIT) && (fabsf(sx1) < COORD_LIMIT) && (fabsf(sy1) < COORD_LIMIT) &&
                     (fabsf(sx2) < COORD_LIMIT) && (fabsf(sy2) < COORD_LIMIT);  // NaN fails
-    if (!ok) return false;
+    if (!ok) {
+        if (!(c0[3] > 0.f || c1[3] > 0.f || c2[3] > 0.f)) return 0;  // entirely behind the camera plane (or NaN)
+        return homog_bbox(S, c0, c1, c2, rx0, rx1, ry0, ry1, pxmin, pxmax, pymin, pymax) ? 2 : 0;
+    }
     X[0] = __float2int_rn(xmul(sx0, (float)SUBPIX)); Y[0] = __float2int_rn(xmul(sy0, (float)SUBPIX));
     X[1] = __float2int_rn(xmul(sx1, (float)SUBPIX)); Y[1] = __float2int_rn(xmul(sy1, (float)SUBPIX));
     X[2] = __float2int_rn(xmul(sx2, (float)SUBPIX)); Y[2] = __float2int_rn(xmul(sy2, (float)SUBPIX));
     const long long area2 = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(Y[1] - Y[0]) * (X[2] - X[0]);
     // back faces of a closed mesh cannot be the front-most surface: skipped (raster rule)
-    if (area2 == 0 || (face != 0 && ((area2 > 0) != (face > 0)))) return false;
+    if (area2 == 0 || (face != 0 && ((area2 > 0) != (face > 0)))) return 0;
     if (area2 < 0) {  // orientation-normalise (coverage only): swap v1 <-> v2
         int tmp = X[1]; X[1] = X[2]; X[2] = tmp;
         tmp = Y[1]; Y[1] = Y[2]; Y[2] = tmp;
@@ -111,7 +184,7 @@ __device__ __forceinline__ bool tri_clip_snap_bbox(const SceneDev& S, const floa
     pxmax = min((xmax - SUBPIX / 2) >> 8, rx1);
     pymin = max((ymin - SUBPIX / 2 + SUBPIX - 1) >> 8, ry0);
     pymax = min((ymax - SUBPIX / 2) >> 8, ry1);
-    return pxmin <= pxmax && pymin <= pymax;
+    return (pxmin <= pxmax && pymin <= pymax) ? 1 : 0;
 }
 
 // One chunk of up to NT triangles (thread i: triangle t, or t < 0 for none) rasterised by the CTA into `zwrite` over the pixel
@@ -135,17 +208,19 @@ __device__ __forceinline__ void cta_raster_chunk(const SceneDev& S, const float*
     TriRec* my = reinterpret_cast<TriRec*>(s_rec + threadIdx.x * REC_WORDS);
     int npx = 0;  // candidates of a small triangle
     int nrows = 0;
-    bool large = false;
-    int X[3], Y[3];
+    bool large = false, homog = false;
+    int X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
     int lxmin = 0, lxmax = -1, lymin = 0, lymax = -1;
     if (t >= 0) {
         float c0[4], c1[4], c2[4];
-        int xmin, xmax, ymin, ymax, pxmin, pxmax, pymin, pymax;
-        if (tri_clip_snap_bbox(S, s_mvp, face, t, rx0, rx1, ry0, ry1, c0, c1, c2, X, Y, xmin, xmax, ymin, ymax, pxmin, pxmax, pymin, pymax)) {
+        int xmin = 0, xmax = 0, ymin = 0, ymax = 0, pxmin, pxmax, pymin, pymax;
+        const int code = tri_clip_snap_bbox(S, s_mvp, face, t, rx0, rx1, ry0, ry1, c0, c1, c2, X, Y, xmin, xmax, ymin, ymax, pxmin, pxmax, pymin, pymax);
+        if (code != 0) {
 #pragma unroll
             for (int k = 0; k < 4; k++) { my->c0[k] = c0[k]; my->c1[k] = c1[k]; my->c2[k] = c2[k]; }
             my->tri = t;
-            if (xmax - xmin <= SMALL_EXTENT && ymax - ymin <= SMALL_EXTENT) {
+            homog = code == 2;
+            if (!homog && xmax - xmin <= SMALL_EXTENT && ymax - ymin <= SMALL_EXTENT) {
                 const int ox = pxmin * SUBPIX + SUBPIX / 2, oy = pymin * SUBPIX + SUBPIX / 2;
                 edge_setup32(X[0], Y[0], X[1], Y[1], ox, oy, my->k0, my->a0, my->b0);
                 edge_setup32(X[1], Y[1], X[2], Y[2], ox, oy, my->k1, my->a1, my->b1);
@@ -253,7 +328,7 @@ __device__ __forceinline__ void cta_raster_chunk(const SceneDev& S, const float*
         TriRec* dst = reinterpret_cast<TriRec*>(s_rec + slot * REC_WORDS);
         *dst = keep;
         dst->k0 = X[0]; dst->a0 = Y[0]; dst->b0 = X[1]; dst->k1 = Y[1]; dst->a1 = X[2]; dst->b1 = Y[2];
-        dst->k2 = lxmax; dst->a2 = lymax; dst->b2 = 0;
+        dst->k2 = lxmax; dst->a2 = lymax; dst->b2 = homog ? 1 : 0;
         dst->pxmin = lxmin; dst->pymin = lymin; dst->bw = lxmax - lxmin + 1;
     }
     __syncthreads();
@@ -266,9 +341,12 @@ __device__ __forceinline__ void cta_raster_chunk(const SceneDev& S, const float*
             const int row = j / bw, col = j - row * bw;
             const int px = r->pxmin + col, py = r->pymin + row;
             const int sx = px * SUBPIX + SUBPIX / 2, sy = py * SUBPIX + SUBPIX / 2;
-            if (edge_inside64(ax, ay, bx, by, sx, sy) && edge_inside64(bx, by, cx, cy, sx, sy) &&
-                edge_inside64(cx, cy, ax, ay, sx, sy))
+            if (r->b2) {  // homogeneous rasterisation (crosses the camera plane / outside the fixed-point range)
+                depth_test_write_homog(r->c0, r->c1, r->c2, r->tri, face, px, py, xs, xo, ys, yo, zwrite);
+            } else if (edge_inside64(ax, ay, bx, by, sx, sy) && edge_inside64(bx, by, cx, cy, sx, sy) &&
+                       edge_inside64(cx, cy, ax, ay, sx, sy)) {
                 depth_test_write(r->c0, r->c1, r->c2, r->tri, px, py, xs, xo, ys, yo, zwrite);
+            }
         }
     }
     __syncthreads();

@@ -249,6 +249,61 @@ def face_signs(cull_sign, proj, M, bbmin=None, bbmax=None):
     return face
 
 
+def _rasterize_homogeneous(clipb, tri, t, H, W, face):
+    """Fragments of ONE triangle that cannot be snapped -- a vertex behind the camera plane (w <= 0) or outside the fixed-point
+    range -- by homogeneous rasterisation (no clipping; the raster rule): at every pixel centre of a
+    conservative bounding box the fragment formula's edge functions decide coverage (inside iff none has the opposite sign of
+    their sum), the interpolated w must be positive (in front of the camera) and z/w in [-1, 1] (between near and far: what
+    clipping against the near plane achieves in GL / nvdiffrast). Same float32 arithmetic as csrc/raster_common.cuh."""
+    c = [clipb[tri[t, k]].astype(F) for k in range(3)]
+    hw, hh = F(0.5) * F(W), F(0.5) * F(H)
+    pts = []
+    bad = False
+    with np.errstate(all="ignore"):
+        for i in range(3):
+            a, b_ = c[i], c[(i + 1) % 3]
+            da, db = a[2] + a[3], b_[2] + b_[3]
+            if da > 0 and a[3] > 0:
+                pts.append((a[0] / a[3] * hw + hw, a[1] / a[3] * hh + hh))
+            if (da > 0) != (db > 0):
+                tt = da / (da - db)
+                x, y, w = a[0] + tt * (b_[0] - a[0]), a[1] + tt * (b_[1] - a[1]), a[3] + tt * (b_[3] - a[3])
+                if w > 0:
+                    pts.append((x / w * hw + hw, y / w * hh + hh))
+                else:
+                    bad = True
+    if not pts:
+        return None
+    P = np.array(pts, dtype=np.float64)
+    if bad or not np.all(np.isfinite(P)) or np.abs(P).max() >= 1e9:
+        x0, x1, y0, y1 = 0, W - 1, 0, H - 1
+    else:
+        x0, x1 = max(int(np.floor(P[:, 0].min())) - 3, 0), min(int(np.ceil(P[:, 0].max())) + 2, W - 1)
+        y0, y1 = max(int(np.floor(P[:, 1].min())) - 3, 0), min(int(np.ceil(P[:, 1].max())) + 2, H - 1)
+    if x0 > x1 or y0 > y1:
+        return None
+    cpy, cpx = np.mgrid[y0:y1 + 1, x0:x1 + 1]
+    cpx, cpy = cpx.reshape(-1), cpy.reshape(-1)
+    fx, fy = pixel_ndc(cpx, cpy, W, H)
+    c0, c1, c2 = (np.broadcast_to(v, (cpx.size, 4)) for v in c)
+    with np.errstate(all="ignore"):
+        a0, a1, a2, _ = shader_terms(c0, c1, c2, fx, fy)
+        sm = (a0 + a1) + a2
+        pos = (sm > 0) & (a0 >= 0) & (a1 >= 0) & (a2 >= 0)
+        neg = (sm < 0) & (a0 <= 0) & (a1 <= 0) & (a2 <= 0)
+        ins = pos | neg
+        if face != 0:
+            ins &= pos == (face > 0)
+        z = (c0[:, 2] * a0 + c1[:, 2] * a1) + c2[:, 2] * a2
+        w = (c0[:, 3] * a0 + c1[:, 3] * a1) + c2[:, 3] * a2
+        ins &= ((w > 0) == pos) & (w != 0)
+        zw = z / w
+        ins &= (zw >= F(-1.0)) & (zw <= F(1.0))
+    if not ins.any():
+        return None
+    return (cpx[ins], cpy[ins], np.full(int(ins.sum()), t, dtype=np.int64), zw[ins].astype(F), a0[ins], a1[ins], a2[ins])
+
+
 def rasterize(clip, tri, H, W, face_sign=None):
     """Restates `dr.rasterize(glctx, pos_clip, tri, [H,W])` (`diffdope/diffdope.py:198-200`).
 
@@ -256,6 +311,9 @@ def rasterize(clip, tri, H, W, face_sign=None):
     are back faces of a closed mesh and are skipped. They can never be the front-most surface, so coverage is
     unchanged; the winner can differ from a no-culling rasteriser only where a back and a front face tie in depth
     within float rounding on a silhouette (the raster rule).
+
+    Triangles with a vertex behind the camera plane (w <= 0) or outside the fixed-point range are not dropped (GL / nvdiffrast clip
+    them): see `_rasterize_homogeneous`. Triangles entirely behind the camera plane are.
 
     clip [B,V,4] float32, tri [T,3] int. Returns rast_out [B,H,W,4] float32 =
     (u, v, z/w, tri_id+1), all-zero at background. The pixel-derivative output
@@ -284,33 +342,44 @@ def rasterize(clip, tri, H, W, face_sign=None):
         pymax = np.minimum((ymax - half) >> 8, H - 1)
         tri_ok &= (pxmin <= pxmax) & (pymin <= pymax)
         ids = np.nonzero(tri_ok)[0]
-        if ids.size == 0:
+        cand = []  # (cpx, cpy, ct, zw, a0, a1, a2) of every fragment that passed coverage and the depth range
+        if ids.size > 0:
+            nx = (pxmax - pxmin + 1)[ids]
+            ny = (pymax - pymin + 1)[ids]
+            # candidate (triangle, pixel) pairs: enumerate the bbox of every triangle
+            counts = nx * ny
+            total = int(counts.sum())
+            rep = np.repeat(np.arange(ids.size), counts)
+            offs = np.arange(total) - np.repeat(np.cumsum(counts) - counts, counts)
+            cpx = pxmin[ids][rep] + offs % nx[rep]
+            cpy = pymin[ids][rep] + offs // nx[rep]
+            ct = ids[rep]
+            evc = tuple(e[ct] for e in ev)
+            ins = _inside(evc, cpx * SUBPIX + half, cpy * SUBPIX + half)
+            cpx, cpy, ct = cpx[ins], cpy[ins], ct[ins]
+            if ct.size > 0:
+                c0, c1, c2 = clip[b][tri[ct, 0]], clip[b][tri[ct, 1]], clip[b][tri[ct, 2]]
+                fx, fy = pixel_ndc(cpx, cpy, W, H)
+                with np.errstate(all="ignore"):
+                    a0, a1, a2, _ = shader_terms(c0, c1, c2, fx, fy)
+                    z = (c0[:, 2] * a0 + c1[:, 2] * a1) + c2[:, 2] * a2
+                    w = (c0[:, 3] * a0 + c1[:, 3] * a1) + c2[:, 3] * a2
+                    zw = z / w
+                    keep = (zw >= F(-1.0)) & (zw <= F(1.0))  # NaN fails both
+                cand.append((cpx[keep], cpy[keep], ct[keep], zw[keep], a0[keep], a1[keep], a2[keep]))
+        # triangles that cross the camera plane (a vertex with w <= 0) or leave the fixed-point range: homogeneous rasterisation
+        wv = clip[b][:, 3]
+        all_ok = ok[tri[:, 0]] & ok[tri[:, 1]] & ok[tri[:, 2]]
+        some_front = (wv[tri[:, 0]] > 0) | (wv[tri[:, 1]] > 0) | (wv[tri[:, 2]] > 0)
+        for t in np.nonzero(~all_ok & some_front)[0]:
+            c = _rasterize_homogeneous(clip[b], tri, int(t), H, W, 0 if face_sign is None else int(face_sign[b]))
+            if c is not None:
+                cand.append(c)
+        if not cand:
             continue
-        nx = (pxmax - pxmin + 1)[ids]
-        ny = (pymax - pymin + 1)[ids]
-        # candidate (triangle, pixel) pairs: enumerate the bbox of every triangle
-        counts = nx * ny
-        total = int(counts.sum())
-        rep = np.repeat(np.arange(ids.size), counts)
-        offs = np.arange(total) - np.repeat(np.cumsum(counts) - counts, counts)
-        cpx = pxmin[ids][rep] + offs % nx[rep]
-        cpy = pymin[ids][rep] + offs // nx[rep]
-        ct = ids[rep]
-        evc = tuple(e[ct] for e in ev)
-        ins = _inside(evc, cpx * SUBPIX + half, cpy * SUBPIX + half)
-        cpx, cpy, ct = cpx[ins], cpy[ins], ct[ins]
+        cpx, cpy, ct, zw, a0, a1, a2 = (np.concatenate([c[k] for c in cand]) for k in range(7))
         if ct.size == 0:
             continue
-        c0, c1, c2 = clip[b][tri[ct, 0]], clip[b][tri[ct, 1]], clip[b][tri[ct, 2]]
-        fx, fy = pixel_ndc(cpx, cpy, W, H)
-        with np.errstate(all="ignore"):
-            a0, a1, a2, _ = shader_terms(c0, c1, c2, fx, fy)
-            z = (c0[:, 2] * a0 + c1[:, 2] * a1) + c2[:, 2] * a2
-            w = (c0[:, 3] * a0 + c1[:, 3] * a1) + c2[:, 3] * a2
-            zw = z / w
-            keep = (zw >= F(-1.0)) & (zw <= F(1.0))  # NaN fails both
-        cpx, cpy, ct, zw = cpx[keep], cpy[keep], ct[keep], zw[keep]
-        a0, a1, a2 = a0[keep], a1[keep], a2[keep]
         key = (_float_key(zw).astype(np.uint64) << np.uint64(32)) | ct.astype(np.uint64)
         pix = cpy * W + cpx
         zbuf = np.full(H * W, EMPTY_KEY, dtype=np.uint64)

@@ -240,6 +240,57 @@ def test_untextured_large_triangles(big):
     assert np.abs(go - grad.cpu().numpy()).max() <= 1e-4 * np.abs(go).max()
 
 
+def test_triangles_crossing_the_camera_plane_match_oracle():
+    """Near-plane handling: triangles with vertices behind the camera plane (w <= 0) are rasterised in homogeneous coordinates
+    instead of being dropped (GL / nvdiffrast clip them). A ground plane passing under the camera, a slanted
+    triangle with one vertex behind, one entirely behind, and a cube the camera sits inside of: ids / barycentrics / z/w bit-equal
+    to the oracle, losses and gradients 1e-4, in both rasterisation modes."""
+    from oracle import refpath
+
+    n = _nat()
+    v = np.array([[-2.0, -0.3, 1.0], [2.0, -0.3, 1.0], [2.0, -0.3, -6.0], [-2.0, -0.3, -6.0],
+                  [0.3, 0.5, -2.0], [0.9, 0.1, -1.5], [0.5, 0.9, 0.7],
+                  [-1.0, 0.2, 0.5], [-0.5, 0.3, 2.0], [-0.8, 0.9, 1.0]], dtype=np.float32)
+    f = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [7, 8, 9]], dtype=np.int32)
+    col = np.random.default_rng(5).random((10, 3)).astype(np.float32)
+    H, W = 96, 128
+    P = refpath.projection_matrix(90.0, 95.0, W / 2 - 3.3, H / 2 + 1.7, W, H)
+    rng = np.random.default_rng(1)
+    gt = dict(rgb=rng.random((H, W, 3)).astype(np.float32), depth=(1 + 3 * rng.random((H, W))).astype(np.float32),
+              segmentation=np.repeat((rng.random((H, W, 1)) > 0.4).astype(np.float32), 3, axis=2))
+    qs = np.array([[0.0, 0.0, 0.0, 1.0], [0.05, -0.08, 0.03, 0.99]], dtype=np.float32)
+    ts = np.array([[0.02, -0.03, 0.0], [-0.05, 0.04, 0.1]], dtype=np.float32)
+    lr = np.array([1.0, 2.0], dtype=np.float32)
+    cube_v = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], dtype=np.float32) * 0.9
+    cube_f = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]], dtype=np.int32)
+    cube_col = np.random.default_rng(3).random((8, 3)).astype(np.float32)
+    cube_q = np.array([[0.3, 0.2, 0.1, 0.9], [0.0, 0.7, 0.1, 0.6]], dtype=np.float32)
+    cube_t = np.array([[0.2, 0.1, -0.6], [-0.1, 0.2, 0.3]], dtype=np.float32)  # the camera is inside the cube: every face crosses the camera plane or is behind it
+    for vv, ff, cc, q, t in ((v, f, col, qs, ts), (cube_v, cube_f, cube_col, cube_q, cube_t)):
+        sc = n.NativeScene(vv, ff, vtx_color=cc)
+        sc.set_camera(P, H, W)
+        g = {k: torch.from_numpy(x).cuda() for k, x in gt.items()}
+        sc.set_target(g["rgb"], g["depth"], g["segmentation"])
+        mesh = refpath.Mesh(vv, ff, vtx_color=cc)
+        r = refpath.render(mesh, P, torch.from_numpy(q), torch.from_numpy(t), H, W)
+        out = sc.render(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda())
+        ro = r["rast_out"].numpy()
+        assert (ro[..., 3] > 0).sum() > 2000
+        assert np.array_equal(ro, out["rast"].cpu().numpy())
+        assert np.array_equal(r["rgb"].numpy(), out["rgb"].cpu().numpy()) and np.array_equal(r["depth"].numpy(), out["depth"].cpu().numpy())
+        assert np.abs(r["mask"].numpy()[..., 0] - out["mask"].cpu().numpy()).max() <= 2e-7
+        logged, gq, gtr, _ = refpath.forward_backward(mesh, P, q, t, {k: torch.from_numpy(x) for k, x in gt.items()}, lr, ALL, H, W)
+        go = np.concatenate([gq, gtr], 1)
+        res = []
+        for mode in ("zbuffer", "binned"):
+            sc.set_raster_mode(mode)
+            loss, grad = sc.loss_grad(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), torch.from_numpy(lr).cuda(), _cfg(n, ALL))
+            assert np.allclose(loss.cpu().numpy(), _loss_table(logged, 2), rtol=1e-4)
+            assert np.abs(go - grad.cpu().numpy()).max() <= 1e-4 * np.abs(go).max()
+            res.append((loss, grad))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
 def test_edge_cases_empty_coverage_and_errors():
     n, sc, mesh, P, gt, H, W = _cube_scene()
     g = {k: torch.from_numpy(v).cuda() for k, v in gt.items()}

@@ -512,6 +512,46 @@ def test_oracle_matches_ray_casting():
     assert np.abs(r["rgb"][0].numpy()[interior] - want[interior]).max() < 3e-5
 
 
+def test_triangles_crossing_the_camera_plane_match_ray_casting():
+    """Near-plane handling (GL / nvdiffrast clip; the oracle rasterises such triangles in homogeneous coordinates, DESIGN.md
+    section 4): a ground plane under the camera whose far end is in view and whose near end lies BEHIND the camera plane (two of
+    its four vertices have w < 0), and a slanted triangle with one vertex behind. Winner, barycentrics and depth against float64
+    ray casting; nothing appears above the horizon or behind the camera; a triangle entirely behind is dropped."""
+    v = np.array([[-2.0, -0.3, 1.0], [2.0, -0.3, 1.0], [2.0, -0.3, -6.0], [-2.0, -0.3, -6.0],
+                  [0.3, 0.5, -2.0], [0.9, 0.1, -1.5], [0.5, 0.9, 0.7],
+                  [-1.0, 0.2, 0.5], [-0.5, 0.3, 2.0], [-0.8, 0.9, 1.0]], dtype=np.float32)
+    f = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [7, 8, 9]], dtype=np.int32)
+    col = np.random.default_rng(5).random((10, 3)).astype(np.float32)
+    mesh = refpath.Mesh(v, f, vtx_color=col)
+    assert mesh.cull_sign == 0
+    H, W = 72, 96
+    P = refpath.projection_matrix(70.0, 75.0, 47.3, 37.1, W, H)
+    for q in ([0.0, 0.0, 0.0, 1.0], [0.05, -0.08, 0.03, 0.99]):
+        q = np.array([q], dtype=np.float32)
+        t = np.array([[0.02, -0.03, 0.0]], dtype=np.float32)
+        r = refpath.render(mesh, P, torch.from_numpy(q), torch.from_numpy(t), H, W)
+        M = r["mtx"][0].numpy().astype(np.float64)
+        pos_cam = v.astype(np.float64) @ M[:3, :3].T + M[:3, 3]
+        assert (pos_cam[f[0], 2] > 0).sum() == 2 and (pos_cam[f[2], 2] > 0).sum() == 1 and (pos_cam[f[3], 2] > 0).all()
+        ids, uv, depth = _raycast(pos_cam, f, P, H, W)
+        rast = r["rast_out"][0].numpy()
+        oid = rast[..., 3].astype(np.int64) - 1
+        assert (oid == 0).sum() + (oid == 1).sum() > 1000 and (oid == 2).sum() > 50, "the crossing triangles are rendered, not dropped"
+        assert not (oid == 3).any(), "a triangle entirely behind the camera plane is dropped"
+        interior = np.ones_like(ids, bool)
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                interior &= np.roll(np.roll(ids, dy, 0), dx, 1) == ids
+        interior[[0, -1], :] = False
+        interior[:, [0, -1]] = False
+        cov = interior & (ids >= 0)
+        assert cov.sum() > 900
+        assert np.array_equal(oid[interior], ids[interior]), "same winner (and same background) away from edges"
+        assert np.abs(rast[..., 0][cov] - uv[..., 0][cov]).max() < 1e-4 and np.abs(rast[..., 1][cov] - uv[..., 1][cov]).max() < 1e-4
+        assert np.abs(r["depth"][0].numpy()[cov] - depth[cov]).max() < 1e-4 * depth[cov].max()
+        assert ((oid >= 0) != (ids >= 0)).sum() <= 0.03 * (ids >= 0).sum()
+
+
 def test_oracle_coverage_matches_opencv_polygon_fill():
     """Silhouette of the example mesh against OpenCV's polygon rasteriser fed with the same 1/256 px fixed-point
     vertices (an independent implementation with a different fill rule: boundary pixels may differ)."""
