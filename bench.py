@@ -138,6 +138,15 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def count(self):
+        """samples written so far (nvidia-smi takes a second or more to start: the caller keeps the load up until enough exist)"""
+        try:
+            self.f.flush()
+            with open(self.path) as f:
+                return sum(1 for line in f if line.count(",") >= 8)
+        except Exception:
+            return 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
@@ -513,7 +522,9 @@ def run_ours(args):
     kms, klaunch = sc.profile_end()
     n_prof = max(klaunch["pixel_kernel"], 1)  # = iterations
     t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.3:  # keep the GPU under the same load long enough for the 20 ms clock sampler (>= 10 samples)
+    # keep the GPU under the same load until the 20 ms clock sampler has delivered >= 10 samples (nvidia-smi needs a second or more
+    # to start on a fresh box; bounded at 10 s)
+    while time.perf_counter() - t_load < 0.3 or (sampler is not None and sampler.proc is not None and sampler.count() < 10 and time.perf_counter() - t_load < 10.0):
         qd4, td4 = fresh_pose()
         sc.optimize(qd4, td4, lr, sched, cfg, b_global=B_global, keep_history=False)
         torch.cuda.synchronize()

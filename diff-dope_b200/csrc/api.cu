@@ -550,7 +550,7 @@ static int ensure_buffers(ddope_scene* s, int B, bool need_partials, cudaStream_
         s->zbuf_cap = zneed;
     }
     if (need_partials) {
-        size_t tiles = (size_t)((d.ww + TILE_W - 1) / TILE_W) * ((d.wh + TILE_H - 1) / TILE_H);
+        size_t tiles = (size_t)((d.ww + TILE_W - 1) / TILE_W) * ((d.wh + TILE_H_MIN - 1) / TILE_H_MIN);
         size_t pneed = (size_t)B * tiles * NACC;
         if (pneed > s->partials_cap) {
             if (s->partials) CK(cudaFree(s->partials));
@@ -572,7 +572,7 @@ static int ensure_buffers(ddope_scene* s, int B, bool need_partials, cudaStream_
 
 static int max_tiles(const ddope_scene* s, int B) {
     const SceneDev& d = s->dev;
-    long long t = (long long)((d.ww + TILE_W - 1) / TILE_W) * ((d.wh + TILE_H - 1) / TILE_H) * B;
+    long long t = (long long)((d.ww + TILE_W - 1) / TILE_W) * ((d.wh + TILE_H_MIN - 1) / TILE_H_MIN) * B;
     return t > 0x7fffffffLL ? 0x7fffffff : (int)t;
 }
 
@@ -781,7 +781,7 @@ struct Part {
 
 static size_t tiles_per_hyp(const ddope_scene* s) {
     const SceneDev& d = s->dev;
-    return (size_t)((d.ww + TILE_W - 1) / TILE_W) * ((d.wh + TILE_H - 1) / TILE_H);
+    return (size_t)((d.ww + TILE_W - 1) / TILE_W) * ((d.wh + TILE_H_MIN - 1) / TILE_H_MIN);
 }
 
 // Split B hypotheses into parts and fork the internal streams from the caller's stream.
@@ -862,7 +862,7 @@ static void enqueue_iteration(ddope_scene* s, const Part& P, float* quat, float*
     const bool binned = P.bins.count != nullptr;
     {
         ProfMark m(s, P.st, K_RASTER);
-        if (binned) launch_bin(s->dev, cur, P.B, P.bins.count, const_cast<int*>(P.bins.ids), P.bins.cap, P.st);
+        if (binned) launch_bin(s->dev, cur, P.B, P.bins.count, const_cast<int*>(P.bins.ids), P.bins.cap, tile_h_of(cfg.use_edge != 0), P.st);
         else launch_raster(s->dev, cur, P.B, P.zbuf, P.multi, P.st);
     }
     {

@@ -5,9 +5,26 @@
 
 namespace ddope {
 
+// One work item of the pixel pass is a tile of 32 x TILE_H pixels handled by a CTA of TILE_H / 4 warps: one warp per row, 4 rows
+// (pixels) per thread. The tile height is a compile-time property of the kernel variant: 16 rows (4 warps) for the plain loss /
+// image passes -- smaller barrier domains, more independent CTAs per SM, measured 7-9 % faster than 32 rows -- and 32 rows (8 warps)
+// with the edge loss, whose 2 px grey halo ring is shaded redundantly per tile (a 16-row tile shades 41 % extra pixels, a 32-row
+// tile 27 %; measured 20 % slower at 16). Everything that lays tiles out (pose / iter kernels, bins, buffer sizes) gets the
+// height from tile_h_of(cfg.use_edge).
+#ifndef DDOPE_TILE_H
+#define DDOPE_TILE_H 16
+#endif
+#ifndef DDOPE_TILE_H_EDGE
+#define DDOPE_TILE_H_EDGE 32
+#endif
 constexpr int TILE_W = 32;
-constexpr int TILE_H = 32;        // one work item of the pixel pass: 32x32 px, 4 px per thread
-constexpr int TILE_THREADS = 256;
+constexpr int TILE_REPS = 4;  // pixels per thread: rows ly0 + warps * rep
+constexpr int TILE_H_PLAIN = DDOPE_TILE_H, TILE_H_EDGE = DDOPE_TILE_H_EDGE;
+constexpr int TILE_H_MIN = TILE_H_PLAIN < TILE_H_EDGE ? TILE_H_PLAIN : TILE_H_EDGE;
+__host__ __device__ constexpr int tile_h_of(bool edge) { return edge ? TILE_H_EDGE : TILE_H_PLAIN; }
+__host__ __device__ constexpr int tile_h_log2(int th) { return th == 32 ? 5 : (th == 16 ? 4 : (th == 8 ? 3 : -1)); }
+__host__ __device__ constexpr int tile_threads_of(bool edge) { return TILE_W * tile_h_of(edge) / TILE_REPS; }
+static_assert(tile_h_log2(TILE_H_PLAIN) > 0 && tile_h_log2(TILE_H_EDGE) > 0, "tile heights must be 8, 16 or 32");
 constexpr int NACC = 20;  // 12 dMVP(rows x,y,w) + 4 dM(row z) + 4 loss sums (rgb, depth, mask, edge)
 constexpr unsigned long long EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
 constexpr int SUBPIX = 256;

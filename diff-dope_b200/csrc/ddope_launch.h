@@ -57,7 +57,7 @@ void launch_copy_mtx(const HypState* hyp, int B, float* mtx, cudaStream_t st);
 // raster.cu
 void launch_clear(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, cudaStream_t st);
 void launch_raster(const SceneDev& S, const HypState* hyp, int B, unsigned long long* zbuf, MultiArgs multi, cudaStream_t st);
-void launch_bin(const SceneDev& S, const HypState* hyp, int B, int* bin_count, int* bin_ids, int bin_cap, cudaStream_t st);
+void launch_bin(const SceneDev& S, const HypState* hyp, int B, int* bin_count, int* bin_ids, int bin_cap, int tile_h, cudaStream_t st);
 
 // pixel.cu
 struct RenderOut {

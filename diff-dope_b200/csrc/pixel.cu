@@ -11,8 +11,8 @@
 
 namespace ddope {
 
-constexpr int IDS_W = TILE_W + 4, IDS_H = TILE_H + 4;  // triangle ids: tile + 2 px halo
-constexpr int MAA_W = TILE_W + 2, MAA_H = TILE_H + 2;  // antialiased mask: tile + 1 px halo
+constexpr int IDS_W = TILE_W + 4;  // triangle ids: tile + 2 px halo (rows: TILE_H + 4, per kernel variant)
+constexpr int MAA_W = TILE_W + 2;  // antialiased mask: tile + 1 px halo
 constexpr int ID_NONE = -1;                             // inside the frame, not covered
 constexpr int ID_OUTSIDE = -2;                          // outside the frame: no pixel, no pair
 
@@ -403,24 +403,38 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int 
         : "memory");
 }
 
-constexpr int BIN_CHUNK = TILE_THREADS;  // triangles rasterised per step by a tile CTA of the binned path
+#ifndef PIXEL_PREFETCH
+#define PIXEL_PREFETCH 1
+#endif
+#ifndef PIXEL_PIPE_FETCH
+#define PIXEL_PIPE_FETCH 1
+#endif
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 
 constexpr int MODE_RENDER = 0;  // write rgb / depth / mask / rast images (ddope_render*)
 constexpr int MODE_LOSS = 1;    // fused reference losses + backward (ddope_loss_grad / ddope_optimize)
 constexpr int MODE_EXT = 2;     // backward of externally supplied image gradients (ddope_render_bwd)
 
-constexpr int NPAIR = IDS_W * IDS_H;  // pair slots per direction, indexed by the pair's first pixel
 constexpr int DI_NONE = 3;            // no pair here / analysis found no usable edge
 
 constexpr int GRAY_W = TILE_W + 4;  // grey image of the render: tile + 2 px halo (edge loss)
 constexpr int DG_W = TILE_W + 2;    // dL/d(Gx,Gy): tile + 1 px halo
 
 template <int MODE, bool EDGE, bool MIP, bool BINNED, bool MULTI>
-__global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED : (EDGE ? PIXEL_MIN_BLOCKS_EDGE : PIXEL_MIN_BLOCKS)) pixel_kernel(SceneDev Sp, const HypState* __restrict__ hyp,
+__global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS_EDGE : (BINNED ? PIXEL_MIN_BLOCKS_BINNED : PIXEL_MIN_BLOCKS)) pixel_kernel(SceneDev Sp, const HypState* __restrict__ hyp,
                                                              const int* __restrict__ total_tiles, int B,
                                                              LossCfgDev cfg,
                                                              const unsigned long long* __restrict__ zbuf,
                                                              float* __restrict__ partials, RenderOut out, ExtGrad ext, BinArgs bins, MultiArgs multi) {
+    // tile geometry of this variant (ddope_common.cuh)
+    constexpr int TILE_H = tile_h_of(EDGE), TILE_THREADS = tile_threads_of(EDGE), TILE_WARPS = TILE_THREADS / 32;
+    constexpr int IDS_H = TILE_H + 4, MAA_H = TILE_H + 2;
+    constexpr int NPAIR = IDS_W * IDS_H;      // pair slots per direction, indexed by the pair's first pixel
+    constexpr int GRAY_H = TILE_H + 4, DG_H = TILE_H + 2;
+    constexpr int BIN_CHUNK = TILE_THREADS;   // triangles rasterised per step by a tile CTA of the binned path
+    static_assert(TILE_WARPS * TILE_REPS == TILE_H && TILE_WARPS >= 2, "one warp per row, 4 rows per thread, warp 1 exists");
     // multi-object call: the SceneDev of the object the current tile's hypothesis belongs to, copied from the scene table
     __shared__ __align__(16) unsigned int s_scene[MULTI ? sizeof(SceneDev) / 4 : 4];
     const SceneDev& S = MULTI ? *reinterpret_cast<const SceneDev*>(s_scene) : Sp;
@@ -442,19 +456,18 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
     __shared__ float s_m2[4];
     __shared__ float s_red[TILE_THREADS / 32][NACC];
     __shared__ unsigned long long s_cov[IDS_H], s_inf[IDS_H];
-    __shared__ int s_b, s_nq;
-    __shared__ float s_gray[EDGE ? GRAY_W * GRAY_W : 1];
-    __shared__ float s_dgx[EDGE ? DG_W * DG_W : 1], s_dgy[EDGE ? DG_W * DG_W : 1];
+    __shared__ int s_nq;
+    __shared__ float s_gray[EDGE ? GRAY_W * GRAY_H : 1];
+    __shared__ float s_dgx[EDGE ? DG_W * DG_H : 1], s_dgy[EDGE ? DG_W * DG_H : 1];
 
     pdl_trigger();
-    bool waited = true;
     pdl_wait();  // z-buffer (or bins) of the preceding launch
     const int total = *total_tiles;
     const int tid = threadIdx.x;
     // pixel centre -> NDC: fx = xs*px + xo (nvdiffrast's xs = 2/W, xo = 1/W - 1), hoisted out of the pixel loop
     // (a multi-object call shares camera, frame and window between its scenes, checked by the API: the leader's values serve all)
     const float ndc_xs = Sp.ndc_xs, ndc_xo = Sp.ndc_xo, ndc_ys = Sp.ndc_ys, ndc_yo = Sp.ndc_yo;
-    const int lx = tid % TILE_W, ly0 = tid / TILE_W;  // this thread's pixels: (lx, ly0 + 8k), k = 0..3
+    const int lx = tid % TILE_W, ly0 = tid / TILE_W;  // this thread's pixels: (lx, ly0 + TILE_WARPS * k), k = 0..3
     unsigned int mbar_use[2] = {0u, 0u};  // completed phases of the two TMA barriers (uniform across the CTA)
     if (BINNED) {
         if (tid == 0) {
@@ -466,26 +479,47 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
         __syncthreads();
     }
 
-#if DYN_TILES
-    // work items are handed out by an atomic counter: tiles differ a lot in cost (silhouette tiles,
-    // fully covered tiles, target-only tiles), static striding left ~10 % of the SMs idle at the end
+    // Work items are handed out by an atomic counter: tiles differ a lot in cost (silhouette tiles, fully covered tiles,
+    // target-only tiles), static striding left ~10 % of the SMs idle at the end. The fetch costs no barrier of its own: lane 0 of
+    // warp 1 draws the NEXT item at the top of an iteration; after the phase-1 barrier (every thread has read the current item by
+    // then) warp 1 locates its hypothesis and overwrites (s_item, s_bsel); the barrier that ends the iteration publishes them.
     int* work_counter = const_cast<int*>(total_tiles) + 1;  // reset to 0 by whichever kernel wrote total_tiles
-    __shared__ int s_item;
+    __shared__ int s_item, s_bsel;
+    // the hypothesis owning work item `it` (one load per participating thread instead of a serial search); threads first, first + step, ...
+    auto locate = [&](int it, int first, int step) {
+        if (it >= total) return;
+        for (int bb = first; bb < B; bb += step) {
+            const int base = hyp[bb].tile_base;
+            if (it >= base && it < base + hyp[bb].tiles_x * hyp[bb].tiles_y) s_bsel = bb;
+        }
+    };
+    // warp 1 only (nx: the drawn item, valid in its lane 0)
+    auto publish_next = [&](int nx) {
+        nx = __shfl_sync(0xffffffffu, nx, 0);
+        if (tid == 32) s_item = nx;
+        locate(nx, tid - 32, 32);
+    };
+#if PIXEL_PIPE_FETCH
+    if (tid == 0) s_item = atomicAdd(work_counter, 1);
+    __syncthreads();
+    locate(s_item, tid, TILE_THREADS);
+    __syncthreads();
+    for (;;) {
+        const int item = s_item;
+        if (item >= total) break;
+        const int b = s_bsel;
+        int next_item = 0;
+        if (tid == 32) next_item = atomicAdd(work_counter, 1);  // consumed after the phase-1 barrier
+#else
     for (;;) {
         if (tid == 0) s_item = atomicAdd(work_counter, 1);
         __syncthreads();
         const int item = s_item;
         if (item >= total) break;
-#else
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-#endif
-        // locate the hypothesis owning this work item (one load per thread instead of a serial search)
-        for (int bb = tid; bb < B; bb += TILE_THREADS) {
-            const int base = hyp[bb].tile_base;
-            if (item >= base && item < base + hyp[bb].tiles_x * hyp[bb].tiles_y) s_b = bb;
-        }
+        locate(item, tid, TILE_THREADS);
         __syncthreads();
-        const int b = s_b;
+        const int b = s_bsel;
+#endif
         const HypState& h = hyp[b];
         if (MULTI) {
             const int obj = h.obj;  // CTA-uniform
@@ -515,12 +549,12 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
             // concurrent with pose_kernel + raster_kernel); only tiles that can contain the object are visited here
             const bool bg = rx1 <= rx0 || ox - 2 >= vx1 || ox + TILE_W + 2 <= vx0 || oy - 2 >= vy1 || oy + TILE_H + 2 <= vy0;
             if (bg) {  // CTA-uniform: render_fill_kernel has written these pixels
-                __syncthreads();  // s_b / s_item are rewritten at the top of the loop
+                __syncthreads();  // every thread has read (s_item, s_bsel)
+#if PIXEL_PIPE_FETCH
+                if (tid >= 32 && tid < 64) publish_next(next_item);
+                __syncthreads();
+#endif
                 continue;
-            }
-            if (!waited) {
-                pdl_wait();
-                waited = true;
             }
         }
 
@@ -577,15 +611,15 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
 
         // 1. triangle ids of tile + 2 px halo, one warp per row (row loads coalesce; all of a warp's
         //    z-buffer loads are issued before any is consumed), plus per-row coverage / in-frame bitmasks
-        bool tile_cov = false;
+        bool tile_cov = false, tile_unc = false;  // this warp's rows: any covered pixel / any uncovered pixel inside the frame
         {
             const int lane = tid & 31, warp = tid >> 5;
-            constexpr int ROWS_PER_WARP = (IDS_H + 7) / 8;
+            constexpr int ROWS_PER_WARP = (IDS_H + TILE_WARPS - 1) / TILE_WARPS;
             int idr[ROWS_PER_WARP][2];
             const unsigned int vw = (unsigned int)(vx1 - vx0);
 #pragma unroll
             for (int k = 0; k < ROWS_PER_WARP; k++) {
-                const int iy = warp + 8 * k;
+                const int iy = warp + TILE_WARPS * k;
                 const int y = oy - 2 + iy;
                 // row tests are warp-uniform; the column tests use one unsigned compare per range
                 const bool row_in = iy < IDS_H && (unsigned int)y < (unsigned int)S.H;
@@ -609,7 +643,7 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
             // (binned path: s_u.z is not touched again; s_alpha, the same storage, is first written in phase 3, two barriers from here)
 #pragma unroll
             for (int k = 0; k < ROWS_PER_WARP; k++) {
-                const int iy = warp + 8 * k;
+                const int iy = warp + TILE_WARPS * k;
                 if (iy >= IDS_H) break;  // warp-uniform
                 const unsigned int c0 = __ballot_sync(0xffffffffu, idr[k][0] >= 0);
                 const unsigned int c1 = __ballot_sync(0xffffffffu, idr[k][1] >= 0);
@@ -622,18 +656,53 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
                     s_inf[iy] = ((unsigned long long)f1 << 32) | f0;
                 }
                 tile_cov |= (c0 | c1) != 0u;
+                tile_unc |= ((f0 & ~c0) | (f1 & ~c1)) != 0u;
+            }
+        }
+        // The barrier that publishes the ids. Image output also learns whether anything of the object is in the tile or its halo.
+        // The 8-warp (edge loss) variant learns whether the tile holds covered AND uncovered pixels, i.e. whether it can have
+        // silhouette pairs at all, and skips phase 2 and its barrier otherwise: lane 0 of each warp votes "covered" (weight 1), lanes
+        // 1 .. TILE_WARPS+1 vote "uncovered" (weight TILE_WARPS+1 per warp), both counts come out of the barrier's population count.
+        // (Measured: +4 % on the stress workload with 8 warps per CTA, -1 % with 4 warps, where phase 2 is cheap to wait for.)
+        constexpr bool UNIFORM_SKIP = EDGE;
+        bool any_cov = true, mixed = true;
+        if (UNIFORM_SKIP) {
+            constexpr int VOTE_W = TILE_WARPS + 1;
+            const int lane_v = tid & 31;
+            const int votes = __syncthreads_count((lane_v == 0 && tile_cov) || (lane_v >= 1 && lane_v <= VOTE_W && tile_unc));
+            any_cov = (votes % VOTE_W) != 0;
+            mixed = any_cov && (votes / VOTE_W) != 0;
+        } else if (MODE == MODE_RENDER) {
+            any_cov = __syncthreads_or(tile_cov ? 1 : 0) != 0;
+        } else {
+            __syncthreads();
+        }
+#if PIXEL_PIPE_FETCH
+        if (tid >= 32 && tid < 64) publish_next(next_item);  // warp 1: the next work item and its hypothesis
+#endif
+        // the edge-loss variant: the triangle records of this thread's four pixels -> L1 while the pair phases (2-4) and the grey halo
+        // ring run (the record gather is the longest dependent load of the shading pass; the plain variants prefetch one pixel ahead
+        // inside phase 5 instead, measured equal to this there)
+        if ((EDGE || PIXEL_PREFETCH == 2) && (MODE != MODE_RENDER || any_cov)) {
+#pragma unroll
+            for (int rep = 0; rep < TILE_REPS; rep++) {
+                const int idp = s_ids[(ly0 + TILE_WARPS * rep + 2) * IDS_W + (lx + 2)];
+                if (idp >= 0) prefetch_l1(S.tripos + 4 * (size_t)idp);
             }
         }
         if (MODE == MODE_RENDER) {
             // image output: nothing of the object in this tile or its halo -> background, already written by render_fill_kernel
-            if (!__syncthreads_or(tile_cov ? 1 : 0)) continue;  // (the barrier also orders s_b / s_item against the next item)
-        } else {
-            __syncthreads();
+            if (!any_cov) {
+                __syncthreads();
+                continue;
+            }
         }
 
         // 2. silhouette pairs (exactly one pixel covered, both in the frame, at least one within the
         //    1 px halo) -> queue, from the row bitmasks. Equal-coverage pairs blend alpha*(1-1) or
         //    alpha*(0-0) = 0 and are skipped. One warp; the queue order is fixed (row-major, H then V).
+        int nq = 0;  // 0 for interior and background tiles: their mask is the plain coverage
+        if (mixed) {
         if (tid < 32) {
             constexpr unsigned long long HMASK = (1ull << (IDS_W - 1)) - 1;           // first pixel ix in [0, W-2]
             constexpr unsigned long long VMASK = ((1ull << (IDS_W - 1)) - 1) & ~1ull;  // ix in [1, W-2]
@@ -676,7 +745,8 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
             if (tid == 31) s_nq = incl;
         }
         __syncthreads();
-        const int nq = s_nq;  // 0 for interior and background tiles: their mask is the plain coverage
+        nq = s_nq;
+        }
 
         if (nq > 0) {
         static_assert((2 * NPAIR) % 4 == 0, "s_di is cleared as 32-bit words");
@@ -743,9 +813,9 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
             //       d grey / d(u,v). Spare iterations shade the 272 pixels of the 2 px halo ring for their grey value only.
             //   E2  Sobel magnitude of the render, the edge loss against the precomputed target edges, dL/d(Gx, Gy)
             //   B   backward: dL/d(u,v) += dL/d grey * d grey/d(u,v), barycentric setup again (no texture fetch), dL/dMVP.
-            float st_gu[TILE_H / 8], st_gv[TILE_H / 8], st_G0[TILE_H / 8], st_G1[TILE_H / 8];
+            float st_gu[TILE_REPS], st_gv[TILE_REPS], st_G0[TILE_REPS], st_G1[TILE_REPS];
             const int wx1 = S.wx0 + S.ww, wy1 = S.wy0 + S.wh;
-            for (int i = tid; i < GRAY_W * GRAY_W - TILE_W * TILE_H; i += TILE_THREADS) {  // halo ring: rows 0,1 | rows 34,35 | columns 0,1,34,35
+            for (int i = tid; i < GRAY_W * GRAY_H - TILE_W * TILE_H; i += TILE_THREADS) {  // halo ring: rows 0,1 | the two rows above the tile | columns 0,1,34,35
                 int ix, iy;
                 if (i < 2 * GRAY_W) { iy = i / GRAY_W; ix = i - iy * GRAY_W; }
                 else if (i < 4 * GRAY_W) { const int j = i - 2 * GRAY_W; iy = j / GRAY_W; ix = j - iy * GRAY_W; iy += TILE_H + 2; }
@@ -763,8 +833,8 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
                 s_gray[iy * GRAY_W + ix] = gray;
             }
 #pragma unroll
-            for (int rep = 0; rep < TILE_H / 8; rep++) {  // A
-                const int ly = ly0 + 8 * rep;
+            for (int rep = 0; rep < TILE_REPS; rep++) {  // A
+                const int ly = ly0 + TILE_WARPS * rep;
                 const int x = ox + lx, y = oy + ly;
                 st_gu[rep] = st_gv[rep] = st_G0[rep] = st_G1[rep] = 0.f;
                 float gray = 0.f;
@@ -842,7 +912,7 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
             __syncthreads();
             // E2. Sobel magnitude of the render, the edge loss against the precomputed target edges and
             //     dL/d(Gx, Gy) over tile + 1 px halo
-            for (int i = tid; i < DG_W * DG_W; i += TILE_THREADS) {
+            for (int i = tid; i < DG_W * DG_H; i += TILE_THREADS) {
                 const int ix = i % DG_W, iy = i / DG_W;
                 const int x = ox - 1 + ix, y = oy - 1 + iy;
                 float dgx = 0.f, dgy = 0.f;
@@ -868,8 +938,8 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
             }
             __syncthreads();
 #pragma unroll
-            for (int rep = 0; rep < TILE_H / 8; rep++) {  // B
-                const int ly = ly0 + 8 * rep;
+            for (int rep = 0; rep < TILE_REPS; rep++) {  // B
+                const int ly = ly0 + TILE_WARPS * rep;
                 const int x = ox + lx, y = oy + ly;
                 if (!(x < gx1 && y < gy1)) continue;
                 const int id = s_ids[(ly + 2) * IDS_W + (lx + 2)];
@@ -888,12 +958,26 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
                 }
             }
         } else {
-        // 5. shading, losses and their backward, 4 pixels per thread
-        for (int rep = 0; rep < TILE_H / 8; rep++) {
-            const int ly = ly0 + 8 * rep;
+        // 5. shading, losses and their backward, 4 pixels per thread. The triangle record of the thread's next pixel is
+        //    prefetched into L1 while the current one is shaded (the record gather is the longest dependent load of the pass).
+#if PIXEL_PREFETCH == 1
+        int id_next = s_ids[(ly0 + 2) * IDS_W + (lx + 2)];
+        if (id_next >= 0) prefetch_l1(S.tripos + 4 * (size_t)id_next);
+#endif
+        for (int rep = 0; rep < TILE_REPS; rep++) {
+            const int ly = ly0 + TILE_WARPS * rep;
             const int x = ox + lx, y = oy + ly;
+#if PIXEL_PREFETCH == 1
+            const int id = id_next;
+            if (rep + 1 < TILE_REPS) {
+                id_next = s_ids[(ly + TILE_WARPS + 2) * IDS_W + (lx + 2)];
+                if (id_next >= 0) prefetch_l1(S.tripos + 4 * (size_t)id_next);
+            }
+            if (!(x < gx1 && y < gy1)) continue;
+#else
             if (!(x < gx1 && y < gy1)) continue;
             const int id = s_ids[(ly + 2) * IDS_W + (lx + 2)];
+#endif
             const float maa = (nq > 0) ? s_maa[(ly + 1) * MAA_W + (lx + 1)] : ((id >= 0) ? 1.f : 0.f);
             const size_t gpix = (size_t)y * S.W + x;
             const size_t wp = ((size_t)b * S.wh + (y - S.wy0)) * S.ww + (x - S.wx0);
@@ -1078,14 +1162,20 @@ __global__ void __launch_bounds__(TILE_THREADS, BINNED ? PIXEL_MIN_BLOCKS_BINNED
                 for (int w = 0; w < TILE_THREADS / 32; w++) v += s_red[w][tid];
                 partials[(size_t)item * NACC + tid] = v;
             }
+            // no barrier here: every shared buffer of this tile was last read before the barrier above, s_red is next written two
+            // barriers into the following tile
+#if !PIXEL_PIPE_FETCH
+            __syncthreads();
+#endif
+        } else {
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
 static int pixel_grid(int max_tiles, int num_sms, bool binned, bool edge) {
-    static const int per_sm = [] { const char* e = getenv("DDOPE_PIXEL_CTAS_PER_SM"); int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 0; }();
-    int g = num_sms * (per_sm ? per_sm : (binned ? PIXEL_MIN_BLOCKS_BINNED : (edge ? PIXEL_MIN_BLOCKS_EDGE : PIXEL_MIN_BLOCKS)));
+    static const int per_sm = [] { const char* e = getenv("DDOPE_PIXEL_CTAS_PER_SM"); int v = e ? atoi(e) : 0; return v >= 1 && v <= 16 ? v : 0; }();
+    int g = num_sms * (per_sm ? per_sm : (edge ? PIXEL_MIN_BLOCKS_EDGE : (binned ? PIXEL_MIN_BLOCKS_BINNED : PIXEL_MIN_BLOCKS)));
     if (g > max_tiles) g = max_tiles;
     return g < 1 ? 1 : g;
 }
@@ -1094,6 +1184,7 @@ template <int MODE, bool EDGE, bool MIP, bool BINNED, bool MULTI = false>
 static void launch_pixel_inst(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int grid, LossCfgDev cfg,
                               const unsigned long long* zbuf, float* partials, RenderOut out, ExtGrad ext, BinArgs bins, cudaStream_t st,
                               MultiArgs multi = {nullptr, nullptr, 0, 0}) {
+    constexpr int TILE_THREADS = tile_threads_of(EDGE), BIN_CHUNK = TILE_THREADS;
     size_t dyn = 0;
     if (BINNED) {
         dyn = sizeof(int) * BIN_CHUNK * REC_WORDS;

@@ -89,7 +89,7 @@ __device__ __forceinline__ bool roi_corner(const SceneDev& S, const float* mvp, 
 // roi_mode 1 (losses): ROI = (screen bbox of the AABB corners, grown) U (bbox of seg != 0), clipped to the window; the tile grid covers it.
 // roi_mode 0 (external image gradients): ROI = tile grid = the whole window.
 // roi_mode 2 (image output): ROI = tile grid = screen bbox of the object only (the rest of the window is filled as background).
-__device__ void hyp_roi_part(const SceneDev& S, bool full, float mnx, float mny, float mxx, float mxy, int roi_mode, HypState& h) {
+__device__ void hyp_roi_part(const SceneDev& S, bool full, float mnx, float mny, float mxx, float mxy, int roi_mode, int tile_h, HypState& h) {
     const int wx0 = S.wx0, wy0 = S.wy0, wx1 = S.wx0 + S.ww, wy1 = S.wy0 + S.wh;  // window, exclusive end
     int x0 = wx0, y0 = wy0, x1 = wx1, y1 = wy1;
     if (roi_mode != 0 && !full) {
@@ -111,7 +111,7 @@ __device__ void hyp_roi_part(const SceneDev& S, bool full, float mnx, float mny,
     // streams out (enumerating the window's other ~350 tiles per hypothesis just to skip them cost 65 us per call)
     h.gx0 = x0; h.gy0 = y0; h.gx1 = x1; h.gy1 = y1;
     h.tiles_x = (h.gx1 - h.gx0 + TILE_W - 1) / TILE_W;
-    h.tiles_y = (h.gy1 - h.gy0 + TILE_H - 1) / TILE_H;
+    h.tiles_y = (h.gy1 - h.gy0 + tile_h - 1) / tile_h;  // tile_h_of(cfg.use_edge): the height the pixel pass variant of this call works with
     h.tile_base = 0;
 }
 
@@ -137,7 +137,7 @@ __device__ void hyp_from_pose(const SceneDev& S, const float* qb, const float* t
             mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
         }
     }
-    hyp_roi_part(S, full, mnx, mny, mxx, mxy, roi_mode, h);
+    hyp_roi_part(S, full, mnx, mny, mxx, mxy, roi_mode, tile_h_of(cfg.use_edge != 0), h);
     hyp_scales(S, lr_b, B_global, cfg, h);
 }
 
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(ITER_THREADS) iter_kernel(SceneDev Sp, const H
             mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
             mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
         }
-        if (lane == 0) hyp_roi_part(S, full, mnx, mny, mxx, mxy, 1, s_n);
+        if (lane == 0) hyp_roi_part(S, full, mnx, mny, mxx, mxy, 1, tile_h_of(cfg.use_edge != 0), s_n);
     }
     __syncthreads();
     {

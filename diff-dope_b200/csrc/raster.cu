@@ -81,7 +81,7 @@ void launch_raster(const SceneDev& S, const HypState* hyp, int B, unsigned long 
 // work-item index (tile_base + ty * tiles_x + tx); a full bin keeps counting, and its tile CTA then falls back to scanning
 // the whole mesh. The append order is arbitrary; the depth test that consumes the bins is order-independent.
 __global__ void __launch_bounds__(RASTER_THREADS) bin_kernel(SceneDev S, const HypState* __restrict__ hyp, int* __restrict__ bin_count,
-                                                             int* __restrict__ bin_ids, int bin_cap) {
+                                                             int* __restrict__ bin_ids, int bin_cap, int th_log2) {
     pdl_trigger();
     pdl_wait();
     const int b = blockIdx.y;
@@ -106,10 +106,10 @@ __global__ void __launch_bounds__(RASTER_THREADS) bin_kernel(SceneDev S, const H
     int X[3], Y[3], xmin, xmax, ymin, ymax, pxmin, pxmax, pymin, pymax;
     if (tri_clip_snap_bbox(S, s_mvp, s_reg[4], t, s_reg[0], s_reg[1], s_reg[2], s_reg[3], c0, c1, c2, X, Y, xmin, xmax, ymin, ymax, pxmin, pxmax, pymin, pymax) == 0)
         return;
-    // tile tx needs ids of x in [gx0 + 32 tx - 2, gx0 + 32 tx + 33]
+    // tile tx needs ids of x in [gx0 + 32 tx - 2, gx0 + 32 tx + 33], tile ty of y in [gy0 + H ty - 2, gy0 + H ty + H + 1] (H = the tile height of the call's pixel pass)
     const int gx0 = s_reg[5], gy0 = s_reg[6], tiles_x = s_reg[7], tiles_y = s_reg[8], base = s_reg[9];
     const int tx0 = max((pxmin - 2 - gx0) >> 5, 0), tx1 = min((pxmax + 2 - gx0) >> 5, tiles_x - 1);
-    const int ty0 = max((pymin - 2 - gy0) >> 5, 0), ty1 = min((pymax + 2 - gy0) >> 5, tiles_y - 1);
+    const int ty0 = max((pymin - 2 - gy0) >> th_log2, 0), ty1 = min((pymax + 2 - gy0) >> th_log2, tiles_y - 1);
     for (int ty = ty0; ty <= ty1; ty++)
         for (int tx = tx0; tx <= tx1; tx++) {
             const int tile = base + ty * tiles_x + tx;
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(RASTER_THREADS) bin_kernel(SceneDev S, const H
         }
 }
 
-void launch_bin(const SceneDev& S, const HypState* hyp, int B, int* bin_count, int* bin_ids, int bin_cap, cudaStream_t st) {
-    launch_kernel(pdl_enabled(), bin_kernel, dim3((S.T + RASTER_THREADS - 1) / RASTER_THREADS, B), dim3(RASTER_THREADS), 0, st, S, hyp, bin_count, bin_ids, bin_cap);
+void launch_bin(const SceneDev& S, const HypState* hyp, int B, int* bin_count, int* bin_ids, int bin_cap, int tile_h, cudaStream_t st) {
+    launch_kernel(pdl_enabled(), bin_kernel, dim3((S.T + RASTER_THREADS - 1) / RASTER_THREADS, B), dim3(RASTER_THREADS), 0, st, S, hyp, bin_count, bin_ids, bin_cap, tile_h_log2(tile_h));
 }
 
 }  // namespace ddope
