@@ -626,25 +626,35 @@ static int render_common(ddope_scene* s, const float* quat, const float* trans, 
     if (int r = ensure_buffers(s, B, false, st)) return r;
     LossCfgDev cfg = {0, 0, 0, 0.f, 0.f, 0.f, 0, 0.f};
     RenderOut out = {rgb, depth, mask, rast};
-    // the background of every output image is streamed out on an internal stream while pose + raster run on the caller's; the
-    // pixel pass (tiles that can contain the object only) starts when both are done
+    // pose_kernel fixes every hypothesis's ROI; from there the background outside the ROIs is streamed out on one internal stream
+    // (render_fill_kernel) while the rasteriser and the pixel pass -- which writes every pixel inside the ROIs -- run on another, both
+    // forked from / joined into the caller's stream. The two sides touch disjoint pixels, so neither waits for the other; measured
+    // (event timeline) the rasteriser nevertheless makes little progress while the 524 MB store stream of the
+    // fill is in flight: the call costs what the three kernels cost back to back.
     if (!s->fork_event) CK(cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming));
-    if (!s->part_stream[1]) CK(cudaStreamCreateWithFlags(&s->part_stream[1], cudaStreamNonBlocking));
-    if (!s->part_done[1]) CK(cudaEventCreateWithFlags(&s->part_done[1], cudaEventDisableTiming));
+    for (int p = 0; p < 2; p++) {
+        if (!s->part_stream[p]) CK(cudaStreamCreateWithFlags(&s->part_stream[p], cudaStreamNonBlocking));
+        if (!s->part_done[p]) CK(cudaEventCreateWithFlags(&s->part_done[p], cudaEventDisableTiming));
+    }
+    cudaStream_t s0 = s->part_stream[0], s1 = s->part_stream[1];
     CK(cudaEventRecord(s->fork_event, st));
-    CK(cudaStreamWaitEvent(s->part_stream[1], s->fork_event, 0));
-    launch_render_fill(out, trans, mtx_in, B, s->dev.wh, s->dev.ww, s->num_sms, s->part_stream[1]);
-    CK(cudaEventRecord(s->part_done[1], s->part_stream[1]));
-    launch_pose(s->dev, quat, trans, mtx_in, nullptr, B, B, cfg, 2, s->hyp, s->total_tiles, st);
-    launch_raster(s->dev, s->hyp, B, s->zbuf, MultiArgs{nullptr, nullptr, 0, 0}, st);
-    CK(cudaStreamWaitEvent(st, s->part_done[1], 0));
-    launch_pixel_render(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), s->zbuf, out, s->num_sms, st);
-    launch_clear(s->dev, s->hyp, B, s->zbuf, st);  // restore the z-buffer invariant
+    CK(cudaStreamWaitEvent(s0, s->fork_event, 0));
+    launch_pose(s->dev, quat, trans, mtx_in, nullptr, B, B, cfg, 2, s->hyp, s->total_tiles, s0);
+    CK(cudaEventRecord(s->fork_event, s0));
+    CK(cudaStreamWaitEvent(s1, s->fork_event, 0));
+    launch_render_fill(out, s->hyp, B, s->dev.wy0, s->dev.wx0, s->dev.wh, s->dev.ww, s->num_sms, s1);
+    CK(cudaEventRecord(s->part_done[1], s1));
+    launch_raster(s->dev, s->hyp, B, s->zbuf, MultiArgs{nullptr, nullptr, 0, 0}, s0);
+    launch_pixel_render(s->dev, s->hyp, s->total_tiles, B, max_tiles(s, B), s->zbuf, out, s->num_sms, s0);
+    launch_clear(s->dev, s->hyp, B, s->zbuf, s0);  // restore the z-buffer invariant
     s->launches = 5;
     if (mtx) {
-        launch_copy_mtx(s->hyp, B, mtx, st);
+        launch_copy_mtx(s->hyp, B, mtx, s0);
         s->launches++;
     }
+    CK(cudaStreamWaitEvent(s0, s->part_done[1], 0));
+    CK(cudaEventRecord(s->part_done[0], s0));
+    CK(cudaStreamWaitEvent(st, s->part_done[0], 0));
     CK_LAUNCH(who);
     return 0;
 }
@@ -785,11 +795,14 @@ static size_t tiles_per_hyp(const ddope_scene* s) {
 }
 
 // Split B hypotheses into parts and fork the internal streams from the caller's stream.
-static int fork_parts(ddope_scene* s, int B, cudaStream_t st, Part* parts, int* n_parts) {
+static int fork_parts(ddope_scene* s, int B, int n_iters, cudaStream_t st, Part* parts, int* n_parts) {
     // measured on B200 (bench workload, us per iteration): B=16: 62 -> 52 (2 parts); B=32: 95 -> 80 (2); B=64: 158 -> 141 (2),
     // 136 (3), 138 (4); B=128: 296 -> 277 (2), 269 (4). DDOPE_PARTS overrides (1 = no split).
     static const int forced = [] { const char* e = getenv("DDOPE_PARTS"); return e ? atoi(e) : 0; }();
     int n = B < 8 ? 1 : (B < 48 ? 2 : (B < 96 ? 3 : 4));
+    // a single iteration has nothing to pipeline: the parts all rasterise and then all shade, in lock-step, and only pay the fork / join
+    // and three under-filled launches instead of one (measured, 64 hypotheses, L2 flushed before the call: 168 us as 3 parts, 159 us as 1)
+    if (n_iters <= 1) n = 1;
     if (forced > 0) n = forced;
     if (n > ddope_scene::MAX_PARTS) n = ddope_scene::MAX_PARTS;
     if (s->profiling || n < 1) n = 1;
@@ -896,7 +909,7 @@ extern "C" int ddope_loss_grad(ddope_scene* s, const float* quat, const float* t
     OptimDev opt = {0, 0.f, 0.f, 0.f, nullptr, 0.f, 0.f};
     Part parts[ddope_scene::MAX_PARTS];
     int n_parts = 1;
-    if (int r = fork_parts(s, B, st, parts, &n_parts)) return r;
+    if (int r = fork_parts(s, B, 1, st, parts, &n_parts)) return r;
     s->hyp_cur = 0;
     for (int p = 0; p < n_parts; p++) {
         enqueue_prologue(s, parts[p], const_cast<float*>(quat), const_cast<float*>(trans), lr_mult, B_global, to_dev(cfg), opt);
@@ -936,7 +949,7 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     s->launches = 0;
     Part parts[ddope_scene::MAX_PARTS];
     int n_parts = 1;
-    if (int r = fork_parts(s, B, st, parts, &n_parts)) return r;
+    if (int r = fork_parts(s, B, n_iters, st, parts, &n_parts)) return r;
 
     // Small batch: the host cannot enqueue ~5 us kernels as fast as the GPU finishes them (3.8 us per launch measured), so the
     // whole call is captured once and launched as a graph. Capture needs a real stream (the caller's may be the legacy default
@@ -1091,7 +1104,7 @@ extern "C" int ddope_optimize_multi(ddope_scene* const* scenes, int n_scenes, co
     s->launches = 0;
     Part parts[ddope_scene::MAX_PARTS];
     int n_parts = 1;
-    if (int r = fork_parts(s, B, st, parts, &n_parts)) return r;
+    if (int r = fork_parts(s, B, n_iters, st, parts, &n_parts)) return r;
     for (int p = 0; p < n_parts; p++) parts[p].multi = {s->multi_scenes, s->multi_meta + parts[p].b0, max_T, mip > 0 ? 1 : 0};
     s->hyp_cur = 0;
     for (int p = 0; p < n_parts; p++) enqueue_prologue(s, parts[p], quat, trans, lr_mult, B, c, opt);

@@ -85,7 +85,7 @@ void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_
 void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,
                          const unsigned long long* zbuf, RenderOut out, int num_sms, cudaStream_t st);
 
-void launch_render_fill(RenderOut out, const float* trans, const float* mtx, int B, int wh, int ww, int num_sms, cudaStream_t st);
+void launch_render_fill(RenderOut out, const HypState* hyp, int B, int wy0, int wx0, int wh, int ww, int num_sms, cudaStream_t st);
 void launch_attr_grad(const SceneDev& S, const HypState* hyp, int B, const unsigned long long* zbuf, const float* d_rgb, float* d_tex, float* d_vcol,
                       cudaStream_t st);
 void launch_tricol(const float* vcol, const int* tri, int T, float4* tricol, cudaStream_t st);

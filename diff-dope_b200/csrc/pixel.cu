@@ -543,20 +543,8 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
         const int vy0 = max(ry0 - 1, S.zy0), vy1 = min(ry1 + 1, S.zy0 + S.zh);
         const unsigned long long* zb = zbuf + (size_t)b * S.zh * S.zw;
 
-        if (MODE == MODE_RENDER) {
-            // image output: a tile whose ids region does not touch the object's ROI is pure background (rgb 0, depth -t_z, mask 0,
-            // rast 0): the whole output was pre-filled with that by render_fill_kernel (a streaming kernel on a second stream,
-            // concurrent with pose_kernel + raster_kernel); only tiles that can contain the object are visited here
-            const bool bg = rx1 <= rx0 || ox - 2 >= vx1 || ox + TILE_W + 2 <= vx0 || oy - 2 >= vy1 || oy + TILE_H + 2 <= vy0;
-            if (bg) {  // CTA-uniform: render_fill_kernel has written these pixels
-                __syncthreads();  // every thread has read (s_item, s_bsel)
-#if PIXEL_PIPE_FETCH
-                if (tid >= 32 && tid < 64) publish_next(next_item);
-                __syncthreads();
-#endif
-                continue;
-            }
-        }
+        // (image output: the tile grid is the object's ROI, whose every pixel this kernel writes, background included; everything
+        //  outside it is written by render_fill_kernel, concurrently)
 
         if (BINNED) {
             // 0. binned path: rasterise this tile's bin into the shared-memory z-buffer. The bin (triangle indices appended by
@@ -659,8 +647,7 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
                 tile_unc |= ((f0 & ~c0) | (f1 & ~c1)) != 0u;
             }
         }
-        // The barrier that publishes the ids. Image output also learns whether anything of the object is in the tile or its halo.
-        // The 8-warp (edge loss) variant learns whether the tile holds covered AND uncovered pixels, i.e. whether it can have
+        // The barrier that publishes the ids. The 8-warp (edge loss) variant learns whether the tile holds covered AND uncovered pixels, i.e. whether it can have
         // silhouette pairs at all, and skips phase 2 and its barrier otherwise: lane 0 of each warp votes "covered" (weight 1), lanes
         // 1 .. TILE_WARPS+1 vote "uncovered" (weight TILE_WARPS+1 per warp), both counts come out of the barrier's population count.
         // (Measured: +4 % on the stress workload with 8 warps per CTA, -1 % with 4 warps, where phase 2 is cheap to wait for.)
@@ -672,8 +659,6 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
             const int votes = __syncthreads_count((lane_v == 0 && tile_cov) || (lane_v >= 1 && lane_v <= VOTE_W && tile_unc));
             any_cov = (votes % VOTE_W) != 0;
             mixed = any_cov && (votes / VOTE_W) != 0;
-        } else if (MODE == MODE_RENDER) {
-            any_cov = __syncthreads_or(tile_cov ? 1 : 0) != 0;
         } else {
             __syncthreads();
         }
@@ -683,18 +668,11 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
         // the edge-loss variant: the triangle records of this thread's four pixels -> L1 while the pair phases (2-4) and the grey halo
         // ring run (the record gather is the longest dependent load of the shading pass; the plain variants prefetch one pixel ahead
         // inside phase 5 instead, measured equal to this there)
-        if ((EDGE || PIXEL_PREFETCH == 2) && (MODE != MODE_RENDER || any_cov)) {
+        if ((EDGE || PIXEL_PREFETCH == 2) && any_cov) {
 #pragma unroll
             for (int rep = 0; rep < TILE_REPS; rep++) {
                 const int idp = s_ids[(ly0 + TILE_WARPS * rep + 2) * IDS_W + (lx + 2)];
                 if (idp >= 0) prefetch_l1(S.tripos + 4 * (size_t)idp);
-            }
-        }
-        if (MODE == MODE_RENDER) {
-            // image output: nothing of the object in this tile or its halo -> background, already written by render_fill_kernel
-            if (!any_cov) {
-                __syncthreads();
-                continue;
             }
         }
 
@@ -1238,35 +1216,46 @@ void launch_pixel_loss(const SceneDev& S, const HypState* hyp, const int* total_
 
 // Background of the image outputs for all hypotheses: rgb 0, depth -t_z (interpolate yields 0 where nothing is covered, so the
 // depth transform leaves -t_z: diffdope/diffdope.py:203-209,228), mask 0, rast 0. Pure streaming stores, 16 bytes per thread and step.
-__global__ void __launch_bounds__(256) render_fill_kernel(RenderOut out, const float* __restrict__ trans, const float* __restrict__ mtx, int B,
-                                                          unsigned int px_per_hyp) {
+// The rectangle pixel_kernel<MODE_RENDER> writes itself -- the hypothesis's tile grid = its ROI [gx0,gx1) x [gy0,gy1) -- is left
+// alone, so the two kernels touch disjoint pixels and run concurrently (this one on an internal stream, after pose_kernel).
+__global__ void __launch_bounds__(256) render_fill_kernel(RenderOut out, const HypState* __restrict__ hyp, int B, int wy0, int wx0, int wh, int ww) {
+    const unsigned int px_per_hyp = (unsigned int)(wh * ww);
     const size_t n = (size_t)B * px_per_hyp;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((px_per_hyp & 3u) == 0) {
-        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n / 4; q += stride) {
-            const size_t wp = q * 4;
-            const int b = (int)(wp / px_per_hyp);
-            const float bgd = mtx ? -mtx[16 * b + 11] : -trans[3 * b + 2];
+    const bool vec = (ww & 3) == 0;  // a group of 4 pixels then never crosses a row (and every group is 16-byte aligned)
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < (vec ? n / 4 : n); q += stride) {
+        const size_t wp = vec ? q * 4 : q;
+        const int b = (int)(wp / px_per_hyp);
+        const unsigned int rem = (unsigned int)(wp - (size_t)b * px_per_hyp);
+        const int y = wy0 + (int)(rem / (unsigned int)ww), x = wx0 + (int)(rem % (unsigned int)ww);
+        const HypState& h = hyp[b];
+        const float bgd = -h.m[11];
+        const int gx0 = h.gx0, gx1 = h.gx1;
+        const bool row_in = y >= h.gy0 && y < h.gy1;
+        if (vec && !(row_in && x + 3 >= gx0 && x < gx1)) {  // the whole group is background
             if (out.rgb) { float4* p = reinterpret_cast<float4*>(out.rgb + wp * 3); p[0] = z4; p[1] = z4; p[2] = z4; }
             if (out.depth) *reinterpret_cast<float4*>(out.depth + wp) = make_float4(bgd, bgd, bgd, bgd);
             if (out.mask) *reinterpret_cast<float4*>(out.mask + wp) = z4;
             if (out.rast) { float4* p = reinterpret_cast<float4*>(out.rast) + wp; p[0] = z4; p[1] = z4; p[2] = z4; p[3] = z4; }
+            continue;
         }
-    } else {
-        for (size_t wp = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wp < n; wp += stride) {
-            const int b = (int)(wp / px_per_hyp);
-            const float bgd = mtx ? -mtx[16 * b + 11] : -trans[3 * b + 2];
-            if (out.rgb) { out.rgb[wp * 3] = 0.f; out.rgb[wp * 3 + 1] = 0.f; out.rgb[wp * 3 + 2] = 0.f; }
-            if (out.depth) out.depth[wp] = bgd;
-            if (out.mask) out.mask[wp] = 0.f;
-            if (out.rast) reinterpret_cast<float4*>(out.rast)[wp] = z4;
+        for (int k = 0; k < (vec ? 4 : 1); k++) {  // a group on the rectangle's border (or the scalar layout): pixel by pixel
+            if (row_in && x + k >= gx0 && x + k < gx1) continue;
+            const size_t w1 = wp + k;
+            if (out.rgb) { out.rgb[w1 * 3] = 0.f; out.rgb[w1 * 3 + 1] = 0.f; out.rgb[w1 * 3 + 2] = 0.f; }
+            if (out.depth) out.depth[w1] = bgd;
+            if (out.mask) out.mask[w1] = 0.f;
+            if (out.rast) reinterpret_cast<float4*>(out.rast)[w1] = z4;
         }
     }
 }
 
-void launch_render_fill(RenderOut out, const float* trans, const float* mtx, int B, int wh, int ww, int num_sms, cudaStream_t st) {
-    render_fill_kernel<<<num_sms * 8, 256, 0, st>>>(out, trans, mtx, B, (unsigned int)(wh * ww));
+void launch_render_fill(RenderOut out, const HypState* hyp, int B, int wy0, int wx0, int wh, int ww, int num_sms, cudaStream_t st) {
+    // few resident CTAs per SM: a grid-stride kernel keeps its thread slots for its whole duration, and the rasteriser and the pixel
+    // pass are meant to run beside it (DDOPE_FILL_CTAS overrides, for measurements)
+    static const int per_sm = [] { const char* e = getenv("DDOPE_FILL_CTAS"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 4; }();
+    render_fill_kernel<<<num_sms * per_sm, 256, 0, st>>>(out, hyp, B, wy0, wx0, wh, ww);
 }
 
 void launch_pixel_render(const SceneDev& S, const HypState* hyp, const int* total_tiles, int B, int max_tiles,

@@ -31,9 +31,12 @@ void launch_clear(const SceneDev& S, const HypState* hyp, int B, unsigned long l
 #define RASTER_THREADS_N 128
 #endif
 constexpr int RASTER_THREADS = RASTER_THREADS_N;
+#ifndef RASTER_MIN_BLOCKS
+#define RASTER_MIN_BLOCKS 1
+#endif
 
 template <bool MULTI>
-__global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(SceneDev Sp, const HypState* __restrict__ hyp,
+__global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_BLOCKS) raster_kernel(SceneDev Sp, const HypState* __restrict__ hyp,
                                                                 unsigned long long* __restrict__ zbuf, MultiArgs multi) {
     pdl_trigger();
     pdl_wait();  // hyp / z-buffer state of the preceding iter_kernel

@@ -551,6 +551,17 @@ class Object3D(torch.nn.Module):
             setattr(self, name, torch.nn.Parameter(torch.ones(batchsize) * float(v)))
         for name, v in zip(("x", "y", "z"), pos):
             setattr(self, name, torch.nn.Parameter(torch.ones(batchsize) * float(v)))
+        per_hyp = getattr(self, "_pose_b", None)
+        if per_hyp is not None:  # extension: per-hypothesis start poses survive set_batchsize / reset_pose
+            ps, qs = per_hyp
+            if len(ps) != batchsize:
+                raise ValueError("Object3D: %d per-hypothesis start poses were given (set_pose with [B,3] / [B,4] arrays) but the batch size is %d; "
+                                 "pass one pose, or as many as there are hypotheses" % (len(ps), batchsize))
+            with torch.no_grad():
+                for i, n in enumerate(("qx", "qy", "qz", "qw")):
+                    getattr(self, n).copy_(torch.tensor(qs[:, i], dtype=torch.float32))
+                for i, n in enumerate(("x", "y", "z")):
+                    getattr(self, n).copy_(torch.tensor(ps[:, i], dtype=torch.float32))
         self.to(device)
 
     def set_pose(self, position, rotation, batchsize=32, opencv2opengl=True, scale=1):
@@ -566,15 +577,17 @@ class Object3D(torch.nn.Module):
                     p, q = _opencv_2_opengl_np(p, q)
                 ps.append(p)
                 qs.append(q)
-            self._position, self._rotation = np.mean(ps, 0), _as_quat(np.mean(qs, 0))
+            ps, qs = np.array(ps, dtype=np.float64), np.array(qs, dtype=np.float64)
+            # the representative pose (repr, logging): mean position, sign-aligned normalised mean quaternion (q and -q are one rotation)
+            aligned = np.where((qs @ qs[0] < 0)[:, None], -qs, qs)
+            qm = aligned.mean(0)
+            qm = qm / np.linalg.norm(qm) if np.linalg.norm(qm) > 0 else qs[0]
+            self._position, self._rotation = ps.mean(0), _as_quat(qm)
+            self._pose_b = (ps, qs)
             device = "cpu" if self.qx is None else self.qx.device
             self._fill(len(ps), device)
-            with torch.no_grad():
-                for i, n in enumerate(("qx", "qy", "qz", "qw")):
-                    getattr(self, n).copy_(torch.tensor(np.array(qs)[:, i], dtype=torch.float32))
-                for i, n in enumerate(("x", "y", "z")):
-                    getattr(self, n).copy_(torch.tensor(np.array(ps)[:, i], dtype=torch.float32))
             return
+        self._pose_b = None
         assert len(position) == 3
         assert len(rotation) == 4 or len(rotation) == 3 or len(rotation) == 9
         rotation = rotation_to_quat(rotation)

@@ -3,7 +3,7 @@
 TAG=${1:-ab}
 mkdir -p gpurun_out
 for i in $(seq 1 ${ROUNDS:-2}); do
-for lib in default diff-dope_b200/diffdope/_lib/alt_*.so; do
+for lib in default $(ls diff-dope_b200/diffdope/_lib/alt_*.so 2>/dev/null); do
   if [ $lib = default ]; then n=default; unset DDOPE_B200_LIB; else n=$(basename $lib .so); export DDOPE_B200_LIB=$PWD/$lib; fi
   ITERS=50 TAG=$n timeout 300 python scripts/dev_kernels.py >> gpurun_out/${TAG}_kernels.log 2>&1
   ITERS=200 timeout 300 python scripts/dev_time.py 2>&1 | grep "ms/iter" | sed "s/^/$n /" >> gpurun_out/${TAG}_kernels.log

@@ -354,6 +354,36 @@ def test_mesh_and_object3d_follow_reference():
     assert len(list(o.parameters())) == 7
 
 
+def test_per_hypothesis_start_poses_survive_refills():
+    """Extension: set_pose with [B,3] / [B,4] arrays. The poses must survive set_batchsize / reset_pose (which refill the parameters),
+    a batch size they do not fit must fail loudly, and the representative quaternion of (q, -q) is q, not NaN."""
+    import diffdope as dd
+
+    o = dd.Object3D(su.POSITION, su.ROTATION, batchsize=2, scale=0.01)
+    q = np.array([0.1, 0.2, 0.3, 0.9]); q /= np.linalg.norm(q)
+    qs = np.stack([q, -q, q])
+    ps = np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0], [7.0, 8.0, 9.0]])
+    o.set_pose(ps, qs, opencv2opengl=False)
+    def rows():
+        qq, tt = o.pose_tensors()
+        return qq.numpy(), tt.numpy()
+    qq, tt = rows()
+    assert qq.shape == (3, 4) and np.allclose(qq, qs, atol=1e-7) and np.allclose(tt, ps)
+    assert np.all(np.isfinite(o._rotation)) and abs(abs(float(np.dot(o._rotation, q))) - 1.0) < 1e-6
+    o.set_batchsize(3)
+    qq, tt = rows()
+    assert np.allclose(qq, qs, atol=1e-7) and np.allclose(tt, ps), "set_batchsize discarded the per-hypothesis poses"
+    with torch.no_grad():
+        o.x.add_(1.0)
+    o.reset_pose()
+    assert np.allclose(rows()[1], ps)
+    with pytest.raises(ValueError):
+        o.set_batchsize(5)
+    o.set_pose([1.0, 2.0, 3.0], list(q), batchsize=5, opencv2opengl=False)  # one pose again: any batch size
+    o.set_batchsize(7)
+    assert rows()[0].shape == (7, 4)
+
+
 def test_shard_bounds_cover_every_hypothesis_once():
     from diffdope import _dist
 
