@@ -76,8 +76,9 @@ def workload_config(n_gpus, scaling="weak"):
         "parallelism": "hypotheses sharded over %d GPU(s), one all-gather of the result table" % n_gpus,
         "l2": "flushed between timed iterations (256 MiB write outside the timed events)",
         "timed_step": "one ddope_optimize call of one iteration (pose, raster, pixel pass, step) for all hypotheses of the rank",
-        "scheduling": "3 kernels per iteration with programmatic dependent launch; hypotheses split into parts on internal streams "
-                      "(raster of one part overlaps the pixel pass of another), joined into the caller's stream",
+        "scheduling": "3 kernels per iteration with programmatic dependent launch. A call of several iterations (value_l2_warm_single_call, e2e) "
+                      "splits the hypotheses into parts on internal streams (raster of one part overlaps the pixel pass of another), joined into "
+                      "the caller's stream; a call of one iteration (the timed step) has nothing to pipeline and runs as one part: 4 launches",
     }
 
 

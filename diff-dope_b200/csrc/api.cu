@@ -46,6 +46,9 @@ struct ddope_scene {
     float* gt_edge = nullptr; // [H,W] Sobel magnitude of the target (edge loss)
     size_t gt_edge_cap = 0;
     bool gt_edge_dirty = true;
+    float4* gt_pack = nullptr;  // [H,W,2] interleaved targets of the loss window (SceneDev::gt_pack)
+    size_t gt_pack_cap = 0;
+    bool gt_pack_dirty = true;
     ddope_optim_cfg optim = {DDOPE_OPT_SGD, 0.9f, 0.999f, 1e-8f, 0};
     float* adam_state = nullptr;  // [B,14]
     int adam_cap = 0;
@@ -352,6 +355,7 @@ extern "C" int ddope_scene_create(ddope_scene** out, const float* pos, int V, co
     d.tex_levels = textured ? 1 : 0; d.tex_filter = DDOPE_TEX_LINEAR;
     for (int l = 0; l < MAX_MIP; l++) d.tex_off[l] = 0;
     d.gt_edge = nullptr;
+    d.gt_pack = nullptr;
     d.seg_bbox = s->seg_bbox;
     for (int k = 0; k < 3; k++) { d.bbmin[k] = 1e30f; d.bbmax[k] = -1e30f; }
     for (int v = 0; v < V; v++)
@@ -400,7 +404,7 @@ extern "C" int ddope_scene_set_bin_capacity(ddope_scene* s, int cap) {
 
 extern "C" int ddope_scene_destroy(ddope_scene* s) {
     if (!s) return 0;
-    cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex4); cudaFree(s->vcol); cudaFree(s->gt_edge); cudaFree(s->adam_state); cudaFree(s->tripos); cudaFree(s->tricol);
+    cudaFree(s->pos); cudaFree(s->tri); cudaFree(s->opp); cudaFree(s->uv); cudaFree(s->tex4); cudaFree(s->vcol); cudaFree(s->gt_edge); cudaFree(s->gt_pack); cudaFree(s->adam_state); cudaFree(s->tripos); cudaFree(s->tricol);
     cudaFree(s->seg_bbox); cudaFree(s->total_tiles); cudaFree(s->hyp); cudaFree(s->zbuf); cudaFree(s->partials);
     cudaFree(s->arrive);
     cudaFree(s->bin_count); cudaFree(s->bin_ids); cudaFree(s->bin_overflow);
@@ -419,6 +423,7 @@ extern "C" int ddope_scene_destroy(ddope_scene* s) {
 static void set_window(ddope_scene* s, int y0, int x0, int h, int w) {
     SceneDev& d = s->dev;
     s->gt_edge_dirty = true;
+    s->gt_pack_dirty = true;
     d.wy0 = y0; d.wx0 = x0; d.wh = h; d.ww = w;
     int zx0 = x0 - 1 < 0 ? 0 : x0 - 1, zy0 = y0 - 1 < 0 ? 0 : y0 - 1;
     int zx1 = x0 + w + 1 > d.W ? d.W : x0 + w + 1, zy1 = y0 + h + 1 > d.H ? d.H : y0 + h + 1;
@@ -433,6 +438,7 @@ extern "C" int ddope_scene_set_camera(ddope_scene* s, const float* proj16, int f
     // ddope_scene_set_target then fails loudly instead of reading memory the caller may have released)
     s->dev.gt_rgb = s->dev.gt_depth = s->dev.gt_seg = nullptr;
     s->gt_edge_dirty = true;
+    s->gt_pack_dirty = true;
     s->dev.H = frame_h; s->dev.W = frame_w;
     {   // nvdiffrast's pixel-centre mapping, in separately rounded float32 operations (same values as oracle/nvdr.py pixel_ndc)
         volatile float w = (float)frame_w, h = (float)frame_h;
@@ -461,6 +467,7 @@ extern "C" int ddope_scene_set_target(ddope_scene* s, const float* rgb, const fl
     SceneDev& d = s->dev;
     d.gt_rgb = rgb; d.gt_depth = depth; d.gt_seg = seg;
     s->gt_edge_dirty = true;
+    s->gt_pack_dirty = true;
     d.seg_pix_stride = seg ? seg_c : 0;
     d.seg_ch_stride = (seg && seg_c == 3) ? 1 : 0;  // a single-channel segmentation serves all three colour channels
     if (seg) {
@@ -597,6 +604,27 @@ static int check_loss_inputs(const ddope_scene* s, const ddope_loss_cfg* cfg, co
 }
 
 // Edge loss: the target's Sobel magnitude over the current window, recomputed when target or window changed.
+// The interleaved copy of the targets the shading pass reads (SceneDev::gt_pack), rebuilt after set_target / set_window / set_camera.
+// Like the target's edge image it is derived data: a caller that changes the CONTENTS of the target tensors in place has to call
+// ddope_scene_set_target again (include/ddope_b200.h).
+static int prepare_targets(ddope_scene* s, cudaStream_t st) {
+    SceneDev& d = s->dev;
+    const size_t need = (size_t)d.H * d.W * 2;
+    if (need > s->gt_pack_cap) {
+        if (s->gt_pack) CK(cudaFree(s->gt_pack));
+        CK(cudaMalloc(&s->gt_pack, sizeof(float4) * need));
+        s->gt_pack_cap = need;
+        s->gt_pack_dirty = true;
+    }
+    d.gt_pack = s->gt_pack;
+    if (s->gt_pack_dirty) {
+        launch_gt_pack(d, s->gt_pack, st);
+        CK(cudaGetLastError());
+        s->gt_pack_dirty = false;
+    }
+    return 0;
+}
+
 static int prepare_edge(ddope_scene* s, const ddope_loss_cfg* cfg, cudaStream_t st) {
     if (!cfg->use_edge) return 0;
     SceneDev& d = s->dev;
@@ -606,6 +634,7 @@ static int prepare_edge(ddope_scene* s, const ddope_loss_cfg* cfg, cudaStream_t 
         CK(cudaMalloc(&s->gt_edge, sizeof(float) * need));
         s->gt_edge_cap = need;
         s->gt_edge_dirty = true;
+    s->gt_pack_dirty = true;
     }
     d.gt_edge = s->gt_edge;
     if (s->gt_edge_dirty) {
@@ -905,6 +934,7 @@ extern "C" int ddope_loss_grad(ddope_scene* s, const float* quat, const float* t
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, true, st)) return r;
     if (int r = prepare_edge(s, cfg, st)) return r;
+    if (int r = prepare_targets(s, st)) return r;
     s->launches = 0;
     OptimDev opt = {0, 0.f, 0.f, 0.f, nullptr, 0.f, 0.f};
     Part parts[ddope_scene::MAX_PARTS];
@@ -933,6 +963,7 @@ extern "C" int ddope_optimize(ddope_scene* s, float* quat, float* trans, const f
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = ensure_buffers(s, B, true, st)) return r;
     if (int r = prepare_edge(s, cfg, st)) return r;
+    if (int r = prepare_targets(s, st)) return r;
     if (s->optim.kind == DDOPE_OPT_ADAM) {
         if (B > s->adam_cap) {
             if (s->optim.step0 > 0 && s->adam_state) return fail("ddope_optimize: Adam continuation (step0 > 0) with a larger batch than the stored moments");
@@ -1065,8 +1096,10 @@ extern "C" int ddope_optimize_multi(ddope_scene* const* scenes, int n_scenes, co
     s->multi_active = true;
     struct Reset { ddope_scene* s; ~Reset() { s->multi_active = false; } } reset{s};
     if (int r = ensure_buffers(s, B, true, st)) return r;
-    for (int k = 0; k < n_scenes; k++)
+    for (int k = 0; k < n_scenes; k++) {
         if (int r = prepare_edge(scenes[k], cfg, st)) return r;
+        if (int r = prepare_targets(scenes[k], st)) return r;
+    }
     if (n_scenes > s->multi_scenes_cap) {
         if (s->multi_scenes) CK(cudaFree(s->multi_scenes));
         s->multi_scenes = nullptr; s->multi_scenes_cap = 0;

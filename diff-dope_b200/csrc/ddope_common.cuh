@@ -56,6 +56,8 @@ struct SceneDev {
     const float* gt_depth;  // [H,W] or null
     const float* gt_seg;    // [H,W,seg_c] or null
     const float* gt_edge;   // [H,W] Sobel magnitude of the target's grey image, zero-padded at the loss window (edge loss) or null
+    const float4* gt_pack;  // [H,W,2]: (r, g, b, depth), (seg_r, seg_g, seg_b, 0) of the loss window's pixels -- the shading pass reads the
+                            // targets of a pixel with two 16-byte loads instead of seven scalar ones (built by prepare_targets, api.cu)
     const int* seg_bbox;    // device int[4]: xmin,ymin,xmax,ymax of seg != 0 (inclusive); xmin > xmax if none
     int V, T, tex_h, tex_w;
     int cull_sign;                   // +1 / -1: closed, consistently oriented mesh with positive / negative volume (back faces

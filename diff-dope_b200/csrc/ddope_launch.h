@@ -90,6 +90,7 @@ void launch_attr_grad(const SceneDev& S, const HypState* hyp, int B, const unsig
                       cudaStream_t st);
 void launch_tricol(const float* vcol, const int* tri, int T, float4* tricol, cudaStream_t st);
 void launch_gt_edge(const SceneDev& S, float* out, cudaStream_t st);
+void launch_gt_pack(const SceneDev& S, float4* out, cudaStream_t st);
 void launch_tex_pack(const float* tex3, size_t n, float4* out, cudaStream_t st);
 void launch_tex_mip(const float4* src, int sw, int sh, float4* dst, int dw, int dh, cudaStream_t st);
 

@@ -820,12 +820,9 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
                     const int id = s_ids[(ly + 2) * IDS_W + (lx + 2)];
                     const float maa = (nq > 0) ? s_maa[(ly + 1) * MAA_W + (lx + 1)] : ((id >= 0) ? 1.f : 0.f);
                     const size_t gpix = (size_t)y * S.W + x;
-                    float seg[3];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) seg[c] = S.gt_seg[gpix * S.seg_pix_stride + c * S.seg_ch_stride];
-                    float gt_rgb[3] = {0.f, 0.f, 0.f}, gt_d = 0.f;
-                    if (cfg.use_rgb) { gt_rgb[0] = S.gt_rgb[gpix * 3]; gt_rgb[1] = S.gt_rgb[gpix * 3 + 1]; gt_rgb[2] = S.gt_rgb[gpix * 3 + 2]; }
-                    if (cfg.use_depth) gt_d = S.gt_depth[gpix];
+                    const float4 ga = S.gt_pack[2 * gpix], gb = S.gt_pack[2 * gpix + 1];  // interleaved targets (SceneDev::gt_pack)
+                    const float seg[3] = {gb.x, gb.y, gb.z};
+                    const float gt_rgb[3] = {ga.x, ga.y, ga.z}, gt_d = ga.w;
                     float depth = -s_m2[3];
                     if (id >= 0) {
                         gtouch = true;
@@ -960,14 +957,11 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
             const size_t gpix = (size_t)y * S.W + x;
             const size_t wp = ((size_t)b * S.wh + (y - S.wy0)) * S.ww + (x - S.wx0);
             float seg[3] = {1.f, 1.f, 1.f};
-            if (MODE == MODE_LOSS && S.gt_seg) {
-#pragma unroll
-                for (int c = 0; c < 3; c++) seg[c] = S.gt_seg[gpix * S.seg_pix_stride + c * S.seg_ch_stride];
-            }
             float gt_rgb[3] = {0.f, 0.f, 0.f}, gt_d = 0.f;  // target loads issued before the dependent mesh gathers
-            if (MODE == MODE_LOSS) {
-                if (cfg.use_rgb) { gt_rgb[0] = S.gt_rgb[gpix * 3]; gt_rgb[1] = S.gt_rgb[gpix * 3 + 1]; gt_rgb[2] = S.gt_rgb[gpix * 3 + 2]; }
-                if (cfg.use_depth) gt_d = S.gt_depth[gpix];
+            if (MODE == MODE_LOSS) {  // two 16-byte loads of the interleaved copy (SceneDev::gt_pack)
+                const float4 ga = S.gt_pack[2 * gpix], gb = S.gt_pack[2 * gpix + 1];
+                gt_rgb[0] = ga.x; gt_rgb[1] = ga.y; gt_rgb[2] = ga.z; gt_d = ga.w;
+                seg[0] = gb.x; seg[1] = gb.y; seg[2] = gb.z;
             }
             float rgb[3] = {0.f, 0.f, 0.f};
             float depth = -s_m2[3];
@@ -1370,6 +1364,32 @@ __global__ void gt_edge_kernel(const float* __restrict__ rgb, int W, int wy0, in
     const float gx = ((g[2][2] - g[2][0]) + 2.f * (g[1][2] - g[1][0])) + (g[0][2] - g[0][0]);
     const float gy = ((g[2][0] - g[0][0]) + 2.f * (g[2][1] - g[0][1])) + (g[2][2] - g[0][2]);
     out[(size_t)y * W + x] = sqrtf(gx * gx + gy * gy + 1e-12f);
+}
+
+// Targets of the loss window, interleaved per pixel: (r, g, b, depth), (seg_r, seg_g, seg_b, 0). A missing rgb / depth image packs zeros
+// (its loss is then off), a missing segmentation packs ones (diffdope/diffdope.py:547-613 multiply by the mask when there is one).
+__global__ void __launch_bounds__(256) gt_pack_kernel(SceneDev S, float4* __restrict__ out) {
+    const int n = S.wh * S.ww;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int y = S.wy0 + i / S.ww, x = S.wx0 + i % S.ww;
+        const size_t g = (size_t)y * S.W + x;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(1.f, 1.f, 1.f, 0.f);
+        if (S.gt_rgb) { a.x = S.gt_rgb[g * 3]; a.y = S.gt_rgb[g * 3 + 1]; a.z = S.gt_rgb[g * 3 + 2]; }
+        if (S.gt_depth) a.w = S.gt_depth[g];
+        if (S.gt_seg) {
+            b.x = S.gt_seg[g * S.seg_pix_stride];
+            b.y = S.gt_seg[g * S.seg_pix_stride + S.seg_ch_stride];
+            b.z = S.gt_seg[g * S.seg_pix_stride + 2 * S.seg_ch_stride];
+        }
+        out[2 * g] = a;
+        out[2 * g + 1] = b;
+    }
+}
+
+void launch_gt_pack(const SceneDev& S, float4* out, cudaStream_t st) {
+    const int n = S.wh * S.ww;
+    if (n <= 0) return;
+    gt_pack_kernel<<<(n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184, 256, 0, st>>>(S, out);
 }
 
 void launch_gt_edge(const SceneDev& S, float* out, cudaStream_t st) {

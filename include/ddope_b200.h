@@ -135,7 +135,9 @@ int ddope_scene_set_camera(ddope_scene* s, const float* proj16_host, int frame_h
 /* gt_tensors (diffdope.py:1646-1651): device pointers, BORROWED (must outlive the calls that
  * use them), one image shared by all hypotheses: rgb [H,W,3], depth [H,W], seg [H,W,seg_c]
  * with seg_c = 3 (as the reference loads it) or 1 (channels identical). Any may be NULL if
- * the loss that needs it is off. Runs one small kernel (bounding box of seg != 0). */
+ * the loss that needs it is off. Runs one small kernel (bounding box of seg != 0). The next loss call derives working copies
+ * from the images (an interleaved per-pixel record of the loss window; the Sobel image for the edge loss), once: after changing the
+ * CONTENTS of the images in place, call this function again. */
 int ddope_scene_set_target(ddope_scene* s, const float* rgb_dev, const float* depth_dev,
                            const float* seg_dev, int seg_c, void* stream);
 
