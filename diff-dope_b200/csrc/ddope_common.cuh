@@ -84,7 +84,7 @@ struct __align__(16) HypState {
     int tiles_x, tiles_y, tile_base;
     float k_edge;
     int face;  // sign of the snapped window-space area of a front-facing triangle (0: rasterise both orientations)
-    int gx0, gy0, gx1, gy1;        // tile grid: 32x32 tiles from (gx0,gy0), pixels up to (gx1,gy1) exclusive (currently always the ROI)
+    int gx0, gy0, gx1, gy1;        // tile grid: 32 x tile_h_of(edge) tiles from (gx0,gy0), pixels up to (gx1,gy1) exclusive (currently always the ROI)
     int obj;                       // index into the scene table of a multi-object call (0 otherwise)
     int pad[2];
 };

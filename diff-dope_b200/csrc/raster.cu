@@ -79,7 +79,7 @@ void launch_raster(const SceneDev& S, const HypState* hyp, int B, unsigned long 
 }
 
 // Binned path, pass 1: one thread per (hypothesis, triangle) runs the same clip / snap / cull / bounding-box code as the
-// rasteriser and appends the triangle's index to the bin of every tile whose 36x36 pixel region (32x32 tile + 2 px halo, the
+// rasteriser and appends the triangle's index to the bin of every tile whose 36 x (TILE_H+4) pixel region (the tile + 2 px halo, the
 // region a tile CTA needs triangle ids for) the bounding box touches. Bins are fixed-capacity id lists addressed by the tile's
 // work-item index (tile_base + ty * tiles_x + tx); a full bin keeps counting, and its tile CTA then falls back to scanning
 // the whole mesh. The append order is arbitrary; the depth test that consumes the bins is order-independent.

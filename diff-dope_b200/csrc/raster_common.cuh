@@ -2,7 +2,7 @@
 //   raster_kernel (raster.cu): one launch over every (hypothesis, triangle), winners through 64-bit atomicMin into a global
 //                              z-buffer over the loss ROI;
 //   binned path (bin_kernel in raster.cu + the tile CTAs of pixel_kernel<..., BINNED>): triangles are first appended to the
-//                              bins of the 36x36 pixel regions (32x32 tile + 2 px halo) they touch, each tile CTA stages its bin
+//                              bins of the pixel regions (tile + 2 px halo) they touch, each tile CTA stages its bin
 //                              with TMA bulk copies and rasterises it into a z-buffer in shared memory.
 // Both run exactly this code on a triangle, so they produce the same keys (bit-equal ids, barycentrics, z/w). The raster rule
 // is the one stated in oracle/nvdr.py and DESIGN.md section 4.

@@ -67,6 +67,28 @@ def matrix_batch_44_from_position_quat(q, p):
     return torch.cat([rr, bottom], dim=1)
 
 
+def _matrix_batch_44_np(q, p):
+    """`matrix_batch_44_from_position_quat` for host float32 arrays, without autograd: the same float32 operations in the same order
+    (bit-equal, pinned in tests/test_host.py), ~20x less host time than ~60 small torch ops. Serves the lazily built 'mtx' of a result."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    p = np.ascontiguousarray(p, dtype=np.float32)
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    two, one = np.float32(2.0), np.float32(1.0)
+    m = np.zeros((q.shape[0], 4, 4), dtype=np.float32)
+    m[:, 0, 0] = one - two * y**2 - two * z**2
+    m[:, 0, 1] = two * x * y - two * z * w
+    m[:, 0, 2] = two * x * z + two * y * w
+    m[:, 1, 0] = two * x * y + two * z * w
+    m[:, 1, 1] = one - two * x**2 - two * z**2
+    m[:, 1, 2] = two * y * z - two * x * w
+    m[:, 2, 0] = two * x * z - two * y * w
+    m[:, 2, 1] = two * y * z + two * x * w
+    m[:, 2, 2] = one - two * x**2 - two * y**2
+    m[:, :3, 3] = p
+    m[:, 3, 3] = one
+    return m
+
+
 class _Quat(np.ndarray):
     """ndarray (x,y,z,w) that also answers `.matrix44` / `.matrix33` like pyrr.Quaternion."""
 
@@ -778,8 +800,8 @@ class _LazyResult(dict):
     def __missing__(self, key):
         if key == "mtx":
             ph = self._owner._pose_hist_host[self._index]
-            qn = ph[:, :4] / torch.norm(ph[:, :4], dim=-1, keepdim=True)
-            dict.__setitem__(self, "mtx", matrix_batch_44_from_position_quat(qn, ph[:, 4:]))
+            qn = ph[:, :4] / torch.norm(ph[:, :4], dim=-1, keepdim=True)  # Object3D.forward (diffdope.py:1085-1098), torch's own norm
+            dict.__setitem__(self, "mtx", torch.from_numpy(_matrix_batch_44_np(qn.numpy(), ph[:, 4:].numpy())))
             return dict.__getitem__(self, "mtx")
         if key not in ("rgb", "depth", "mask"):
             raise KeyError(key)

@@ -158,7 +158,7 @@ int ddope_mesh_orientation(const float* pos_host, int V, const int32_t* tri_host
 
 /* How ddope_loss_grad / ddope_optimize rasterise (same raster rule, bit-identical results; replaces dr.rasterize's GL draw,
  * diffdope/diffdope.py:198-200). mode 0: one launch over every (hypothesis, triangle), winners through 64-bit atomicMin into a
- * global z-buffer over the loss ROI. mode 1 ("binned"): a binning launch appends each visible triangle to the bins of the 32x32
+ * global z-buffer over the loss ROI. mode 1 ("binned"): a binning launch appends each visible triangle to the bins of the 32x16 (edge loss: 32x32)
  * pixel tiles (+ 2 px halo) it touches; each tile CTA of the pixel pass stages its bin into shared memory with TMA bulk copies
  * and rasterises it into a shared-memory z-buffer before shading -- no global z-buffer traffic, no restore pass. The default is the
  * faster one on the benchmark workload; the environment variable DDOPE_RASTER=zbuffer|binned overrides it

@@ -354,6 +354,21 @@ def test_mesh_and_object3d_follow_reference():
     assert len(list(o.parameters())) == 7
 
 
+def test_host_pose_matrix_is_bit_equal_to_the_differentiable_one():
+    """The numpy float32 builder behind the lazily made 'mtx' of a result equals matrix_batch_44_from_position_quat (itself pinned
+    bit-equal to the reference's function by the golden vectors) bit for bit, on unit and non-unit quaternions."""
+    from diffdope.diffdope import _matrix_batch_44_np, matrix_batch_44_from_position_quat
+
+    g = torch.Generator().manual_seed(7)
+    for scale in (1.0, 3.7, 1e-3):
+        q = torch.randn(257, 4, generator=g)
+        q = q / torch.norm(q, dim=-1, keepdim=True) * scale
+        p = torch.randn(257, 3, generator=g) * 50.0
+        a = matrix_batch_44_from_position_quat(q, p).numpy()
+        b = _matrix_batch_44_np(q.numpy(), p.numpy())
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+
+
 def test_per_hypothesis_start_poses_survive_refills():
     """Extension: set_pose with [B,3] / [B,4] arrays. The poses must survive set_batchsize / reset_pose (which refill the parameters),
     a batch size they do not fit must fail loudly, and the representative quaternion of (q, -q) is q, not NaN."""
