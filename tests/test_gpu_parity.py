@@ -141,6 +141,40 @@ def test_window_and_shard_divisor(ex_half):
         ex.sc.set_window(0, 0, ex.H, ex.W)
 
 
+@pytest.mark.parametrize("hw,edge", [((7, 45), False), ((16, 32), False), ((17, 33), False), ((49, 95), False), ((33, 64), True), ((31, 97), True)])
+def test_windows_that_do_not_fit_the_tile_grid(ex_half, hw, edge):
+    """The pixel pass works on 32x16 tiles (32x32 with the edge loss), 4 pixel rows per thread. Windows smaller than a tile, one row /
+    column larger than a multiple of it, and cut through the object at odd offsets: losses and gradients against the full-frame
+    oracle, image output bit-equal to the oracle's slice (ragged last tile row / column, tiles with a single live warp)."""
+    from oracle import refpath
+
+    ex = ex_half
+    c = su.centred_window(ex.gt["segmentation"], 128, ex.H, ex.W)  # 128 x 128 around the object's centre
+    win = (c[0] + 64 - hw[0] // 2 + 5, c[1] + 64 - hw[1] // 2 - 7, hw[0], hw[1])
+    losses = dict(ALL, l1_edge=True, weight_edge=0.5) if edge else ALL
+    ex.sc.set_window(*win)
+    try:
+        B = 2
+        qs, ts = su.perturbed_poses(ex.q, ex.t, B)
+        lr = su.lr_multipliers(B)
+        loss, grad = ex.sc.loss_grad(torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda(), torch.from_numpy(lr).cuda(), _cfg(ex.n, losses))
+        logged, gq, gtr, _ = refpath.forward_backward(ex.oracle_mesh(), ex.P, qs, ts, ex.gt_t(), lr, losses, ex.H, ex.W, window=win)
+        # atol: a window inside the object has a mask loss of exactly 0 here and of ~4e-9 in the oracle, which interpolates the constant 1
+        # as u + v + (1 - u - v) = 1 +- 1 ulp (DESIGN.md section 5, deliberate deviations); every other entry is O(0.1)
+        assert np.allclose(loss.cpu().numpy(), _loss_table(logged, B), rtol=1e-4, atol=1e-7)
+        go, gg = np.concatenate([gq, gtr], 1), grad.cpu().numpy()
+        assert np.abs(go).max() > 0 and np.abs(go - gg).max() <= 1e-4 * np.abs(go).max()
+        out = ex.sc.render(torch.from_numpy(qs).cuda(), torch.from_numpy(ts).cuda())
+        r = refpath.render(ex.oracle_mesh(), ex.P, torch.from_numpy(qs), torch.from_numpy(ts), ex.H, ex.W)
+        y0, x0, h, w = win
+        assert np.array_equal(r["rast_out"].numpy()[:, y0:y0 + h, x0:x0 + w, 3], out["rast"].cpu().numpy()[..., 3])
+        assert np.array_equal(r["rgb"].numpy()[:, y0:y0 + h, x0:x0 + w], out["rgb"].cpu().numpy())
+        assert np.array_equal(r["depth"].numpy()[:, y0:y0 + h, x0:x0 + w], out["depth"].cpu().numpy())
+        assert np.abs(r["mask"].numpy()[:, y0:y0 + h, x0:x0 + w, 0] - out["mask"].cpu().numpy()).max() <= 1.2e-7
+    finally:
+        ex.sc.set_window(0, 0, ex.H, ex.W)
+
+
 def test_golden_fixture():
     g = np.load(GOLDEN)
     ex = Example(float(g["resize"]))
