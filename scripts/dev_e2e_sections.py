@@ -33,4 +33,16 @@ for rep in range(6):
     if rank == 0:
         print("world %d K %d rep %d: setup %.3f | enqueue (host, async) %.3f | gpu done after %.3f | finish (gather + D2H + host tables) %.3f | argmin/pose %.3f | closing barrier %.3f | total %.3f ms"
               % (world, K, rep, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t2s - t1), 1e3 * (t3 - t2s), 1e3 * (t4 - t3), 1e3 * (t5 - t4), 1e3 * (t5 - t0)), flush=True)
+if os.environ.get("PROFILE") and rank == 0:
+    import cProfile, pstats, io
+    d.losses_values = {}; d.optimization_results = []; d.optimizer = d._make_optimizer(); d._refresh_gt()
+    st = d._fused_enqueue(); torch.cuda.synchronize()
+    pr = cProfile.Profile(); pr.enable()
+    d._fused_finish(st); best = int(d.get_argmin()); p = d.get_pose(best)
+    pr.disable()
+    s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(22); print(s.getvalue()[:4500])
+    pr = cProfile.Profile(); pr.enable()
+    d.losses_values = {}; d.optimization_results = []; d.optimizer = d._make_optimizer(); d._refresh_gt(); st = d._fused_enqueue()
+    pr.disable(); torch.cuda.synchronize()
+    s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(14); print(s.getvalue()[:3500])
 if world > 1: dist.destroy_process_group()
