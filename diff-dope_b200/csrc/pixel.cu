@@ -484,13 +484,19 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
     // warp 1 draws the NEXT item at the top of an iteration; after the phase-1 barrier (every thread has read the current item by
     // then) warp 1 locates its hypothesis and overwrites (s_item, s_bsel); the barrier that ends the iteration publishes them.
     int* work_counter = const_cast<int*>(total_tiles) + 1;  // reset to 0 by whichever kernel wrote total_tiles
-    __shared__ int s_item, s_bsel;
-    // the hypothesis owning work item `it` (one load per participating thread instead of a serial search); threads first, first + step, ...
+    __shared__ int s_item, s_bsel, s_tx, s_ty;
+    // the hypothesis owning work item `it` (one load per participating thread instead of a serial search) and the item's tile
+    // coordinates in that hypothesis's grid (one division by the thread that finds it instead of one per thread); threads first, first + step, ...
     auto locate = [&](int it, int first, int step) {
         if (it >= total) return;
         for (int bb = first; bb < B; bb += step) {
-            const int base = hyp[bb].tile_base;
-            if (it >= base && it < base + hyp[bb].tiles_x * hyp[bb].tiles_y) s_bsel = bb;
+            const int base = hyp[bb].tile_base, ntx = hyp[bb].tiles_x;
+            if (it >= base && it < base + ntx * hyp[bb].tiles_y) {
+                s_bsel = bb;
+                const int local = it - base;
+                s_ty = local / ntx;
+                s_tx = local - (local / ntx) * ntx;
+            }
         }
     };
     // warp 1 only (nx: the drawn item, valid in its lane 0)
@@ -508,6 +514,7 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
         const int item = s_item;
         if (item >= total) break;
         const int b = s_bsel;
+        const int tx = s_tx, ty = s_ty;
         int next_item = 0;
         if (tid == 32) next_item = atomicAdd(work_counter, 1);  // consumed after the phase-1 barrier
 #else
@@ -519,6 +526,7 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
         locate(item, tid, TILE_THREADS);
         __syncthreads();
         const int b = s_bsel;
+        const int tx = s_tx, ty = s_ty;
 #endif
         const HypState& h = hyp[b];
         if (MULTI) {
@@ -534,8 +542,6 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
         if (tid < 4) s_m2[tid] = h.m[8 + tid];
         const int rx0 = h.rx0, ry0 = h.ry0, rx1 = h.rx1, ry1 = h.ry1;
         const int gx1 = h.gx1, gy1 = h.gy1;  // end of the tile grid (== the ROI except for image output)
-        const int local = item - h.tile_base;
-        const int tx = local % h.tiles_x, ty = local / h.tiles_x;
         const int ox = h.gx0 + tx * TILE_W, oy = h.gy0 + ty * TILE_H;  // tile origin, frame pixels
         const float k_rgb = h.k_rgb, k_depth = h.k_depth, k_mask = h.k_mask, k_edge = h.k_edge;
         // valid z-buffer region of this hypothesis
@@ -597,54 +603,63 @@ __global__ void __launch_bounds__(tile_threads_of(EDGE), EDGE ? PIXEL_MIN_BLOCKS
             __syncthreads();
         }
 
-        // 1. triangle ids of tile + 2 px halo, one warp per row (row loads coalesce; all of a warp's
-        //    z-buffer loads are issued before any is consumed), plus per-row coverage / in-frame bitmasks
-        bool tile_cov = false, tile_unc = false;  // this warp's rows: any covered pixel / any uncovered pixel inside the frame
+        // 1. triangle ids of tile + 2 px halo, plus per-row coverage / in-frame bitmasks. One warp per row for columns 0..31 (row loads
+        //    coalesce); the four right-halo columns 32..35 of EIGHT rows share one warp pass (lane = 4 * row + column) instead of costing
+        //    every row a second, 4-lanes-of-32 pass: 6 instead of 10 passes per warp on a 16-row tile. All of a warp's z-buffer loads are
+        //    issued before any is consumed. A row's 64-bit masks are written as two 32-bit words, by whichever warps own the two parts.
+        bool tile_cov = false, tile_unc = false;  // this warp's elements: any covered pixel / any uncovered pixel inside the frame
         {
             const int lane = tid & 31, warp = tid >> 5;
             constexpr int ROWS_PER_WARP = (IDS_H + TILE_WARPS - 1) / TILE_WARPS;
-            int idr[ROWS_PER_WARP][2];
+            constexpr int HALO_PASSES = (IDS_H + 7) / 8, HALO_PER_WARP = (HALO_PASSES + TILE_WARPS - 1) / TILE_WARPS;
+            int idr[ROWS_PER_WARP], idh[HALO_PER_WARP];
             const unsigned int vw = (unsigned int)(vx1 - vx0);
-#pragma unroll
-            for (int k = 0; k < ROWS_PER_WARP; k++) {
-                const int iy = warp + TILE_WARPS * k;
-                const int y = oy - 2 + iy;
-                // row tests are warp-uniform; the column tests use one unsigned compare per range
-                const bool row_in = iy < IDS_H && (unsigned int)y < (unsigned int)S.H;
-                const bool row_z = row_in && y >= vy0 && y < vy1;
-                const unsigned long long* zrow = BINNED ? (s_u.z + iy * IDS_W - (ox - 2)) : (zb + (size_t)(y - S.zy0) * S.zw - S.zx0);
-#pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    const int ix = lane + 32 * half;
-                    const int x = ox - 2 + ix;
-                    int id = ID_OUTSIDE;
-                    if (row_in && (half == 0 || ix < IDS_W) && (unsigned int)x < (unsigned int)S.W) {
-                        id = ID_NONE;
-                        if (row_z && (unsigned int)(x - vx0) < vw) {
-                            const unsigned long long key = zrow[x];
-                            if (key != EMPTY_KEY) id = (int)(unsigned int)(key & 0xFFFFFFFFull);
-                        }
+            auto load_id = [&](int ix, int iy) -> int {
+                const int x = ox - 2 + ix, y = oy - 2 + iy;
+                int id = ID_OUTSIDE;
+                if (iy < IDS_H && (unsigned int)y < (unsigned int)S.H && (unsigned int)x < (unsigned int)S.W) {
+                    id = ID_NONE;
+                    if (y >= vy0 && y < vy1 && (unsigned int)(x - vx0) < vw) {
+                        const unsigned long long key = BINNED ? s_u.z[iy * IDS_W + ix] : zb[(size_t)(y - S.zy0) * S.zw + (x - S.zx0)];
+                        if (key != EMPTY_KEY) id = (int)(unsigned int)(key & 0xFFFFFFFFull);
                     }
-                    idr[k][half] = id;
                 }
-            }
+                return id;
+            };
+#pragma unroll
+            for (int k = 0; k < ROWS_PER_WARP; k++) idr[k] = load_id(lane, warp + TILE_WARPS * k);
+#pragma unroll
+            for (int j = 0; j < HALO_PER_WARP; j++) idh[j] = load_id(32 + (lane & 3), 8 * (warp + TILE_WARPS * j) + (lane >> 2));
             // (binned path: s_u.z is not touched again; s_alpha, the same storage, is first written in phase 3, two barriers from here)
+            unsigned int* cov32 = reinterpret_cast<unsigned int*>(s_cov);
+            unsigned int* inf32 = reinterpret_cast<unsigned int*>(s_inf);
 #pragma unroll
             for (int k = 0; k < ROWS_PER_WARP; k++) {
                 const int iy = warp + TILE_WARPS * k;
                 if (iy >= IDS_H) break;  // warp-uniform
-                const unsigned int c0 = __ballot_sync(0xffffffffu, idr[k][0] >= 0);
-                const unsigned int c1 = __ballot_sync(0xffffffffu, idr[k][1] >= 0);
-                const unsigned int f0 = __ballot_sync(0xffffffffu, idr[k][0] != ID_OUTSIDE);
-                const unsigned int f1 = __ballot_sync(0xffffffffu, idr[k][1] != ID_OUTSIDE);
-                s_ids[iy * IDS_W + lane] = idr[k][0];
-                if (lane < IDS_W - 32) s_ids[iy * IDS_W + 32 + lane] = idr[k][1];
-                if (lane == 0) {
-                    s_cov[iy] = ((unsigned long long)c1 << 32) | c0;
-                    s_inf[iy] = ((unsigned long long)f1 << 32) | f0;
+                const unsigned int c0 = __ballot_sync(0xffffffffu, idr[k] >= 0);
+                const unsigned int f0 = __ballot_sync(0xffffffffu, idr[k] != ID_OUTSIDE);
+                s_ids[iy * IDS_W + lane] = idr[k];
+                if (lane == 0) { cov32[2 * iy] = c0; inf32[2 * iy] = f0; }
+                tile_cov |= c0 != 0u;
+                tile_unc |= (f0 & ~c0) != 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < HALO_PER_WARP; j++) {
+                const int pass = warp + TILE_WARPS * j;
+                if (pass >= HALO_PASSES) break;  // warp-uniform
+                const unsigned int ch = __ballot_sync(0xffffffffu, idh[j] >= 0);
+                const unsigned int fh = __ballot_sync(0xffffffffu, idh[j] != ID_OUTSIDE);
+                const int iy = 8 * pass + (lane >> 2);
+                if (iy < IDS_H) {
+                    s_ids[iy * IDS_W + 32 + (lane & 3)] = idh[j];
+                    if ((lane & 3) == 0) {
+                        cov32[2 * iy + 1] = (ch >> (lane & 28)) & 0xFu;
+                        inf32[2 * iy + 1] = (fh >> (lane & 28)) & 0xFu;
+                    }
                 }
-                tile_cov |= (c0 | c1) != 0u;
-                tile_unc |= ((f0 & ~c0) | (f1 & ~c1)) != 0u;
+                tile_cov |= ch != 0u;
+                tile_unc |= (fh & ~ch) != 0u;
             }
         }
         // The barrier that publishes the ids. The 8-warp (edge loss) variant learns whether the tile holds covered AND uncovered pixels, i.e. whether it can have
