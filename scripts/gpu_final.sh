@@ -7,4 +7,4 @@ rm -f gpurun_out/parity_measured.jsonl
 echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
 tail -4 gpurun_out/${TAG}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-SKIP_BENCH= bash scripts/gpu_r2l.sh ${TAG}
+SKIP_BENCH= bash scripts/gpu_evidence.sh ${TAG}
