@@ -12,9 +12,9 @@ done
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29713 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/${TAG}_bench2_cfgs.json 2> gpurun_out/${TAG}_bench2_cfgs.err
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29715 bench.py --gpus 2 --steps 20 --warmup 3 --scaling strong > gpurun_out/${TAG}_bench2_strong.json 2> gpurun_out/${TAG}_bench2_strong.err
 tail -8 gpurun_out/${TAG}_pytest.log
-python - <<'PY'
+python - <<PY
 import json, glob
-for f in sorted(glob.glob('gpurun_out/r2i_bench*.json')):
+for f in sorted(glob.glob('gpurun_out/' + "${TAG}" + '_bench*.json')):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, 'N', d['n_gpus'], 'K', d['steps'], 'value %.0f' % d['value'], 'hot %.0f' % d['value_l2_warm_single_call'], 'e2e', d['e2e'].get('value'), d['e2e'].get('ms_per_step'), d['e2e'].get('multi_gpu_check'), d['e2e'].get('error'))
