@@ -29,6 +29,7 @@ import numpy as np
 import torch
 
 from . import _native
+from ._obj import load_obj
 from ._ply import load_ply
 from ._quat import opencv_2_opengl as _opencv_2_opengl_np
 from ._quat import quat_to_matrix33, rotation_to_quat
@@ -473,14 +474,20 @@ class Camera:
 
 
 class Mesh(torch.nn.Module):
-    """Mesh arrays as torch tensors (`diffdope/diffdope.py:746-935`). Loaded with the in-repo PLY
-    reader; one copy of every array is kept and batch dimensions are `expand` views."""
+    """Mesh arrays as torch tensors (`diffdope/diffdope.py:746-935`). Loaded with the in-repo PLY / Wavefront OBJ
+    readers (the reference goes through trimesh); one copy of every array is kept and batch dimensions are `expand` views."""
 
     def __init__(self, path_model, scale):
         super().__init__()
         self.path_model = path_model
         self.to_process = ["pos", "pos_idx", "vtx_color", "tex", "uv", "uv_idx", "vtx_normals"]
-        ply = load_ply(self.path_model)
+        ext = os.path.splitext(str(self.path_model))[1].lower()
+        if ext == ".obj":
+            ply = load_obj(self.path_model)
+        elif ext == ".ply":
+            ply = load_ply(self.path_model)
+        else:
+            raise ValueError("%s: unsupported mesh format %r (PLY and Wavefront OBJ are read; convert glb / stl / ... first)" % (self.path_model, ext))
         pos = torch.from_numpy(ply.vertices.astype(np.float32)) * scale
         self._pos = pos
         self._pos_idx = torch.from_numpy(ply.faces.astype(np.int32))

@@ -354,6 +354,60 @@ def test_mesh_and_object3d_follow_reference():
     assert len(list(o.parameters())) == 7
 
 
+def test_obj_reader_matches_the_ply_reader_and_handles_seams(tmp_path):
+    """Wavefront OBJ (what trimesh.load serves the reference for .obj models): the example mesh rewritten as OBJ + MTL loads to the
+    arrays the PLY gives; a hand-written file covers separate v / vt indices (uv seam -> duplicated vertex), a quad, negative
+    indices, `v//vn` corners and an untextured file with vertex colours; other extensions fail with a clear message."""
+    import cv2
+
+    import diffdope as dd
+    from diffdope._obj import load_obj
+    from diffdope._ply import load_ply
+
+    src = os.path.join(su.DATA, "mesh", "AlphabetSoup.ply")
+    ply = load_ply(src)
+    obj = tmp_path / "soup.obj"
+    with open(obj, "w") as f:
+        f.write("mtllib soup.mtl\nusemtl m0\n")
+        for v in ply.vertices:
+            f.write("v %r %r %r\n" % tuple(float(x) for x in v))
+        for t in ply.uv:
+            f.write("vt %r %r\n" % tuple(float(x) for x in t))
+        for a, b, c in ply.faces:
+            f.write("f %d/%d %d/%d %d/%d\n" % (a + 1, a + 1, b + 1, b + 1, c + 1, c + 1))
+    (tmp_path / "soup.mtl").write_text("newmtl m0\nKd 1 1 1\nmap_Kd -clamp on %s\n" % os.path.join(su.DATA, "mesh", "AlphabetSoup.png"))
+    o = load_obj(str(obj))
+    # every vertex of the example is used by a face, but not in index order: compare through the faces
+    assert o.faces.shape == ply.faces.shape
+    assert np.array_equal(o.vertices[o.faces], ply.vertices[ply.faces]) and np.array_equal(o.uv[o.faces], ply.uv[ply.faces])
+    assert np.array_equal(o.texture_image, ply.texture_image)
+    m_obj, m_ply = dd.Mesh(str(obj), scale=0.01), dd.Mesh(src, scale=0.01)
+    assert m_obj.has_textured_map and torch.equal(m_obj.tex, m_ply.tex)
+    assert torch.equal(m_obj.pos[m_obj.pos_idx.long()], m_ply.pos[m_ply.pos_idx.long()]) and torch.equal(m_obj.uv[m_obj.uv_idx.long()], m_ply.uv[m_ply.pos_idx.long()])
+
+    tex = tmp_path / "t.png"
+    cv2.imwrite(str(tex), np.arange(4 * 4 * 3, dtype=np.uint8).reshape(4, 4, 3))
+    (tmp_path / "q.mtl").write_text("newmtl skin\nmap_Kd t.png\n")
+    (tmp_path / "q.obj").write_text(
+        "# a quad and a triangle sharing an edge, the shared corners with different uv on the two faces\n"
+        "mtllib q.mtl\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 2 0 0\n"
+        "vt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvt 0.5 0.5\nvt 0.25 0.75\nvn 0 0 1\n"
+        "usemtl skin\nf 1/1/1 2/2/1 3/3/1 4/4/1\nf -4/5/1 -1/6/1 3/3/1\n")
+    q = load_obj(str(tmp_path / "q.obj"))
+    assert q.faces.tolist() == [[0, 1, 2], [0, 2, 3], [4, 5, 2]], "fan triangulation, corners re-indexed in order of first appearance"
+    assert q.vertices.shape == (6, 3) and np.array_equal(q.vertices[4], [1, 0, 0]) and np.array_equal(q.vertices[5], [2, 0, 0])
+    assert np.array_equal(q.uv[4], [0.5, 0.5]) and np.array_equal(q.uv[1], [1, 0]) and np.array_equal(q.vertex_normals[5], [0, 0, 1])
+    assert q.texture_image.shape == (4, 4, 3) and q.texture_image[0, 0].tolist() == [2, 1, 0], "RGB, row 0 = top row of the file"
+
+    (tmp_path / "c.obj").write_text("v 0 0 0 1 0 0\nv 1 0 0 0 1 0\nv 0 1 0 0 0 1\nvn 0 0 1\nf 1//1 2//1 3//1\n")
+    c = load_obj(str(tmp_path / "c.obj"))
+    assert c.uv is None and c.faces.tolist() == [[0, 1, 2]] and c.vertex_colors.tolist() == [[255, 0, 0], [0, 255, 0], [0, 0, 255]]
+    mc = dd.Mesh(str(tmp_path / "c.obj"), scale=1.0)
+    assert not mc.has_textured_map and tuple(mc.vtx_color.shape) == (3, 3)
+    with pytest.raises(ValueError, match="unsupported mesh format"):
+        dd.Mesh(str(tmp_path / "model.glb"), scale=1.0)
+
+
 def test_host_pose_matrix_is_bit_equal_to_the_differentiable_one():
     """The numpy float32 builder behind the lazily made 'mtx' of a result equals matrix_batch_44_from_position_quat (itself pinned
     bit-equal to the reference's function by the golden vectors) bit for bit, on unit and non-unit quaternions."""
