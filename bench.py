@@ -226,7 +226,7 @@ def run_reference_arm(args):
     ref = CpuReference(sample_hyp, threads)
     for _ in range(min(args.warmup, 1)):
         ref.iterate(1)
-    steps = max(1, min(args.steps, 10))  # bounded (~15 s of CPU work): each step is one iteration of a 2-hypothesis sample
+    steps = max(1, min(args.steps, 25))  # bounded (~1.5 s of CPU work per step, <= 40 s): each step is one iteration of a 2-hypothesis sample
     dt = sum(ref.iterate(1) for _ in range(steps))
     value = sample_hyp * steps / dt
     sample = ("%d hypotheses x 1 iteration per step of the bench workload (full 1920x1080 frame rendered as the reference "
