@@ -248,10 +248,12 @@ int ddope_optimize_multi(ddope_scene* const* scenes, int n_scenes, const int32_t
                          float* quat_dev, float* trans_dev, const float* lr_mult_dev, int B, const float* lr_sched_host, int n_iters,
                          const ddope_loss_cfg* cfg, float* pose_hist_dev, float* loss_hist_dev, void* stream);
 
-/* Streams: ddope_loss_grad / ddope_optimize order all their work on `stream`. For 8 or more hypotheses they fork
- * two to four internal streams from it (event wait), run one contiguous part of the hypotheses on each -- the
- * issue-bound raster kernel of one part overlaps the latency-bound pixel kernel of another -- and join them back
- * into `stream` before returning; the caller sees ordinary stream semantics and bit-identical results. */
+/* Streams: ddope_loss_grad / ddope_optimize order all their work on `stream`. ddope_optimize with 8 or more hypotheses and more
+ * than one iteration forks two to four internal streams from it (event wait), runs one contiguous part of the hypotheses on each --
+ * the issue-bound raster kernel of one part overlaps the latency-bound pixel kernel of another -- and joins them back into `stream`
+ * before returning; the caller sees ordinary stream semantics and bit-identical results. A single iteration (ddope_loss_grad,
+ * n_iters = 1) has nothing to pipeline and runs as one part. ddope_render* fork two internal streams the same way (background fill
+ * beside rasteriser + pixel pass). */
 
 /* Small batches (fewer than 8 hypotheses, one part), opt-in: with ddope_scene_set_graph(s, 1) or DDOPE_GRAPH=1, ddope_optimize
  * captures its 1 + 3 n_iters launches into a CUDA graph on an internal stream (programmatic-dependent-launch edges kept), keeps the
